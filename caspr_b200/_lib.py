@@ -1,0 +1,82 @@
+"""ctypes binding of libcaspr_b200.so (the C ABI declared in include/caspr_b200.h).
+
+The product path has NO fallback: if the library is missing, importing this module raises and
+every model call fails loudly.  Build it with ``python -m caspr_b200.build`` (or
+``__graft_entry__.build()``).
+"""
+import ctypes
+import os
+from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_size_t,
+                    c_void_p)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libcaspr_b200.so')
+
+
+class CasprError(RuntimeError):
+    def __init__(self, status, where):
+        self.status = status
+        super().__init__('%s failed: %s (status %d)' % (where, status_string(status), status))
+
+
+class CnfWeights(Structure):
+    _fields_ = [('W', c_void_p * 4), ('b', c_void_p * 4), ('Wgate', c_void_p * 4),
+                ('bgate', c_void_p * 4), ('Wbias', c_void_p * 4), ('hidden', c_int),
+                ('ctx_dim', c_int)]
+
+
+class MbnParams(Structure):
+    _fields_ = [('weight', c_void_p), ('bias', c_void_p), ('running_mean', c_void_p),
+                ('running_var', c_void_p)]
+
+
+# name -> (restype, argtypes); mirrors include/caspr_b200.h one to one
+_P = c_void_p
+SIGNATURES = {
+    'caspr_version': (c_int, []),
+    'caspr_build_arch': (c_char_p, []),
+    'caspr_status_string': (c_char_p, [c_int]),
+    'caspr_fps': (c_int, [_P, c_int, c_int, c_int, _P, _P, _P]),
+    'caspr_ball_query2': (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_int, _P, c_float, c_int, _P, _P]),
+    'caspr_group_points': (c_int, [_P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P]),
+    'caspr_three_nn': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P]),
+    'caspr_three_interp_concat': (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
+                                          _P, c_int, _P]),
+    'caspr_linear': (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    'caspr_groupnorm': (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_float, c_int, c_int, _P,
+                                c_int, _P, _P]),
+    'caspr_augment_xyz': (c_int, [_P, c_int, _P, _P]),
+    'caspr_strip_time': (c_int, [_P, c_int, _P, _P]),
+    'caspr_broadcast_rows': (c_int, [_P, c_int, c_int, c_int, c_int, _P, c_int, _P]),
+    'caspr_latent_ode_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'caspr_latent_ode_solve': (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P,
+                                       POINTER(c_double), c_int, c_float, c_float, _P, _P,
+                                       POINTER(c_int32), _P, c_size_t, _P]),
+    'caspr_cnf_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    'caspr_cnf_flow': (c_int, [_P, _P, _P, _P, c_int, c_int, POINTER(CnfWeights), POINTER(MbnParams),
+                               POINTER(MbnParams), c_float, c_int, c_float, c_float, c_int, _P, _P, _P,
+                               POINTER(c_int32), _P, c_size_t, _P]),
+    'caspr_cnf_feval': (c_int, [_P, _P, _P, c_int, c_int, POINTER(CnfWeights), c_float, c_int, _P, _P,
+                                _P, c_size_t, _P]),
+    'caspr_chamfer': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P]),
+}
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        'libcaspr_b200.so not found at %s.  caspr_b200 has no CPU or PyTorch fallback: build the '
+        'CUDA library first with `python -m caspr_b200.build`.' % LIB_PATH)
+
+lib = ctypes.CDLL(LIB_PATH)
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)          # AttributeError here = header / library out of sync
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def status_string(status):
+    return lib.caspr_status_string(int(status)).decode()
+
+
+def check(status, where):
+    if status != 0:
+        raise CasprError(status, where)

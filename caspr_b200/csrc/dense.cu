@@ -1,0 +1,394 @@
+// Dense per-point building blocks of the TPointNet++ encoder in fp32 SIMT:
+// 1x1-conv / Linear (row-major "rows x channels" GEMM with strided operands so that concat
+// buffers are written in place), GroupNorm over row-blocks with fused ReLU / max-pool, and a
+// few layout kernels.  Replaces the torch Conv1d/GroupNorm/ReLU/max calls of
+// caspr/models/pointnet2.py:637-642,677-699,471-481,207-212, pointnet.py:27-46 and
+// tpointnet2.py:59-62,99-112.  The tensor-core (tcgen05) variant of the GEMM lives in
+// gemm_tc.cu; this file is the exact-fp32 engine and the fallback-free baseline it is
+// validated against.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == CASPR_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == CASPR_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+  return v;
+}
+
+// ---------------------------------------------------------------------------- linear
+// Y[r, n] = act_out(sum_k act_in(X[r,k]) * W[n,k] + bias[n]).
+// 256 threads as 16x16; CTA tile BM x BN, k-slab 16; thread tile TM x TN with
+// TM = BM/16, TN = BN/16.  Operands are staged k-major in shared memory so the inner loop
+// reads are conflict-free broadcasts.
+template <int BM, int BN>
+__global__ void __launch_bounds__(256)
+linear_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
+              const float* __restrict__ bias, float* __restrict__ Y, int ldy, int rows, int Cin,
+              int Cout, int act_in, int act_out) {
+  constexpr int BK = 16;
+  constexpr int TM = BM / 16, TN = BN / 16;
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const long long row0 = (long long)blockIdx.x * BM;
+  const int col0 = blockIdx.y * BN;
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  // loader mapping: each thread loads A elements (r = tid/16 + 16*i, k = tid%16)
+  constexpr int A_PER_T = BM * BK / 256;
+  constexpr int B_PER_T = BN * BK / 256;
+  float ra[A_PER_T], rb[B_PER_T];
+  const int lk = tid & 15, lr = tid >> 4;
+
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < A_PER_T; ++i) {
+      long long r = row0 + lr + 16 * i;
+      int k = k0 + lk;
+      float v = 0.f;
+      if (r < rows && k < Cin) v = X[r * ldx + k];
+      if (act_in == CASPR_ACT_RELU) v = fmaxf(v, 0.f);
+      ra[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < B_PER_T; ++i) {
+      int n = col0 + lr + 16 * i;
+      int k = k0 + lk;
+      rb[i] = (n < Cout && k < Cin) ? W[(long long)n * ldw + k] : 0.f;
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < A_PER_T; ++i) As[buf][lk][lr + 16 * i] = ra[i];
+#pragma unroll
+    for (int i = 0; i < B_PER_T; ++i) Bs[buf][lk][lr + 16 * i] = rb[i];
+  };
+
+  // thread (tx,ty) owns rows  (i/4)*64 + ty*4 + i%4  and columns colmap(j): groups of four
+  // consecutive elements per thread so the shared-memory reads are conflict-free LDS.128.
+  auto colmap = [&](int j) { return TN >= 4 ? (j / 4) * 64 + tx * 4 + (j & 3) : tx * TN + j; };
+  auto rowmap = [&](int i) { return (i / 4) * 64 + ty * 4 + (i & 3); };
+
+  const int nk = (Cin + BK - 1) / BK;
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tiles((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[TM], bfrag[TN];
+#pragma unroll
+      for (int i4 = 0; i4 < TM / 4; ++i4) {
+        float4 v = *reinterpret_cast<const float4*>(&As[buf][k][i4 * 64 + ty * 4]);
+        a[i4 * 4 + 0] = v.x; a[i4 * 4 + 1] = v.y; a[i4 * 4 + 2] = v.z; a[i4 * 4 + 3] = v.w;
+      }
+      if constexpr (TN >= 4) {
+#pragma unroll
+        for (int j4 = 0; j4 < TN / 4; ++j4) {
+          float4 v = *reinterpret_cast<const float4*>(&Bs[buf][k][j4 * 64 + tx * 4]);
+          bfrag[j4 * 4 + 0] = v.x; bfrag[j4 * 4 + 1] = v.y; bfrag[j4 * 4 + 2] = v.z; bfrag[j4 * 4 + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < TN; ++j) bfrag[j] = Bs[buf][k][tx * TN + j];
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bfrag[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    long long r = row0 + rowmap(i);
+    if (r >= rows) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int n = col0 + colmap(j);
+      if (n >= Cout) continue;
+      float v = acc[i][j] + (bias ? bias[n] : 0.f);
+      Y[r * ldy + n] = apply_act(v, act_out);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------- GroupNorm
+// Small samples (one CTA per sample, whole sample staged in shared memory): the per-ball
+// GroupNorm of the set-abstraction MLPs (pointnet2.py:642 on (B'*M, C, ns)).
+__global__ void __launch_bounds__(256)
+groupnorm_small_kernel(float* __restrict__ X, int ldx, int rows_per_sample, int C, int groups,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                       int relu, int write_back, float* __restrict__ maxout, int ld_max) {
+  extern __shared__ float tile[];                 // rows_per_sample x C
+  __shared__ float s_mean[64], s_rstd[64];
+  const int sample = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int R = rows_per_sample;
+  float* base = X + (size_t)sample * R * ldx;
+  for (int i = tid; i < R * C; i += 256) {
+    int r = i / C, c = i - r * C;
+    tile[i] = base[(size_t)r * ldx + c];
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  const int gsz = cpg * R;
+  for (int g = warp; g < groups; g += 8) {
+    float s = 0.f;
+    for (int i = lane; i < gsz; i += 32) {
+      int r = i / cpg, c = g * cpg + (i - r * cpg);
+      s += tile[r * C + c];
+    }
+    s = warp_sum(s);
+    const float mean = s / (float)gsz;
+    float v = 0.f;
+    for (int i = lane; i < gsz; i += 32) {
+      int r = i / cpg, c = g * cpg + (i - r * cpg);
+      float d = tile[r * C + c] - mean;
+      v += d * d;
+    }
+    v = warp_sum(v);
+    if (lane == 0) {
+      s_mean[g] = mean;
+      s_rstd[g] = 1.0f / sqrtf(v / (float)gsz + eps);
+    }
+  }
+  __syncthreads();
+  if (write_back) {
+    for (int i = tid; i < R * C; i += 256) {
+      int r = i / C, c = i - r * C;
+      int g = c / cpg;
+      float v = (tile[i] - s_mean[g]) * s_rstd[g] * gamma[c] + beta[c];
+      if (relu) v = fmaxf(v, 0.f);
+      base[(size_t)r * ldx + c] = v;
+    }
+  }
+  if (maxout) {
+    for (int c = tid; c < C; c += 256) {
+      int g = c / cpg;
+      const float mu = s_mean[g], rs = s_rstd[g], ga = gamma[c], be = beta[c];
+      float m = -3.0e38f;
+      for (int r = 0; r < R; ++r) {
+        float v = (tile[r * C + c] - mu) * rs * ga + be;
+        if (relu) v = fmaxf(v, 0.f);
+        m = fmaxf(m, v);
+      }
+      maxout[(size_t)sample * ld_max + c] = m;
+    }
+  }
+}
+
+// Large samples: pass 1 accumulates per-(sample, group) sum / sum of squares in fp64,
+// pass 2 normalises (and max-pools through ordered-uint atomics).
+constexpr int kGnRowsPerCta = 64;
+
+__global__ void __launch_bounds__(256)
+groupnorm_stats_kernel(const float* __restrict__ X, int ldx, int rows_per_sample, int C, int groups,
+                       double* __restrict__ stats) {
+  const int sample = blockIdx.y;
+  const int r0 = blockIdx.x * kGnRowsPerCta;
+  const int r1 = min(rows_per_sample, r0 + kGnRowsPerCta);
+  const int cpg = C / groups;
+  const float* base = X + (size_t)sample * rows_per_sample * ldx;
+  __shared__ double sh_s[64], sh_q[64];
+  for (int g = threadIdx.x; g < groups; g += 256) { sh_s[g] = 0.0; sh_q[g] = 0.0; }
+  __syncthreads();
+  // thread owns a fixed channel stripe so its group index is constant per c
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float s = 0.f, q = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      float v = base[(size_t)r * ldx + c];
+      s += v;
+      q = fmaf(v, v, q);
+    }
+    atomicAdd(&sh_s[c / cpg], (double)s);
+    atomicAdd(&sh_q[c / cpg], (double)q);
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < groups; g += 256) {
+    atomicAdd(&stats[((size_t)sample * groups + g) * 2 + 0], sh_s[g]);
+    atomicAdd(&stats[((size_t)sample * groups + g) * 2 + 1], sh_q[g]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+groupnorm_apply_kernel(float* __restrict__ X, int ldx, int rows_per_sample, int C, int groups,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                       int relu, int write_back, const double* __restrict__ stats,
+                       unsigned* __restrict__ maxout_ordered, int ld_max) {
+  const int sample = blockIdx.y;
+  const int r0 = blockIdx.x * kGnRowsPerCta;
+  const int r1 = min(rows_per_sample, r0 + kGnRowsPerCta);
+  const int cpg = C / groups;
+  const double cnt = (double)cpg * (double)rows_per_sample;
+  float* base = X + (size_t)sample * rows_per_sample * ldx;
+  __shared__ float s_mean[64], s_rstd[64];
+  for (int g = threadIdx.x; g < groups; g += 256) {
+    double s = stats[((size_t)sample * groups + g) * 2 + 0];
+    double q = stats[((size_t)sample * groups + g) * 2 + 1];
+    double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[g] = (float)mean;
+    s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const int g = c / cpg;
+    const float mu = s_mean[g], rs = s_rstd[g], ga = gamma[c], be = beta[c];
+    float m = -3.0e38f;
+    for (int r = r0; r < r1; ++r) {
+      float v = (base[(size_t)r * ldx + c] - mu) * rs * ga + be;
+      if (relu) v = fmaxf(v, 0.f);
+      if (write_back) base[(size_t)r * ldx + c] = v;
+      m = fmaxf(m, v);
+    }
+    if (maxout_ordered) atomicMax(&maxout_ordered[(size_t)sample * ld_max + c], float_to_ordered(m));
+  }
+}
+
+__global__ void fill_u32_kernel(unsigned* p, int samples, int C, int ld, unsigned v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < samples * C) p[(size_t)(i / C) * ld + (i % C)] = v;
+}
+__global__ void decode_ordered_kernel(unsigned* p, int samples, int C, int ld) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < samples * C) {
+    size_t o = (size_t)(i / C) * ld + (i % C);
+    reinterpret_cast<float*>(p)[o] = ordered_to_float(p[o]);
+  }
+}
+
+// ----------------------------------------------------------------------- layout ops
+__global__ void augment_xyz_kernel(const float* __restrict__ x4, int rows, float* __restrict__ out9) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float4 p = reinterpret_cast<const float4*>(x4)[r];
+  float* o = out9 + (size_t)r * 9;
+  o[0] = p.x; o[1] = p.y; o[2] = p.z;
+  o[3] = __fmul_rn(p.x, p.x); o[4] = __fmul_rn(p.y, p.y); o[5] = __fmul_rn(p.z, p.z);
+  o[6] = __fmul_rn(p.x, p.z); o[7] = __fmul_rn(p.x, p.y); o[8] = __fmul_rn(p.z, p.y);
+}
+__global__ void strip_time_kernel(const float* __restrict__ x4, int rows, float* __restrict__ xyz3) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float4 p = reinterpret_cast<const float4*>(x4)[r];
+  float* o = xyz3 + (size_t)r * 3;
+  o[0] = p.x; o[1] = p.y; o[2] = p.z;
+}
+__global__ void broadcast_rows_kernel(const float* __restrict__ src, int ld_src, int rows_per_sample,
+                                      int C, long long total, float* __restrict__ dst, int ld_dst) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    long long row = i / C;
+    int c = (int)(i - row * C);
+    long long s = row / rows_per_sample;
+    dst[row * ld_dst + c] = src[s * ld_src + c];
+  }
+}
+
+}  // namespace
+
+extern "C" int caspr_linear(const float* X, int ldx, const float* W, int ldw, const float* bias,
+                            float* Y, int ldy, int rows, int Cin, int Cout, int act_in, int act_out,
+                            void* stream) {
+  CASPR_REQUIRE(X && W && Y && rows > 0 && Cin > 0 && Cout > 0);
+  CASPR_REQUIRE(ldx >= Cin && ldw >= Cin && ldy >= Cout);
+  CASPR_REQUIRE(act_in == CASPR_ACT_NONE || act_in == CASPR_ACT_RELU);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (Cout > 64) {
+    dim3 grid(ceil_div(rows, 128), ceil_div(Cout, 128));
+    linear_kernel<128, 128><<<grid, 256, 0, s>>>(X, ldx, W, ldw, bias, Y, ldy, rows, Cin, Cout, act_in, act_out);
+  } else if (Cout > 32) {
+    dim3 grid(ceil_div(rows, 128), ceil_div(Cout, 64));
+    linear_kernel<128, 64><<<grid, 256, 0, s>>>(X, ldx, W, ldw, bias, Y, ldy, rows, Cin, Cout, act_in, act_out);
+  } else if (Cout > 16) {
+    dim3 grid(ceil_div(rows, 128), ceil_div(Cout, 32));
+    linear_kernel<128, 32><<<grid, 256, 0, s>>>(X, ldx, W, ldw, bias, Y, ldy, rows, Cin, Cout, act_in, act_out);
+  } else {
+    dim3 grid(ceil_div(rows, 128), 1);
+    linear_kernel<128, 16><<<grid, 256, 0, s>>>(X, ldx, W, ldw, bias, Y, ldy, rows, Cin, Cout, act_in, act_out);
+  }
+  CASPR_CHECK_LAUNCH();
+  return CASPR_OK;
+}
+
+extern "C" int caspr_groupnorm(float* X, int ldx, int samples, int rows_per_sample, int C, int groups,
+                               const float* gamma, const float* beta, float eps, int relu,
+                               int write_back, float* maxout, int ld_max, double* stats_ws,
+                               void* stream) {
+  CASPR_REQUIRE(X && gamma && beta && samples > 0 && rows_per_sample > 0 && C > 0);
+  CASPR_REQUIRE(groups > 0 && groups <= 64 && C % groups == 0 && ldx >= C);
+  CASPR_REQUIRE(write_back || maxout);
+  CASPR_REQUIRE(!maxout || ld_max >= C);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t tile_bytes = (size_t)rows_per_sample * C * sizeof(float);
+  if (rows_per_sample <= 64 && tile_bytes <= 96 * 1024) {
+    if (tile_bytes > 48 * 1024) {
+      if (cudaFuncSetAttribute(groupnorm_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               96 * 1024) != cudaSuccess)
+        return CASPR_EINVAL;
+    }
+    groupnorm_small_kernel<<<samples, 256, tile_bytes, s>>>(X, ldx, rows_per_sample, C, groups, gamma,
+                                                            beta, eps, relu, write_back, maxout, ld_max);
+    CASPR_CHECK_LAUNCH();
+    return CASPR_OK;
+  }
+  CASPR_REQUIRE(stats_ws != nullptr);
+  if (cudaMemsetAsync(stats_ws, 0, (size_t)samples * groups * 2 * sizeof(double), s) != cudaSuccess)
+    return CASPR_ELAUNCH;
+  dim3 grid(ceil_div(rows_per_sample, kGnRowsPerCta), samples);
+  groupnorm_stats_kernel<<<grid, 256, 0, s>>>(X, ldx, rows_per_sample, C, groups, stats_ws);
+  CASPR_CHECK_LAUNCH();
+  unsigned* mo = reinterpret_cast<unsigned*>(maxout);
+  if (mo) {
+    fill_u32_kernel<<<ceil_div(samples * C, 256), 256, 0, s>>>(mo, samples, C, ld_max, 0u);
+    CASPR_CHECK_LAUNCH();
+  }
+  groupnorm_apply_kernel<<<grid, 256, 0, s>>>(X, ldx, rows_per_sample, C, groups, gamma, beta, eps, relu,
+                                             write_back, stats_ws, mo, ld_max);
+  CASPR_CHECK_LAUNCH();
+  if (mo) {
+    decode_ordered_kernel<<<ceil_div(samples * C, 256), 256, 0, s>>>(mo, samples, C, ld_max);
+    CASPR_CHECK_LAUNCH();
+  }
+  return CASPR_OK;
+}
+
+extern "C" int caspr_augment_xyz(const float* x4, int rows, float* out9, void* stream) {
+  CASPR_REQUIRE(x4 && out9 && rows > 0 && ((uintptr_t)x4 & 15) == 0);
+  augment_xyz_kernel<<<ceil_div(rows, 256), 256, 0, (cudaStream_t)stream>>>(x4, rows, out9);
+  CASPR_CHECK_LAUNCH();
+  return CASPR_OK;
+}
+
+extern "C" int caspr_strip_time(const float* x4, int rows, float* xyz3, void* stream) {
+  CASPR_REQUIRE(x4 && xyz3 && rows > 0 && ((uintptr_t)x4 & 15) == 0);
+  strip_time_kernel<<<ceil_div(rows, 256), 256, 0, (cudaStream_t)stream>>>(x4, rows, xyz3);
+  CASPR_CHECK_LAUNCH();
+  return CASPR_OK;
+}
+
+extern "C" int caspr_broadcast_rows(const float* src, int ld_src, int samples, int rows_per_sample,
+                                    int C, float* dst, int ld_dst, void* stream) {
+  CASPR_REQUIRE(src && dst && samples > 0 && rows_per_sample > 0 && C > 0 && ld_src >= C && ld_dst >= C);
+  long long total = (long long)samples * rows_per_sample * C;
+  int blocks = (int)((total + 255) / 256 < 148LL * 32 ? (total + 255) / 256 : 148LL * 32);
+  broadcast_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, ld_src, rows_per_sample, C, total,
+                                                                   dst, ld_dst);
+  CASPR_CHECK_LAUNCH();
+  return CASPR_OK;
+}

@@ -1,0 +1,301 @@
+"""Torch-tensor front-ends of the C-ABI entry points (include/caspr_b200.h).
+
+Every function takes CUDA fp32 / int32 tensors, allocates outputs with torch (the library
+never allocates), enqueues on torch's current stream and raises ``CasprError`` on a non-zero
+status.  Activations are "rows x channels" (channels-last); a tensor's row stride is passed
+as the leading dimension, so column slices of a wider buffer can be read and written in
+place (that is how the concat buffers of the encoder are filled without copies).
+
+These replace the Kaolin ops bound at reference caspr/models/pointnet2.py:7-10, the torch
+Conv1d/GroupNorm calls around them, and torchdiffeq's odeint (latent_ode_model.py:98,
+cnf.py:102-119).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+CNF_SIMT_FP32, CNF_TC_FP16X3 = 0, 1
+
+# kernels launched through this module since the last reset (bench.py's gpu_launches claim is
+# derived from the per-entry-point launch counts documented in DESIGN.md)
+CALLS = {}
+
+
+def _count(name):
+    CALLS[name] = CALLS.get(name, 0) + 1
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _f32(t, name):
+    if not (t.is_cuda and t.dtype == torch.float32):
+        raise TypeError('%s must be a CUDA float32 tensor, got %s on %s' % (name, t.dtype, t.device))
+    return t
+
+
+def _rows2d(t, name):
+    """(rows, C) view requirements: unit stride along channels; returns (tensor, ld)."""
+    _f32(t, name)
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError('%s must be 2-D with unit channel stride' % name)
+    return t, t.stride(0)
+
+
+# ------------------------------------------------------------------------------- geometry
+def fps(xyz, m):
+    """furthest_point_sampling + gather (pointnet2.py:384-387): xyz (B,N,3) -> idx (B,M) int32, new_xyz (B,M,3)."""
+    _f32(xyz, 'xyz')
+    xyz = xyz.contiguous()
+    B, N, _ = xyz.shape
+    idx = torch.empty(B, m, dtype=torch.int32, device=xyz.device)
+    new_xyz = torch.empty(B, m, 3, dtype=torch.float32, device=xyz.device)
+    _count('fps')
+    check(lib.caspr_fps(_p(xyz), B, N, m, _p(idx), _p(new_xyz), _stream()), 'caspr_fps')
+    return idx, new_xyz
+
+
+def ball_query2(xyz, new_xyz, r0, ns0, r1, ns1):
+    """Both ball queries of one SA level in one scan -> idx0 (B,M,ns0), idx1 (B,M,ns1) int32."""
+    xyz, new_xyz = _f32(xyz, 'xyz').contiguous(), _f32(new_xyz, 'new_xyz').contiguous()
+    B, N, _ = xyz.shape
+    M = new_xyz.shape[1]
+    idx0 = torch.empty(B, M, ns0, dtype=torch.int32, device=xyz.device)
+    idx1 = torch.empty(B, M, ns1, dtype=torch.int32, device=xyz.device)
+    _count('ball_query2')
+    check(lib.caspr_ball_query2(_p(xyz), _p(new_xyz), B, N, M, float(r0), ns0, _p(idx0), float(r1), ns1,
+                                _p(idx1), _stream()), 'caspr_ball_query2')
+    return idx0, idx1
+
+
+def group_points(xyz, new_xyz, feat, idx):
+    """Grouping layer output as rows: (B*M*ns, 3+C) = [xyz[idx]-centre | feat[idx]].
+
+    feat: (B,N,C) channels-last view with unit channel stride (row stride free) or None."""
+    B, N, _ = xyz.shape
+    M, ns = idx.shape[1], idx.shape[2]
+    C, ld_feat = 0, 0
+    if feat is not None:
+        _f32(feat, 'feat')
+        assert feat.dim() == 3 and feat.stride(2) == 1 and feat.stride(0) == N * feat.stride(1)
+        C, ld_feat = feat.shape[2], feat.stride(1)
+    out = torch.empty(B * M * ns, 3 + C, dtype=torch.float32, device=xyz.device)
+    _count('group_points')
+    check(lib.caspr_group_points(_p(xyz), _p(new_xyz), _p(feat), ld_feat, _p(idx), B, N, M, C, ns, _p(out),
+                                 3 + C, _stream()), 'caspr_group_points')
+    return out
+
+
+def three_nn(unknown, known):
+    """three_nn (pointnet2.py:514): -> dist (B,n,3) Euclidean, idx (B,n,3) int32."""
+    unknown, known = _f32(unknown, 'unknown').contiguous(), _f32(known, 'known').contiguous()
+    B, n, _ = unknown.shape
+    m = known.shape[1]
+    dist = torch.empty(B, n, 3, dtype=torch.float32, device=unknown.device)
+    idx = torch.empty(B, n, 3, dtype=torch.int32, device=unknown.device)
+    _count('three_nn')
+    check(lib.caspr_three_nn(_p(unknown), _p(known), B, n, m, _p(dist), _p(idx), _stream()), 'caspr_three_nn')
+    return dist, idx
+
+
+def three_interp_concat(feat_prev, idx, dist, skip):
+    """pointnet2.py:516-523: rows (B*n, Cp+Cs) = [inverse-distance interpolation of feat_prev | skip].
+
+    feat_prev (B,m,Cp), skip (B,n,Cs) channels-last views (unit channel stride) or None."""
+    B, n, _ = idx.shape
+    m, Cp = feat_prev.shape[1], feat_prev.shape[2]
+    assert feat_prev.stride(2) == 1 and feat_prev.stride(0) == m * feat_prev.stride(1)
+    Cs, ld_skip = 0, 0
+    if skip is not None:
+        assert skip.stride(2) == 1 and skip.stride(0) == n * skip.stride(1)
+        Cs, ld_skip = skip.shape[2], skip.stride(1)
+    out = torch.empty(B * n, Cp + Cs, dtype=torch.float32, device=idx.device)
+    _count('three_interp_concat')
+    check(lib.caspr_three_interp_concat(_p(feat_prev), feat_prev.stride(1), _p(idx), _p(dist), _p(skip), ld_skip,
+                                        B, n, m, Cp, Cs, _p(out), Cp + Cs, _stream()),
+          'caspr_three_interp_concat')
+    return out
+
+
+# ------------------------------------------------------------------------------ dense ops
+def linear(x, weight, bias=None, out=None, act_in=ACT_NONE, act_out=ACT_NONE):
+    """1x1 Conv1d / Linear on rows: y = act_out(act_in(x) @ W^T + b).
+
+    x (rows, Cin) view; weight (Cout, Cin) or Conv1d-shaped (Cout, Cin, 1); out optional (rows, Cout) view."""
+    x, ldx = _rows2d(x, 'x')
+    w = weight.reshape(weight.shape[0], weight.shape[1])
+    _f32(w, 'weight')
+    assert w.is_contiguous()
+    rows, cin = x.shape
+    cout = w.shape[0]
+    assert w.shape[1] == cin
+    if out is None:
+        out = torch.empty(rows, cout, dtype=torch.float32, device=x.device)
+    out, ldy = _rows2d(out, 'out')
+    assert out.shape == (rows, cout)
+    _count('linear')
+    check(lib.caspr_linear(_p(x), ldx, _p(w), cin, _p(bias), _p(out), ldy, rows, cin, cout, act_in, act_out,
+                           _stream()), 'caspr_linear')
+    return out
+
+
+def groupnorm(x, samples, rows_per_sample, groups, gamma, beta, eps=1e-5, relu=False, write_back=True,
+              maxout=None):
+    """In-place GroupNorm(groups, C) over `samples` blocks of consecutive rows, fused ReLU / max-pool.
+
+    x (samples*rows_per_sample, C) view.  maxout: optional (samples, C) view receiving the max over
+    the rows of each sample of the normalised (and ReLU'd) values."""
+    x, ldx = _rows2d(x, 'x')
+    C = x.shape[1]
+    assert x.shape[0] == samples * rows_per_sample
+    ld_max = 0
+    if maxout is not None:
+        maxout, ld_max = _rows2d(maxout, 'maxout')
+        assert maxout.shape == (samples, C)
+    stats = torch.empty(samples * groups * 2, dtype=torch.float64, device=x.device)
+    _count('groupnorm')
+    check(lib.caspr_groupnorm(_p(x), ldx, samples, rows_per_sample, C, groups, _p(gamma), _p(beta), float(eps),
+                              int(relu), int(write_back), _p(maxout), ld_max, _p(stats), _stream()),
+          'caspr_groupnorm')
+    return x
+
+
+def augment_xyz(x4):
+    """tpointnet2.py:79-90 with both augmentations: (R,4) -> (R,9) [x,y,z,x2,y2,z2,xz,xy,yz]."""
+    _f32(x4, 'x4')
+    x4 = x4.contiguous()
+    out = torch.empty(x4.shape[0], 9, dtype=torch.float32, device=x4.device)
+    _count('augment_xyz')
+    check(lib.caspr_augment_xyz(_p(x4), x4.shape[0], _p(out), _stream()), 'caspr_augment_xyz')
+    return out
+
+
+def strip_time(x4):
+    _f32(x4, 'x4')
+    x4 = x4.contiguous()
+    out = torch.empty(x4.shape[0], 3, dtype=torch.float32, device=x4.device)
+    _count('strip_time')
+    check(lib.caspr_strip_time(_p(x4), x4.shape[0], _p(out), _stream()), 'caspr_strip_time')
+    return out
+
+
+def broadcast_rows(src, rows_per_sample, dst):
+    """dst[s*rows_per_sample + r, :] = src[s, :] (pointnet.py:44-46 repeat + concat)."""
+    src, ld_src = _rows2d(src, 'src')
+    dst, ld_dst = _rows2d(dst, 'dst')
+    samples, C = src.shape
+    assert dst.shape == (samples * rows_per_sample, C)
+    _count('broadcast_rows')
+    check(lib.caspr_broadcast_rows(_p(src), ld_src, samples, rows_per_sample, C, _p(dst), ld_dst, _stream()),
+          'caspr_broadcast_rows')
+    return dst
+
+
+# ------------------------------------------------------------------------------ latent ODE
+def latent_ode_solve(z0, weights, biases, times, rtol, atol):
+    """dopri5 solve of the latent dynamics MLP.  z0 (B,D); times: increasing python floats /
+    1-D tensor (times[0] = start).  Returns out (nT,B,D) and the info list [status,nfe,acc,rej,...]."""
+    _f32(z0, 'z0')
+    z0 = z0.contiguous()
+    B, D = z0.shape
+    H = weights[0].shape[0]
+    tl = [float(t) for t in times]
+    nT = len(tl)
+    h_times = (ctypes.c_double * nT)(*tl)
+    out = torch.empty(nT, B, D, dtype=torch.float32, device=z0.device)
+    info = torch.zeros(8, dtype=torch.int32, device=z0.device)
+    h_info = (ctypes.c_int32 * 8)()
+    ws_bytes = lib.caspr_latent_ode_workspace_bytes(B, D, H)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z0.device)
+    w = [x.contiguous() for x in weights]
+    b = [x.contiguous() for x in biases]
+    _count('latent_ode_solve')
+    rc = lib.caspr_latent_ode_solve(_p(z0), B, D, H, _p(w[0]), _p(b[0]), _p(w[1]), _p(b[1]), _p(w[2]), _p(b[2]),
+                                    _p(w[3]), _p(b[3]), h_times, nT, float(rtol), float(atol), _p(out), _p(info),
+                                    h_info, _p(ws), ws_bytes, _stream())
+    return out, list(h_info), rc
+
+
+# -------------------------------------------------------------------------------------- CNF
+class CnfWeightPack(object):
+    """Keeps the tensors referenced by a caspr_cnf_weights struct alive."""
+
+    def __init__(self, layers, hidden, ctx_dim):
+        # layers: list of 4 dicts with W, b, Wgate, bgate, Wbias (contiguous CUDA fp32 tensors)
+        self.keep = layers
+        self.struct = _lib.CnfWeights()
+        for l, d in enumerate(layers):
+            for k in ('W', 'b', 'Wgate', 'bgate', 'Wbias'):
+                t = d[k]
+                assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+                getattr(self.struct, k)[l] = t.data_ptr()
+        self.struct.hidden = hidden
+        self.struct.ctx_dim = ctx_dim
+
+
+def _mbn_struct(m):
+    if m is None:
+        return None, None
+    keep = [m[k].contiguous() for k in ('weight', 'bias', 'running_mean', 'running_var')]
+    s = _lib.MbnParams(*[t.data_ptr() for t in keep])
+    return s, keep
+
+
+def cnf_flow(x, logp, e, ctx, pack, mbn0, mbn2, end_time, reverse, rtol=1e-5, atol=1e-5, engine=CNF_SIMT_FP32):
+    """One pass through [MBN, CNF, MBN] (or its inverse).  x (F,P,3), logp (F,P) or None, e (F,P,3),
+    ctx (F,ctx_dim).  Returns x_out, logp_out (or None), info list, status."""
+    x, e, ctx = _f32(x, 'x').contiguous(), _f32(e, 'e').contiguous(), _f32(ctx, 'ctx').contiguous()
+    F, P, _ = x.shape
+    if logp is not None:
+        logp = _f32(logp, 'logp').contiguous()
+    x_out = torch.empty_like(x)
+    logp_out = torch.empty(F, P, dtype=torch.float32, device=x.device) if logp is not None else None
+    info = torch.zeros(8, dtype=torch.int32, device=x.device)
+    h_info = (ctypes.c_int32 * 8)()
+    ws_bytes = lib.caspr_cnf_workspace_bytes(F, P, pack.struct.hidden, pack.struct.ctx_dim, engine)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    s0, k0 = _mbn_struct(mbn0)
+    s2, k2 = _mbn_struct(mbn2)
+    _count('cnf_flow')
+    rc = lib.caspr_cnf_flow(_p(x), _p(logp), _p(e), _p(ctx), F, P, ctypes.byref(pack.struct),
+                            ctypes.byref(s0) if s0 is not None else None,
+                            ctypes.byref(s2) if s2 is not None else None,
+                            float(end_time), int(bool(reverse)), float(rtol), float(atol), int(engine),
+                            _p(x_out), _p(logp_out), _p(info), h_info, _p(ws), ws_bytes, _stream())
+    del k0, k2
+    return x_out, logp_out, list(h_info), rc
+
+
+def cnf_feval(y, e, ctx, pack, t, engine=CNF_SIMT_FP32):
+    """One dynamics evaluation: returns dy (F,P,3), neg_div (F,P)."""
+    y, e, ctx = _f32(y, 'y').contiguous(), _f32(e, 'e').contiguous(), _f32(ctx, 'ctx').contiguous()
+    F, P, _ = y.shape
+    dy = torch.empty_like(y)
+    nd = torch.empty(F, P, dtype=torch.float32, device=y.device)
+    ws_bytes = lib.caspr_cnf_workspace_bytes(F, P, pack.struct.hidden, pack.struct.ctx_dim, engine)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=y.device)
+    _count('cnf_feval')
+    check(lib.caspr_cnf_feval(_p(y), _p(e), _p(ctx), F, P, ctypes.byref(pack.struct), float(t), int(engine),
+                              _p(dy), _p(nd), _p(ws), ws_bytes, _stream()), 'caspr_cnf_feval')
+    return dy, nd
+
+
+def chamfer(a, b):
+    """Squared-NN distances both ways: a (B,P,3), b (B,Q,3) -> d_ab (B,P), d_ba (B,Q)."""
+    a, b = _f32(a, 'a').contiguous(), _f32(b, 'b').contiguous()
+    B, P, _ = a.shape
+    Q = b.shape[1]
+    d_ab = torch.empty(B, P, dtype=torch.float32, device=a.device)
+    d_ba = torch.empty(B, Q, dtype=torch.float32, device=a.device)
+    _count('chamfer')
+    check(lib.caspr_chamfer(_p(a), _p(b), B, P, Q, _p(d_ab), _p(d_ba), _stream()), 'caspr_chamfer')
+    return d_ab, d_ba

@@ -1,0 +1,189 @@
+/*
+ * caspr_b200.h — C-ABI of libcaspr_b200.so (hand-written sm_100a CUDA for the
+ * CaSPR reconstruction hot path).
+ *
+ * Conventions (every entry point):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
+ *     parameter name starts with `h_` (host);
+ *   - the caller owns all memory (inputs, outputs, workspaces); the library never
+ *     allocates device memory, never frees and never keeps a pointer after return;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); only the
+ *     two *_solve entry points synchronise that stream (documented there);
+ *   - returns 0 on success, a negative caspr_status otherwise; never throws/aborts;
+ *   - fp32 data, int32 indices; "rows x channels" (channels-last) activations.
+ *
+ * File:line citations name the reference interface each entry point replaces
+ * (paths relative to /root/reference/caspr/models unless stated).
+ */
+#ifndef CASPR_B200_H_
+#define CASPR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  CASPR_OK = 0,
+  CASPR_EINVAL = -1,        /* bad shape / null pointer / unsupported size      */
+  CASPR_ELAUNCH = -2,       /* cudaGetLastError() != cudaSuccess after a launch */
+  CASPR_EWORKSPACE = -3,    /* workspace too small                              */
+  CASPR_ESOLVER_DT = -4,    /* torchdiffeq's "underflow in dt" assertion         */
+  CASPR_ESOLVER_NONFINITE = -5, /* torchdiffeq's "non-finite values in state"    */
+  CASPR_ESOLVER_MAXSTEPS = -6,  /* max_num_steps exceeded                        */
+  CASPR_ERANGE = -7         /* split-precision operand left the fp16 range      */
+} caspr_status;
+
+/* Library / build identification. */
+int caspr_version(void);                    /* e.g. 100 = 0.1.0                       */
+const char* caspr_build_arch(void);         /* "sm_100a"                              */
+const char* caspr_status_string(int status);
+
+/* ------------------------------------------------------------------ geometry
+ * Replaces the Kaolin ops imported at pointnet2.py:7-10.  Arithmetic is the
+ * declared canonical one of oracle/pointnet2_ops.py: d2 = ((dx*dx)+(dy*dy))+(dz*dz)
+ * in fp32 without FMA contraction, ties -> lowest index, FPS skips |p|^2 <= 1e-3. */
+
+/* furthest_point_sampling + fps_gather_by_index (pointnet2.py:384-387).
+ * xyz (B,N,3) -> idx (B,M) int32 and, if new_xyz != NULL, new_xyz (B,M,3). */
+int caspr_fps(const float* xyz, int B, int N, int M, int32_t* idx, float* new_xyz, void* stream);
+
+/* Ball query of PointNet2GroupingLayer for BOTH scales of one set-abstraction level
+ * in one scan (pointnet2.py:340-342,391): for each centre the first ns points in index
+ * order with d2 < r^2, unfilled slots = first hit.  r0 <= r1 required.
+ * idx0 (B,M,ns0), idx1 (B,M,ns1) int32; either may be NULL. */
+int caspr_ball_query2(const float* xyz, const float* new_xyz, int B, int N, int M,
+                      float r0, int ns0, int32_t* idx0, float r1, int ns1, int32_t* idx1,
+                      void* stream);
+
+/* group_gather_by_index x2 + centre subtraction + channel concat (pointnet2.py:391-398).
+ * feat is channels-last (B,N,C) with row stride ld_feat floats (C may be 0, feat NULL).
+ * out rows = B*M*ns, each row [dx,dy,dz | feat(C)], row stride ld_out floats (>= 3+C). */
+int caspr_group_points(const float* xyz, const float* new_xyz, const float* feat, int ld_feat,
+                       const int32_t* idx, int B, int N, int M, int C, int ns, float* out, int ld_out,
+                       void* stream);
+
+/* three_nn (pointnet2.py:514): unknown (B,n,3), known (B,m,3) -> dist (B,n,3) Euclidean,
+ * idx (B,n,3) int32; strict '<' running best-3 over ascending index. */
+int caspr_three_nn(const float* unknown, const float* known, int B, int n, int m,
+                   float* dist, int32_t* idx, void* stream);
+
+/* inverse-distance weights + three_interpolate + skip concat (pointnet2.py:516-523).
+ * feat_prev (B,m,Cp) channels-last with row stride ld_prev; skip (B,n,Cs) row stride ld_skip
+ * (Cs may be 0); out (B,n,Cp+Cs) row stride ld_out = [interp | skip]. */
+int caspr_three_interp_concat(const float* feat_prev, int ld_prev, const int32_t* idx, const float* dist,
+                              const float* skip, int ld_skip, int B, int n, int m, int Cp, int Cs,
+                              float* out, int ld_out, void* stream);
+
+/* ------------------------------------------------------------------ dense ops
+ * Replace the Conv1d(k=1)/Linear/GroupNorm/ReLU/max calls of pointnet2.py:637-642,
+ * 677-699,471-481,207-212; pointnet.py:27-46; tpointnet2.py:59-62,99-112. */
+
+enum { CASPR_ACT_NONE = 0, CASPR_ACT_RELU = 1, CASPR_ACT_SIGMOID = 2 };
+
+/* Y[r, 0:Cout] = act_out( act_in(X[r, 0:Cin]) . W[0:Cout, 0:Cin]^T + bias ),  fp32 SIMT.
+ * X row stride ldx, W row stride ldw, Y row stride ldy (floats). bias may be NULL. */
+int caspr_linear(const float* X, int ldx, const float* W, int ldw, const float* bias,
+                 float* Y, int ldy, int rows, int Cin, int Cout, int act_in, int act_out,
+                 void* stream);
+
+/* GroupNorm over samples of `rows_per_sample` consecutive rows (torch.nn.GroupNorm(groups, C)
+ * on (samples, C, rows_per_sample)), eps as given; optional ReLU; optional max over the rows
+ * of each sample AFTER normalisation (and after ReLU if set) into maxout (samples, C) with
+ * row stride ld_max.  If write_back == 0 X is left untouched (only maxout is produced).
+ * stats_ws: >= samples*groups*2 doubles (used when a sample spans several CTAs). */
+int caspr_groupnorm(float* X, int ldx, int samples, int rows_per_sample, int C, int groups,
+                    const float* gamma, const float* beta, float eps, int relu,
+                    int write_back, float* maxout, int ld_max, double* stats_ws, void* stream);
+
+/* tpointnet2.py:79-90: x (R,4) rows [x,y,z,t] -> out (R,9) rows [x,y,z,x2,y2,z2,xz,xy,yz]. */
+int caspr_augment_xyz(const float* x4, int rows, float* out9, void* stream);
+
+/* xyz (R,3) contiguous from x (R,4). */
+int caspr_strip_time(const float* x4, int rows, float* xyz3, void* stream);
+
+/* pointnet.py:44-46 / tpointnet2.py:96: dst[s*rows_per_sample + r, 0:C] = src[s, 0:C]. */
+int caspr_broadcast_rows(const float* src, int ld_src, int samples, int rows_per_sample, int C,
+                         float* dst, int ld_dst, void* stream);
+
+/* ---------------------------------------------------------------- latent ODE
+ * Replaces LatentODE.forward -> ODESolver -> torchdiffeq.odeint_adjoint(dopri5)
+ * (latent_ode_model.py:45-70,98) with DynamicsNet (latent_ode_model.py:129-147):
+ * Linear(D,H) tanh Linear(H,H) tanh Linear(H,H) tanh Linear(H,D).
+ * One persistent CTA runs the whole adaptive solve (torchdiffeq 0.0.1 semantics,
+ * oracle/odeint001.py) for all B sequences: the step controller is batch-global.
+ * z0 (B,D); h_times: nT float64 HOST values, strictly increasing, times[0] = start;
+ * out (nT,B,D); info (8 int32, device): [status, nfe, accepted steps, rejected steps,..].
+ * Synchronises `stream` before returning (reads info) and maps solver failures to
+ * CASPR_ESOLVER_*.  h_info (8 int32, host) receives a copy of info. */
+size_t caspr_latent_ode_workspace_bytes(int B, int D, int H);
+int caspr_latent_ode_solve(const float* z0, int B, int D, int H,
+                           const float* W0, const float* b0, const float* W1, const float* b1,
+                           const float* W2, const float* b2, const float* W3, const float* b3,
+                           const double* h_times, int nT, float rtol, float atol,
+                           float* out, int32_t* info, int32_t* h_info,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ----------------------------------------------------------------------- CNF
+ * Replaces SequentialFlow/CNF/ODEfunc/ODEnet/ConcatSquashLinear/MovingBatchNorm1d
+ * (cnf.py:33-48,70-128; odefunc.py:13-31,98-105,119-142; diffeq_layers.py:76-90;
+ * normalization.py:59-108) and torchdiffeq's dopri5 for the 3-tuple state. */
+
+typedef struct {
+  /* ODEnet main weights, row-major (out,in): W1 (H,3) W2 (H,H) W3 (H,H) W4 (3,H) */
+  const float* W[4];
+  const float* b[4];
+  /* hyper nets, row-major (out, 1+ctx): column 0 multiplies t */
+  const float* Wgate[4];
+  const float* bgate[4];
+  const float* Wbias[4];
+  int hidden;            /* H = 512 */
+  int ctx_dim;           /* 1600    */
+} caspr_cnf_weights;
+
+typedef struct {
+  /* MovingBatchNorm1d (eval): chain[0] (data side) and chain[2] (base side): 3 floats each */
+  const float* weight;
+  const float* bias;
+  const float* running_mean;
+  const float* running_var;
+} caspr_mbn_params;
+
+enum { CASPR_CNF_SIMT_FP32 = 0, CASPR_CNF_TC_FP16X3 = 1 };
+
+/* Workspace for a solve over `frames` contexts x `pts` points each. */
+size_t caspr_cnf_workspace_bytes(int frames, int pts, int hidden, int ctx_dim, int engine);
+
+/* One full flow evaluation x -> chain (forward: MBN0, CNF 0->T, MBN2; reverse: MBN2^-1,
+ * CNF T->0, MBN0^-1), dopri5 rtol/atol on (x, logp), context carried as a zero-dynamics state.
+ *   x_in (frames,pts,3); logp_in (frames,pts) or NULL (treated as zeros, cnf.py:71-74);
+ *   e (frames,pts,3) Hutchinson noise (odefunc.py:127-128), fixed for the whole solve;
+ *   ctx (frames,ctx_dim); end_time = sqrt_end_time^2 (cnf.py:89-91);
+ *   x_out (frames,pts,3); logp_out (frames,pts) or NULL.
+ * info/h_info: 8 int32 [status, nfe, accepted, rejected, ...].  Synchronises `stream`
+ * (polls the device-side controller every few steps). */
+int caspr_cnf_flow(const float* x_in, const float* logp_in, const float* e, const float* ctx,
+                   int frames, int pts, const caspr_cnf_weights* w,
+                   const caspr_mbn_params* mbn0, const caspr_mbn_params* mbn2,
+                   float end_time, int reverse, float rtol, float atol, int engine,
+                   float* x_out, float* logp_out, int32_t* info, int32_t* h_info,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* One dynamics evaluation (dy, -div) = ODEfunc(t, (y, logp, ctx)) for testing/profiling:
+ * y (frames,pts,3), e (frames,pts,3) -> dy (frames,pts,3), neg_div (frames,pts). */
+int caspr_cnf_feval(const float* y, const float* e, const float* ctx, int frames, int pts,
+                    const caspr_cnf_weights* w, float t, int engine,
+                    float* dy, float* neg_div, void* workspace, size_t workspace_bytes, void* stream);
+
+/* -------------------------------------------------------------------- metric
+ * Symmetric squared-NN Chamfer distance (reference utils/evaluations.py:40-43 via
+ * tk3dv ChamferDistance): a (B,P,3), b (B,Q,3) -> d_ab (B,P) min sq dist a->b, d_ba (B,Q). */
+int caspr_chamfer(const float* a, const float* b, int B, int P, int Q,
+                  float* d_ab, float* d_ba, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* CASPR_B200_H_ */

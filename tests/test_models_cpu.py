@@ -1,0 +1,61 @@
+"""Host-side mirror of the reference interface: state_dict layout, loaders, loud failure without CUDA."""
+import pytest
+import torch
+
+from caspr_b200.synth import load_manifest, synthetic_state_dict, synthetic_sequences
+
+
+def test_state_dict_matches_reference_manifest(lib_built):
+    from caspr_b200.models import CaSPR
+    model = CaSPR()
+    sd = model.state_dict()
+    man = load_manifest()
+    assert list(sd.keys()) == list(man.keys())          # 238 keys, same order as the reference
+    assert len(sd) == 238
+    for k, shape in man.items():
+        assert list(sd[k].shape) == shape, k
+    assert sum(p.numel() for p in model.parameters()) == 16262189
+
+
+def test_load_reference_style_checkpoint(lib_built):
+    from caspr_b200.models import CaSPR
+    sd = synthetic_state_dict(0)
+    model = CaSPR()
+    # reference torch_utils.load_weights strips a DataParallel 'module.' prefix and uses strict=False
+    wrapped = {'module.' + k: v for k, v in sd.items()}
+    stripped = {k[len('module.'):]: v for k, v in wrapped.items()}
+    missing, unexpected = model.load_state_dict(stripped, strict=False)
+    assert not missing and not unexpected
+    enc = {k[len('encoder.'):]: v for k, v in sd.items() if k.startswith('encoder.')}
+    model.encoder.load_state_dict(enc)                  # torch_utils.load_encoder_weights_from_full
+    a = model.latent_ode.ode_func.dynamics_net[0].weight
+    b = model.latent_ode.solver.ode_func.dynamics_net[0].weight
+    assert a.data_ptr() == b.data_ptr()                 # aliased module registered twice
+
+
+def test_ctor_variants(lib_built):
+    from caspr_b200.models import CaSPR
+    m = CaSPR(pretrain_tnocs=True)
+    assert not hasattr(m, 'point_cnf')
+    m = CaSPR(regress_tnocs=False)
+    assert not hasattr(m.encoder, 'conv3')
+    m = CaSPR(augment_quad=False, augment_pairs=False)
+    assert m.encoder.local_extract.set_abstractions[0].pointnet_modules[0].conv_layers[0].weight.shape[1] == 3
+
+
+def test_no_cpu_fallback(lib_built):
+    from caspr_b200.models import CaSPR
+    model = CaSPR().eval()
+    x, _ = synthetic_sequences(1, 2, 64, seed=0)
+    with pytest.raises((RuntimeError, TypeError)):
+        model.encode(x)                                  # CPU tensor: must fail loudly, never fall back
+
+
+def test_synthetic_generators_are_deterministic():
+    a = synthetic_state_dict(0)
+    b = synthetic_state_dict(0)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    x1, n1 = synthetic_sequences(2, 3, 128, seed=4)
+    x2, n2 = synthetic_sequences(2, 3, 128, seed=4)
+    assert torch.equal(x1, x2) and torch.equal(n1, n2)
+    assert x1.shape == (2, 3, 128, 4) and float(x1[..., 2].min()) > 0.5

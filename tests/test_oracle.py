@@ -1,0 +1,106 @@
+"""Pin the oracle restatement (oracle/caspr_oracle.py, pure CPU) against the fixtures frozen from the
+UNMODIFIED reference modules (tests/golden/make_golden.py), and — when /root/reference is present —
+against the live reference modules themselves."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from caspr_b200.synth import synthetic_state_dict, synthetic_sequences
+from oracle.caspr_oracle import CasprOracle, chamfer_distance
+from oracle import pointnet2_ops as pn2
+from oracle.reference_loader import reference_available
+
+
+@pytest.fixture(scope='module', params=['vig', 'def'])
+def case(request, golden_dir):
+    tag = request.param
+    gold = dict(np.load(os.path.join(golden_dir, 'caspr_%s.npz' % tag)))
+    sd = synthetic_state_dict(0, cnf_init='vigorous' if tag == 'vig' else 'default')
+    x, nocs = synthetic_sequences(1, 3, 1024, seed=1)
+    torch.set_num_threads(8)
+    return tag, gold, CasprOracle(sd), x, nocs
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-12)
+
+
+def test_geometry_indices_bit_exact(case):
+    _, gold, _, x, _ = case
+    xyz = x.view(3, 1024, 4)[:, :, :3].contiguous()
+    for lvl, m in enumerate([1024, 512, 256, 64, 16]):
+        idx = pn2.furthest_point_sampling(xyz, m)
+        assert np.array_equal(idx.numpy(), gold['fps_idx_%d' % lvl])
+        new_xyz = pn2.fps_gather_by_index(xyz.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
+        if lvl in (0, 2, 4):
+            r = [0.02, 0.05, 0.1, 0.2, 0.4, 0.8][lvl + 1]
+            assert np.array_equal(pn2.ball_query(r, 32, xyz, new_xyz).numpy(), gold['ball_idx_%d_1' % lvl])
+        xyz = new_xyz
+
+
+def test_encode_matches_reference_fixture(case):
+    _, gold, oracle, x, _ = case
+    z0, tnocs = oracle.encode(x)
+    assert _rel(z0, gold['z0']) < 1e-5
+    assert _rel(tnocs, gold['tnocs']) < 1e-5
+
+
+def test_reconstruct_matches_reference_fixture(case):
+    _, gold, oracle, x, _ = case
+    y = torch.from_numpy(gold['rec_y']).reshape(3, 256, 3)
+    e = torch.from_numpy(gold['rec_e'])
+    _, _, xr, _ = oracle.reconstruct(x, num_points=256, y=y, e=e)
+    assert list(oracle.get_nfe()) == list(gold['rec_nfe'])
+    assert _rel(xr, gold['rec_x']) < 1e-5
+
+
+def test_interpolated_reconstruct_matches_reference_fixture(case):
+    _, gold, oracle, x, _ = case
+    y = torch.from_numpy(gold['interp_y'])[:, 0]
+    e = torch.from_numpy(gold['interp_e'])
+    _, _, xr, _ = oracle.reconstruct(x, num_points=128, constant_in_time=True,
+                                     timestamps=torch.linspace(0, 1, 5), y=y, e=e)
+    assert list(oracle.get_nfe()) == list(gold['interp_nfe'])
+    assert _rel(xr, gold['interp_x']) < 1e-5
+
+
+def test_decode_config1_matches_reference_fixture(case):
+    """BASELINE config 1: decode 512 points from one frozen latent on the CPU."""
+    _, gold, oracle, _, _ = case
+    z = torch.from_numpy(gold['dec_z'])
+    _, _, xd = oracle.decode(z, num_points=512, y=torch.from_numpy(gold['dec_y']).reshape(1, 512, 3),
+                             e=torch.from_numpy(gold['dec_e']))
+    assert oracle.get_nfe()[1] == gold['dec_nfe'][1]
+    assert _rel(xd, gold['dec_x']) < 1e-5
+
+
+def test_forward_nll_matches_reference_fixture(case):
+    _, gold, oracle, x, nocs = case
+    nll, tl = oracle.forward(x, nocs, e=torch.from_numpy(gold['fwd_e']))
+    assert list(oracle.get_nfe()) == list(gold['fwd_nfe'])
+    assert _rel(nll, gold['fwd_nll']) < 1e-4
+    assert abs(float(tl.mean()) - float(gold['fwd_tnocs_l1_mean'])) < 1e-6
+
+
+def test_chamfer_definition():
+    a = torch.tensor([[[0., 0, 0], [1, 0, 0]]])
+    b = torch.tensor([[[0., 0, 0.5]]])
+    cd = chamfer_distance(a, b)
+    assert abs(float(cd) - ((0.25 + 1.25) / 2 + 0.25)) < 1e-6
+
+
+@pytest.mark.skipif(not reference_available(), reason='/root/reference only exists in the dev container')
+def test_oracle_matches_live_reference_modules():
+    from oracle.reference_loader import build_reference_caspr
+    sd = synthetic_state_dict(3)
+    x, _ = synthetic_sequences(1, 2, 1024, seed=9)
+    ref = build_reference_caspr()
+    ref.load_state_dict(sd)
+    ref.eval()
+    with torch.no_grad():
+        z0_ref, tn_ref = ref.encode(x)
+    z0, tn = CasprOracle(sd).encode(x)
+    assert _rel(z0, z0_ref) < 1e-5 and _rel(tn, tn_ref) < 1e-5
