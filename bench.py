@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Benchmark of the CaSPR reconstruction hot path (BASELINE.json metric: reconstructed points/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one ``CaSPR.reconstruct`` call (TPointNet++ encode -> latent ODE -> CNF decode) over one
+batch of synthetic sequences.  Workload = BASELINE.json configs[1] ("rigid cars"): 10 frames x 1024
+input points, 2048 reconstructed points per frame, batch 8 per GPU; with N GPUs every rank processes
+its own batch of 8 sequences (batch-sharded, no data-path collective; weak scaling).
+
+Prints ONE JSON line on rank 0 (see the driver contract): `value` is device-resident throughput,
+`e2e` goes through the public API with host buffers (pinned H2D of the input, CPU-generator base
+samples as the reference draws them, D2H of the reconstruction), `roofline` is the dominant kernel
+timed with CUDA events inside the timed region, `cpu_baseline` is the CPU oracle on a bounded sample.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch                      # noqa: E402
+
+WORKLOADS = {
+    # name: (B per GPU, T, N input pts, P sampled pts, interpolated query steps or None, warping)
+    'cars_rigid_T10_N1024_P2048_B8': (8, 10, 1024, 2048, None, False),          # BASELINE configs[1]
+    'chairs_rigid_T10_N2048_P2048_B4': (4, 10, 2048, 2048, None, False),        # configs[2]: 32 over 8 GPUs
+    'warping_cars_T10_N2048_P2048_S20_B4': (4, 10, 2048, 2048, 20, True),       # configs[3]
+}
+DEFAULT_WORKLOAD = 'cars_rigid_T10_N1024_P2048_B8'
+METRIC = 'reconstructed_points_per_sec'
+UNIT = 'points/s'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument('--cnf-init', default='vigorous', choices=['vigorous', 'default'])
+    ap.add_argument('--engine', default='auto', choices=['auto', 'simt', 'tc'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {'hbm_gbs': p['hbm_gbs'], 'tf_burst': p['bf16_tflops'], 'tf_sustained': p['bf16_tflops_sustained'],
+                'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'tf_burst': 1590.0, 'tf_sustained': 1400.0, 'source': 'fallback'}
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = str(gpu_index)
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.QUERY, '--format=csv,noheader,nounits',
+                                          '-lms', '200', '-i', self.gpu], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, r[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(smax) if smax else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------- inputs
+def make_inputs(workload, seed, cnf_init):
+    from caspr_b200.synth import synthetic_state_dict, synthetic_sequences
+    B, T, N, P, S, warping = WORKLOADS[workload]
+    sd = synthetic_state_dict(0, cnf_init=cnf_init)
+    x, _ = synthetic_sequences(B, T, N, seed=100 + seed, warping=warping, max_timestamp=1.0 if warping else 5.0)
+    Tq = S if S is not None else T
+    g = torch.Generator().manual_seed(1000 + seed)
+    nb = B if S is not None else B * T                     # constant_in_time shares one base cloud per sequence
+    y = torch.randn(nb, P, 3, generator=g)
+    e = torch.randn(B * Tq, P, 3, generator=g)
+    kwargs = {'num_points': P}
+    if S is not None:
+        kwargs.update(constant_in_time=True, timestamps=torch.linspace(0, 1, S), max_timestamp=1.0)
+    return sd, x, y, e, kwargs, (B, T, N, P, Tq)
+
+
+def cpu_reference_step(oracle, x1, y1, e1, kwargs):
+    t0 = time.perf_counter()
+    oracle.reconstruct(x1, y=y1, e=e1, **kwargs)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU path (PyTorch + torchdiffeq-0.0.1 semantics) on the host cores.  The
+    reference's dependencies cannot be installed here, so this is the oracle port of the same math
+    (kind "port"); each step is a bounded sample: ONE sequence of the workload."""
+    if rank != 0:
+        return
+    from oracle.caspr_oracle import CasprOracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd, x, y, e, kwargs, (B, T, N, P, Tq) = make_inputs(args.workload, 0, args.cnf_init)
+    per_seq_y = y.shape[0] // B
+    x1, y1, e1 = x[:1], y[:per_seq_y], e[:Tq]
+    oracle = CasprOracle(sd)
+    for _ in range(args.warmup):
+        cpu_reference_step(oracle, x1, y1, e1, kwargs)
+    times = [cpu_reference_step(oracle, x1, y1, e1, kwargs) for _ in range(args.steps)]
+    total = sum(times)
+    pts = Tq * P * args.steps
+    value = pts / total
+    sample = '1 of %d sequences per step (B=1,T=%d,N=%d,P=%d), oracle port, %d threads' % (B, T, N, P, cores)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': args.workload, 'cnf_init': args.cnf_init, 'nfe': oracle.get_nfe()},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------- ours
+def run_ours(args, rank, world, local_rank):
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --impl ours needs a CUDA device (there is no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    from caspr_b200.build import build_library
+    build_library()
+    from caspr_b200 import _lib
+    from caspr_b200 import ops
+    from caspr_b200.models import CaSPR
+    from caspr_b200.models.cnf import SequentialFlow
+    lib = _lib.lib
+
+    if args.engine == 'tc':
+        SequentialFlow.engine = ops.CNF_TC_FP16X3
+    elif args.engine == 'simt':
+        SequentialFlow.engine = ops.CNF_SIMT_FP32
+    engine_name = 'tc_fp16x3' if SequentialFlow.engine == ops.CNF_TC_FP16X3 else 'simt_fp32'
+
+    sd, x, y, e, kwargs, (B, T, N, P, Tq) = make_inputs(args.workload, rank, args.cnf_init)
+    model = CaSPR().to(dev).eval()
+    model.load_state_dict(sd)
+    x_pin = x.pin_memory()
+    x_dev, y_dev, e_dev = x.to(dev), y.to(dev), e.to(dev)
+    kw_dev = dict(kwargs)
+    if 'timestamps' in kw_dev:
+        kw_dev['timestamps'] = kw_dev['timestamps'].to(dev)
+    pts_per_step = B * Tq * P
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+
+    def step_resident():
+        return model.reconstruct(x_dev, y=y_dev, e=e_dev, **kw_dev)
+
+    def step_e2e():
+        xd = x_pin.to(dev, non_blocking=True)
+        _, _, xr, _ = model.reconstruct(xd, **kw_dev)           # base samples drawn on the CPU like the reference
+        return xr.cpu()                                        # device -> host read of the result
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+
+    # ---- timed region 1: device-resident throughput
+    sampler = ClockSampler(local_rank)
+    barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    lib.caspr_profile_enable(1)
+    launches0 = lib.caspr_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step_resident()
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier()
+    launches = lib.caspr_launch_count() - launches0
+    lib.caspr_profile_enable(0)
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    nfe = [int(v) for v in model.get_nfe()]
+    prof = {}
+    for name, kid in (('cnf_mid_layer_kernel', 0), ('cnf_fused_tc_kernel', 1)):
+        tot, cnt = ctypes.c_double(), ctypes.c_longlong()
+        lib.caspr_profile_read(kid, ctypes.byref(tot), ctypes.byref(cnt))
+        prof[name] = (tot.value, cnt.value)
+
+    # ---- timed region 2: end to end through the public API with host buffers
+    step_e2e()
+    barrier()
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
+    f0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    f1.record()
+    torch.cuda.synchronize()
+    wall_ms = 1e3 * (time.perf_counter() - t_wall)
+    barrier()
+    ms_e2e = max(f0.elapsed_time(f1), wall_ms)        # host-side RNG / copies count too
+
+    t = torch.tensor([ms, ms_e2e, float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, ms_e2e, launches = float(tmax[0]), float(tmax[1]), int(tsum[2])
+    if rank != 0:
+        return
+
+    peaks = load_peaks()
+    value = world * pts_per_step * args.steps / (ms * 1e-3)
+    e2e_value = world * pts_per_step * args.steps / (ms_e2e * 1e-3)
+    # dominant kernel: the H x H layers of the CNF dynamics over [activation ; tangent] rows
+    H = 512
+    n_pts = B * Tq * P
+    if prof['cnf_fused_tc_kernel'][1] > 0:
+        kname = 'cnf_fused_tc_kernel'
+        flop_per_launch = 2.0 * 2 * n_pts * (2 * H * H + 2 * 3 * H)       # whole f-eval: both GEMMs x {h, v} + 3<->H
+    else:
+        kname = 'cnf_mid_layer_kernel'
+        flop_per_launch = 2.0 * 2 * n_pts * H * H                          # one H x H layer x {h, v}
+    tot_ms, cnt = prof[kname]
+    roofline = None
+    if cnt > 0:
+        avg_ms = tot_ms / cnt
+        achieved = flop_per_launch / (avg_ms * 1e-3) / 1e12
+        roofline = {'bound': 'tensor', 'kernel': kname, 'achieved': achieved, 'peak': peaks['tf_sustained'],
+                    'unit': 'TFLOP/s', 'frac': achieved / peaks['tf_sustained'], 'traffic': None,
+                    'peak_source': peaks['source'] + ' bf16 dense sustained', 'launches': cnt,
+                    'avg_launch_ms': avg_ms, 'share_of_step': tot_ms / ms,
+                    'flop_per_launch': flop_per_launch}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle.caspr_oracle import CasprOracle
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        per_seq_y = y.shape[0] // B
+        oracle = CasprOracle(sd)
+        dt = cpu_reference_step(oracle, x[:1], y[:per_seq_y], e[:Tq], kwargs)
+        cpu_baseline = {'value': Tq * P / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                        'sample': '1 of %d sequences (B=1,T=%d,N=%d,P=%d), 1 run, %.1f s, nfe %s'
+                                  % (B, T, N, P, dt, oracle.get_nfe())}
+
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': args.workload, 'batch_per_gpu': B, 'global_batch': B * world, 'frames': T,
+                       'input_points': N, 'sampled_points': P, 'query_steps': Tq, 'cnf_init': args.cnf_init,
+                       'nfe_latent_cnf': nfe, 'engine': engine_name, 'parallelism': 'batch-shard x%d' % world,
+                       'l2': 'working set per dynamics evaluation (>1 GB of activations) exceeds the 126 MB L2; no flush'},
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(x.numel() * 4 + y.numel() * 4),
+                    'd2h_bytes_per_step': int(B * Tq * P * 3 * 4), 'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus:
+        if args.gpus > 1 and world == 1:
+            raise SystemExit('launch multi-GPU runs with: python -m torch.distributed.run --nnodes=1 '
+                             '--nproc-per-node %d --master-addr 127.0.0.1 bench.py --gpus %d ...' % (args.gpus, args.gpus))
+    run_ours(args, rank, world, local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

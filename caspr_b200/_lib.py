@@ -36,6 +36,9 @@ SIGNATURES = {
     'caspr_version': (c_int, []),
     'caspr_build_arch': (c_char_p, []),
     'caspr_status_string': (c_char_p, [c_int]),
+    'caspr_launch_count': (ctypes.c_ulonglong, []),
+    'caspr_profile_enable': (None, [c_int]),
+    'caspr_profile_read': (c_int, [c_int, POINTER(c_double), POINTER(ctypes.c_longlong)]),
     'caspr_fps': (c_int, [_P, c_int, c_int, c_int, _P, _P, _P]),
     'caspr_ball_query2': (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_int, _P, c_float, c_int, _P, _P]),
     'caspr_group_points': (c_int, [_P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P]),

@@ -598,9 +598,9 @@ int prepare_hyper(const CnfWorkspace& w, const caspr_cnf_weights* cw, const floa
     rc = caspr_linear(ctx, C, cw->Wbias[l] + 1, C + 1, nullptr, w.Bc + off, ctot, frames, C, D,
                       CASPR_ACT_NONE, CASPR_ACT_NONE, s);
     if (rc) return rc;
-    gather_col0_kernel<<<ceil_div(D, 128), 128, 0, s>>>(cw->Wgate[l], C + 1, D, w.wg_t + off);
-    gather_col0_kernel<<<ceil_div(D, 128), 128, 0, s>>>(cw->Wbias[l], C + 1, D, w.wb_t + off);
-    copy_f32_kernel<<<ceil_div(D, 128), 128, 0, s>>>(cw->b[l], D, w.lbias + off);
+    CASPR_COUNT(); gather_col0_kernel<<<ceil_div(D, 128), 128, 0, s>>>(cw->Wgate[l], C + 1, D, w.wg_t + off);
+    CASPR_COUNT(); gather_col0_kernel<<<ceil_div(D, 128), 128, 0, s>>>(cw->Wbias[l], C + 1, D, w.wb_t + off);
+    CASPR_COUNT(); copy_f32_kernel<<<ceil_div(D, 128), 128, 0, s>>>(cw->b[l], D, w.lbias + off);
     CASPR_CHECK_LAUNCH();
     off += D;
   }
@@ -614,16 +614,20 @@ int enqueue_feval(const CnfWorkspace& w, const caspr_cnf_weights* cw, const floa
   const int n = frames * pts;
   const int ctot = hyper_ld(H);
   const long long tot = (long long)frames * ctot;
-  cnf_hyper_stage_kernel<<<(int)((tot + 255) / 256), 256, 0, s>>>(
+  CASPR_COUNT(); cnf_hyper_stage_kernel<<<(int)((tot + 255) / 256), 256, 0, s>>>(
       w.Gc, w.Bc, w.wg_t, w.wb_t, w.lbias, frames, 3 * H + 3, ctot, stage, reverse, w.st, w.gate, w.biasf);
-  cnf_layer0_kernel<<<blocks_for(n, 8, 148 * 16), 256, 0, s>>>(
+  CASPR_COUNT(); cnf_layer0_kernel<<<blocks_for(n, 8, 148 * 16), 256, 0, s>>>(
       w.y0, w.kbuf, (size_t)n, e, cw->W[0], H, n, pts, stage, w.gate, w.biasf, ctot, w.st, w.Ha, w.Va);
   dim3 grid(ceil_div(n, kMidBM), H / kMidBN);
-  cnf_mid_layer_kernel<<<grid, 256, 0, s>>>(w.Ha, w.Va, cw->W[1], H, n, pts, w.gate + H, w.biasf + H,
+  caspr_prof_begin(CASPR_PROF_CNF_MID_SIMT, s);
+  CASPR_COUNT(); cnf_mid_layer_kernel<<<grid, 256, 0, s>>>(w.Ha, w.Va, cw->W[1], H, n, pts, w.gate + H, w.biasf + H,
                                             ctot, w.st, w.Hb, w.Vb);
-  cnf_mid_layer_kernel<<<grid, 256, 0, s>>>(w.Hb, w.Vb, cw->W[2], H, n, pts, w.gate + 2 * H,
+  caspr_prof_end(CASPR_PROF_CNF_MID_SIMT, s);
+  caspr_prof_begin(CASPR_PROF_CNF_MID_SIMT, s);
+  CASPR_COUNT(); cnf_mid_layer_kernel<<<grid, 256, 0, s>>>(w.Hb, w.Vb, cw->W[2], H, n, pts, w.gate + 2 * H,
                                             w.biasf + 2 * H, ctot, w.st, w.Ha, w.Va);
-  cnf_last_layer_kernel<<<blocks_for(n, 8, 148 * 16), 256, 0, s>>>(
+  caspr_prof_end(CASPR_PROF_CNF_MID_SIMT, s);
+  CASPR_COUNT(); cnf_last_layer_kernel<<<blocks_for(n, 8, 148 * 16), 256, 0, s>>>(
       w.Ha, w.Va, cw->W[3], H, n, pts, e, w.gate + 3 * H, w.biasf + 3 * H, ctot, reverse, w.st,
       w.kbuf + (size_t)stage * n);
   CASPR_CHECK_LAUNCH();
@@ -682,7 +686,7 @@ extern "C" int caspr_cnf_flow(const float* x_in, const float* logp_in, const flo
   int rc = prepare_hyper(w, cw, ctx, frames, s);
   if (rc) return rc;
   const int eb = blocks_for(n, 256, 148 * 8);
-  cnf_init_state_kernel<<<ceil_div(n, 256), 256, 0, s>>>(x_in, logp_in, n, pre, reverse, w.y0);
+  CASPR_COUNT(); cnf_init_state_kernel<<<ceil_div(n, 256), 256, 0, s>>>(x_in, logp_in, n, pre, reverse, w.y0);
   CASPR_CHECK_LAUNCH();
   // odeint001.odeint: decreasing times are integrated as -f(-t) over [-T, 0]
   const float t_start = reverse ? -end_time : 0.f;
@@ -698,16 +702,16 @@ extern "C" int caspr_cnf_flow(const float* x_in, const float* logp_in, const flo
   }
   rc = enqueue_feval(w, cw, e, frames, pts, 0, reverse, s);
   if (rc) return rc;
-  cnf_init_norm_kernel<<<eb, 256, 0, s>>>(w.y0, w.kbuf, n, rtol, atol, w.st);
-  cnf_init_controller_kernel<<<1, 1, 0, s>>>(w.st, n, t_start, t_stop);
+  CASPR_COUNT(); cnf_init_norm_kernel<<<eb, 256, 0, s>>>(w.y0, w.kbuf, n, rtol, atol, w.st);
+  CASPR_COUNT(); cnf_init_controller_kernel<<<1, 1, 0, s>>>(w.st, n, t_start, t_stop);
   CASPR_CHECK_LAUNCH();
 
   const int have_logp = logp_in != nullptr;
   if (!(t_stop > t_start)) {
-    cnf_passthrough_kernel<<<ceil_div(n, 256), 256, 0, s>>>(w.y0, n, post, reverse, have_logp, x_out, logp_out);
+    CASPR_COUNT(); cnf_passthrough_kernel<<<ceil_div(n, 256), 256, 0, s>>>(w.y0, n, post, reverse, have_logp, x_out, logp_out);
     CASPR_CHECK_LAUNCH();
   }
-  const int kBatch = 2, kMaxSteps = 100000;
+  const int kBatch = 1, kMaxSteps = 100000;
   int step_id = 0;
   CnfState hst;
   for (;;) {
@@ -716,9 +720,9 @@ extern "C" int caspr_cnf_flow(const float* x_in, const float* logp_in, const flo
         rc = enqueue_feval(w, cw, e, frames, pts, stage, reverse, s);
         if (rc) return rc;
       }
-      cnf_error_kernel<<<eb, 256, 0, s>>>(w.y0, w.kbuf, (size_t)n, n, rtol, atol, w.st, w.y1);
-      cnf_controller_kernel<<<1, 1, 0, s>>>(w.st, n, step_id);
-      cnf_finalize_kernel<<<eb, 256, 0, s>>>(w.y0, w.kbuf, (size_t)n, w.y1, n, step_id, w.st, post, reverse,
+      CASPR_COUNT(); cnf_error_kernel<<<eb, 256, 0, s>>>(w.y0, w.kbuf, (size_t)n, n, rtol, atol, w.st, w.y1);
+      CASPR_COUNT(); cnf_controller_kernel<<<1, 1, 0, s>>>(w.st, n, step_id);
+      CASPR_COUNT(); cnf_finalize_kernel<<<eb, 256, 0, s>>>(w.y0, w.kbuf, (size_t)n, w.y1, n, step_id, w.st, post, reverse,
                                              have_logp, x_out, logp_out);
       CASPR_CHECK_LAUNCH();
     }
@@ -758,7 +762,7 @@ extern "C" int caspr_cnf_feval(const float* y, const float* e, const float* ctx,
   int rc = prepare_hyper(w, cw, ctx, frames, s);
   if (rc) return rc;
   MbnDev none = load_mbn(nullptr, nullptr);
-  cnf_init_state_kernel<<<ceil_div(n, 256), 256, 0, s>>>(y, nullptr, n, none, 0, w.y0);
+  CASPR_COUNT(); cnf_init_state_kernel<<<ceil_div(n, 256), 256, 0, s>>>(y, nullptr, n, none, 0, w.y0);
   CASPR_CHECK_LAUNCH();
   rc = enqueue_feval(w, cw, e, frames, pts, 0, 0, s);
   if (rc) return rc;

@@ -15,6 +15,14 @@
     if (!(cond)) return CASPR_EINVAL;   \
   } while (0)
 
+// every kernel launch of the library is counted (bench.py reports it as gpu_launches)
+extern unsigned long long g_caspr_launches;
+#define CASPR_COUNT() (++g_caspr_launches)
+
+// optional CUDA-event timing of selected kernels (caspr_profile_* in misc.cu)
+void caspr_prof_begin(int kernel_id, cudaStream_t s);
+void caspr_prof_end(int kernel_id, cudaStream_t s);
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

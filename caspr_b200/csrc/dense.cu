@@ -311,16 +311,16 @@ extern "C" int caspr_linear(const float* X, int ldx, const float* W, int ldw, co
   cudaStream_t s = (cudaStream_t)stream;
   if (Cout > 64) {
     dim3 grid(ceil_div(rows, 128), ceil_div(Cout, 128));
-    linear_kernel<128, 128><<<grid, 256, 0, s>>>(X, ldx, W, ldw, bias, Y, ldy, rows, Cin, Cout, act_in, act_out);
+    CASPR_COUNT(); linear_kernel<128, 128><<<grid, 256, 0, s>>>(X, ldx, W, ldw, bias, Y, ldy, rows, Cin, Cout, act_in, act_out);
   } else if (Cout > 32) {
     dim3 grid(ceil_div(rows, 128), ceil_div(Cout, 64));
-    linear_kernel<128, 64><<<grid, 256, 0, s>>>(X, ldx, W, ldw, bias, Y, ldy, rows, Cin, Cout, act_in, act_out);
+    CASPR_COUNT(); linear_kernel<128, 64><<<grid, 256, 0, s>>>(X, ldx, W, ldw, bias, Y, ldy, rows, Cin, Cout, act_in, act_out);
   } else if (Cout > 16) {
     dim3 grid(ceil_div(rows, 128), ceil_div(Cout, 32));
-    linear_kernel<128, 32><<<grid, 256, 0, s>>>(X, ldx, W, ldw, bias, Y, ldy, rows, Cin, Cout, act_in, act_out);
+    CASPR_COUNT(); linear_kernel<128, 32><<<grid, 256, 0, s>>>(X, ldx, W, ldw, bias, Y, ldy, rows, Cin, Cout, act_in, act_out);
   } else {
     dim3 grid(ceil_div(rows, 128), 1);
-    linear_kernel<128, 16><<<grid, 256, 0, s>>>(X, ldx, W, ldw, bias, Y, ldy, rows, Cin, Cout, act_in, act_out);
+    CASPR_COUNT(); linear_kernel<128, 16><<<grid, 256, 0, s>>>(X, ldx, W, ldw, bias, Y, ldy, rows, Cin, Cout, act_in, act_out);
   }
   CASPR_CHECK_LAUNCH();
   return CASPR_OK;
@@ -342,7 +342,7 @@ extern "C" int caspr_groupnorm(float* X, int ldx, int samples, int rows_per_samp
                                96 * 1024) != cudaSuccess)
         return CASPR_EINVAL;
     }
-    groupnorm_small_kernel<<<samples, 256, tile_bytes, s>>>(X, ldx, rows_per_sample, C, groups, gamma,
+    CASPR_COUNT(); groupnorm_small_kernel<<<samples, 256, tile_bytes, s>>>(X, ldx, rows_per_sample, C, groups, gamma,
                                                             beta, eps, relu, write_back, maxout, ld_max);
     CASPR_CHECK_LAUNCH();
     return CASPR_OK;
@@ -351,18 +351,18 @@ extern "C" int caspr_groupnorm(float* X, int ldx, int samples, int rows_per_samp
   if (cudaMemsetAsync(stats_ws, 0, (size_t)samples * groups * 2 * sizeof(double), s) != cudaSuccess)
     return CASPR_ELAUNCH;
   dim3 grid(ceil_div(rows_per_sample, kGnRowsPerCta), samples);
-  groupnorm_stats_kernel<<<grid, 256, 0, s>>>(X, ldx, rows_per_sample, C, groups, stats_ws);
+  CASPR_COUNT(); groupnorm_stats_kernel<<<grid, 256, 0, s>>>(X, ldx, rows_per_sample, C, groups, stats_ws);
   CASPR_CHECK_LAUNCH();
   unsigned* mo = reinterpret_cast<unsigned*>(maxout);
   if (mo) {
-    fill_u32_kernel<<<ceil_div(samples * C, 256), 256, 0, s>>>(mo, samples, C, ld_max, 0u);
+    CASPR_COUNT(); fill_u32_kernel<<<ceil_div(samples * C, 256), 256, 0, s>>>(mo, samples, C, ld_max, 0u);
     CASPR_CHECK_LAUNCH();
   }
-  groupnorm_apply_kernel<<<grid, 256, 0, s>>>(X, ldx, rows_per_sample, C, groups, gamma, beta, eps, relu,
+  CASPR_COUNT(); groupnorm_apply_kernel<<<grid, 256, 0, s>>>(X, ldx, rows_per_sample, C, groups, gamma, beta, eps, relu,
                                              write_back, stats_ws, mo, ld_max);
   CASPR_CHECK_LAUNCH();
   if (mo) {
-    decode_ordered_kernel<<<ceil_div(samples * C, 256), 256, 0, s>>>(mo, samples, C, ld_max);
+    CASPR_COUNT(); decode_ordered_kernel<<<ceil_div(samples * C, 256), 256, 0, s>>>(mo, samples, C, ld_max);
     CASPR_CHECK_LAUNCH();
   }
   return CASPR_OK;
@@ -370,14 +370,14 @@ extern "C" int caspr_groupnorm(float* X, int ldx, int samples, int rows_per_samp
 
 extern "C" int caspr_augment_xyz(const float* x4, int rows, float* out9, void* stream) {
   CASPR_REQUIRE(x4 && out9 && rows > 0 && ((uintptr_t)x4 & 15) == 0);
-  augment_xyz_kernel<<<ceil_div(rows, 256), 256, 0, (cudaStream_t)stream>>>(x4, rows, out9);
+  CASPR_COUNT(); augment_xyz_kernel<<<ceil_div(rows, 256), 256, 0, (cudaStream_t)stream>>>(x4, rows, out9);
   CASPR_CHECK_LAUNCH();
   return CASPR_OK;
 }
 
 extern "C" int caspr_strip_time(const float* x4, int rows, float* xyz3, void* stream) {
   CASPR_REQUIRE(x4 && xyz3 && rows > 0 && ((uintptr_t)x4 & 15) == 0);
-  strip_time_kernel<<<ceil_div(rows, 256), 256, 0, (cudaStream_t)stream>>>(x4, rows, xyz3);
+  CASPR_COUNT(); strip_time_kernel<<<ceil_div(rows, 256), 256, 0, (cudaStream_t)stream>>>(x4, rows, xyz3);
   CASPR_CHECK_LAUNCH();
   return CASPR_OK;
 }
@@ -387,7 +387,7 @@ extern "C" int caspr_broadcast_rows(const float* src, int ld_src, int samples, i
   CASPR_REQUIRE(src && dst && samples > 0 && rows_per_sample > 0 && C > 0 && ld_src >= C && ld_dst >= C);
   long long total = (long long)samples * rows_per_sample * C;
   int blocks = (int)((total + 255) / 256 < 148LL * 32 ? (total + 255) / 256 : 148LL * 32);
-  broadcast_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, ld_src, rows_per_sample, C, total,
+  CASPR_COUNT(); broadcast_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, ld_src, rows_per_sample, C, total,
                                                                    dst, ld_dst);
   CASPR_CHECK_LAUNCH();
   return CASPR_OK;

@@ -114,7 +114,7 @@ int launch_fps(const float* xyz, int B, int N, int M, int32_t* idx, float* new_x
                              (int)smem) != cudaSuccess)
       return CASPR_EINVAL;
   }
-  fps_kernel<THREADS, PPT><<<B, THREADS, smem, s>>>(xyz, N, M, idx, new_xyz);
+  CASPR_COUNT(); fps_kernel<THREADS, PPT><<<B, THREADS, smem, s>>>(xyz, N, M, idx, new_xyz);
   CASPR_CHECK_LAUNCH();
   return CASPR_OK;
 }
@@ -307,7 +307,7 @@ extern "C" int caspr_ball_query2(const float* xyz, const float* new_xyz, int B, 
   }
   const float r0sq = r0 * r0, r1sq = r1 * r1;     // fp32, as upstream / the oracle
   dim3 grid(ceil_div(M, kBqCentresPerCta), B);
-  ball_query2_kernel<<<grid, kBqThreads, smem, (cudaStream_t)stream>>>(
+  CASPR_COUNT(); ball_query2_kernel<<<grid, kBqThreads, smem, (cudaStream_t)stream>>>(
       xyz, new_xyz, N, M, r0sq, ns0, idx0, r1sq, ns1, idx1);
   CASPR_CHECK_LAUNCH();
   return CASPR_OK;
@@ -320,7 +320,7 @@ extern "C" int caspr_group_points(const float* xyz, const float* new_xyz, const 
   CASPR_REQUIRE((C == 0 || (feat && ld_feat >= C)) && ld_out >= 3 + C);
   long long rows = (long long)B * M * ns;
   int blocks = (int)((rows + 7) / 8 < 148LL * 16 ? (rows + 7) / 8 : 148LL * 16);
-  group_points_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(xyz, new_xyz, feat, ld_feat, idx, N, M, C, ns,
+  CASPR_COUNT(); group_points_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(xyz, new_xyz, feat, ld_feat, idx, N, M, C, ns,
                                                                   rows, out, ld_out);
   CASPR_CHECK_LAUNCH();
   return CASPR_OK;
@@ -336,7 +336,7 @@ extern "C" int caspr_three_nn(const float* unknown, const float* known, int B, i
       return CASPR_EINVAL;
   }
   dim3 grid(ceil_div(n, kNnThreads), B);
-  three_nn_kernel<<<grid, kNnThreads, smem, (cudaStream_t)stream>>>(unknown, known, n, m, dist, idx);
+  CASPR_COUNT(); three_nn_kernel<<<grid, kNnThreads, smem, (cudaStream_t)stream>>>(unknown, known, n, m, dist, idx);
   CASPR_CHECK_LAUNCH();
   return CASPR_OK;
 }
@@ -349,7 +349,7 @@ extern "C" int caspr_three_interp_concat(const float* feat_prev, int ld_prev, co
   CASPR_REQUIRE((Cs == 0 || skip) && ld_out >= Cp + Cs && ld_prev >= Cp && (Cs == 0 || ld_skip >= Cs));
   long long rows = (long long)B * n;
   int blocks = (int)((rows + 7) / 8 < 148LL * 16 ? (rows + 7) / 8 : 148LL * 16);
-  three_interp_concat_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+  CASPR_COUNT(); three_interp_concat_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
       feat_prev, ld_prev, idx, dist, skip, ld_skip, n, m, Cp, Cs, rows, out, ld_out);
   CASPR_CHECK_LAUNCH();
   return CASPR_OK;

@@ -250,7 +250,7 @@ extern "C" int caspr_latent_ode_solve(const float* z0, int B, int D, int H, cons
   p.W[0] = W0; p.W[1] = W1; p.W[2] = W2; p.W[3] = W3;
   p.b[0] = b0; p.b[1] = b1; p.b[2] = b2; p.b[3] = b3;
   p.B = B; p.D = D; p.H = H;
-  latent_ode_kernel<<<1, kThreads, 0, s>>>(p, z0, d_times, nT, rtol, atol, out, info, ws, 100000);
+  CASPR_COUNT(); latent_ode_kernel<<<1, kThreads, 0, s>>>(p, z0, d_times, nT, rtol, atol, out, info, ws, 100000);
   CASPR_CHECK_LAUNCH();
   if (cudaMemcpyAsync(h_info, info, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, s) != cudaSuccess)
     return CASPR_ELAUNCH;

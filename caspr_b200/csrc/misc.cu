@@ -17,6 +17,65 @@ extern "C" const char* caspr_status_string(int status) {
   }
 }
 
+// ------------------------------------------------------------------ launch count / profiling
+unsigned long long g_caspr_launches = 0;
+extern "C" unsigned long long caspr_launch_count(void) { return g_caspr_launches; }
+
+namespace {
+constexpr int kProfKernels = 8;
+constexpr int kProfMaxPairs = 16384;
+struct ProfSlot {
+  cudaEvent_t beg[kProfMaxPairs], end[kProfMaxPairs];
+  int created = 0, used = 0;
+  long long dropped = 0;
+};
+ProfSlot* g_prof[kProfKernels] = {nullptr};
+int g_prof_on = 0;
+}  // namespace
+
+void caspr_prof_begin(int id, cudaStream_t s) {
+  if (!g_prof_on || id < 0 || id >= kProfKernels) return;
+  if (!g_prof[id]) g_prof[id] = new ProfSlot();
+  ProfSlot* p = g_prof[id];
+  if (p->used >= kProfMaxPairs) { p->dropped++; return; }
+  if (p->used >= p->created) {
+    cudaEventCreate(&p->beg[p->created]);
+    cudaEventCreate(&p->end[p->created]);
+    p->created++;
+  }
+  cudaEventRecord(p->beg[p->used], s);
+}
+void caspr_prof_end(int id, cudaStream_t s) {
+  if (!g_prof_on || id < 0 || id >= kProfKernels || !g_prof[id]) return;
+  ProfSlot* p = g_prof[id];
+  if (p->used >= kProfMaxPairs) return;
+  cudaEventRecord(p->end[p->used], s);
+  p->used++;
+}
+
+extern "C" void caspr_profile_enable(int on) {
+  g_prof_on = on ? 1 : 0;
+  if (on)
+    for (int i = 0; i < kProfKernels; ++i)
+      if (g_prof[i]) { g_prof[i]->used = 0; g_prof[i]->dropped = 0; }
+}
+
+extern "C" int caspr_profile_read(int kernel_id, double* total_ms, long long* launches) {
+  CASPR_REQUIRE(kernel_id >= 0 && kernel_id < kProfKernels && total_ms && launches);
+  *total_ms = 0.0;
+  *launches = 0;
+  ProfSlot* p = g_prof[kernel_id];
+  if (!p) return CASPR_OK;
+  for (int i = 0; i < p->used; ++i) {
+    if (cudaEventSynchronize(p->end[i]) != cudaSuccess) return CASPR_ELAUNCH;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p->beg[i], p->end[i]) != cudaSuccess) return CASPR_ELAUNCH;
+    *total_ms += (double)ms;
+  }
+  *launches = p->used;
+  return CASPR_OK;
+}
+
 namespace {
 
 // Squared nearest-neighbour distance from every point of `a` to the cloud `b` (one direction of
@@ -56,8 +115,8 @@ extern "C" int caspr_chamfer(const float* a, const float* b, int B, int P, int Q
                              float* d_ba, void* stream) {
   CASPR_REQUIRE(a && b && B > 0 && P > 0 && Q > 0 && (d_ab || d_ba));
   cudaStream_t s = (cudaStream_t)stream;
-  if (d_ab) chamfer_dir_kernel<<<dim3(ceil_div(P, 256), B), 256, 0, s>>>(a, b, P, Q, d_ab);
-  if (d_ba) chamfer_dir_kernel<<<dim3(ceil_div(Q, 256), B), 256, 0, s>>>(b, a, Q, P, d_ba);
+  if (d_ab) { CASPR_COUNT(); chamfer_dir_kernel<<<dim3(ceil_div(P, 256), B), 256, 0, s>>>(a, b, P, Q, d_ab); }
+  if (d_ba) { CASPR_COUNT(); chamfer_dir_kernel<<<dim3(ceil_div(Q, 256), B), 256, 0, s>>>(b, a, Q, P, d_ba); }
   CASPR_CHECK_LAUNCH();
   return CASPR_OK;
 }

@@ -41,6 +41,17 @@ int caspr_version(void);                    /* e.g. 100 = 0.1.0                 
 const char* caspr_build_arch(void);         /* "sm_100a"                              */
 const char* caspr_status_string(int status);
 
+/* Number of kernels the library has launched in this process (bench.py: gpu_launches). */
+unsigned long long caspr_launch_count(void);
+
+/* CUDA-event timing of the dominant kernels, measured on the stream they are launched on.
+ * caspr_profile_enable(1) clears the records and starts recording one event pair around every
+ * launch of the kernels below; caspr_profile_read waits for the recorded events and returns the
+ * summed device time and the number of launches recorded. */
+enum { CASPR_PROF_CNF_MID_SIMT = 0, CASPR_PROF_CNF_FUSED_TC = 1, CASPR_PROF_LINEAR = 2, CASPR_PROF_FPS = 3 };
+void caspr_profile_enable(int on);
+int caspr_profile_read(int kernel_id, double* total_ms, long long* launches);
+
 /* ------------------------------------------------------------------ geometry
  * Replaces the Kaolin ops imported at pointnet2.py:7-10.  Arithmetic is the
  * declared canonical one of oracle/pointnet2_ops.py: d2 = ((dx*dx)+(dy*dy))+(dz*dz)

@@ -1,0 +1,299 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the fixtures frozen
+from the reference modules.  Integer / index work must be bit-exact; floating point is held to the
+tolerance stated in each test (north_star: reconstructed coordinates within 1e-4 relative)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from caspr_b200.synth import synthetic_state_dict, synthetic_sequences   # noqa: E402
+from oracle import pointnet2_ops as pn2                                   # noqa: E402
+from oracle.caspr_oracle import CasprOracle, chamfer_distance             # noqa: E402
+
+DEV = 'cuda:0'
+
+
+@pytest.fixture(scope='module')
+def ops(lib_built):
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    from caspr_b200 import ops as _ops
+    return _ops
+
+
+def _rel(a, b):
+    a = a.detach().cpu().double().numpy() if torch.is_tensor(a) else np.asarray(a, dtype=np.float64)
+    b = b.detach().cpu().double().numpy() if torch.is_tensor(b) else np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-12)
+
+
+def _clouds(B, N, seed, kind='camera'):
+    x, nocs = synthetic_sequences(B, 1, N, seed=seed)
+    src = x if kind == 'camera' else nocs
+    return src[:, 0, :, :3].contiguous()
+
+
+# ------------------------------------------------------------------------------ geometry
+@pytest.mark.parametrize('N,M', [(2048, 1024), (1024, 1024), (1024, 512), (512, 256), (256, 64), (64, 16),
+                                 (1000, 333), (37, 5)])
+def test_fps_bit_exact(ops, N, M):
+    for kind in ('camera', 'nocs'):          # NOCS clouds exercise the |p|^2 <= 1e-3 skip rule
+        xyz = _clouds(3, N, seed=N + M, kind=kind)
+        ref = pn2.furthest_point_sampling(xyz, M)
+        idx, new_xyz = ops.fps(xyz.to(DEV), M)
+        assert torch.equal(idx.cpu(), ref)
+        gathered = torch.gather(xyz, 1, ref.long().unsqueeze(-1).expand(-1, -1, 3))
+        assert torch.equal(new_xyz.cpu(), gathered)
+
+
+def test_fps_duplicates_and_origin_points(ops):
+    g = torch.Generator().manual_seed(0)
+    xyz = torch.rand(2, 300, 3, generator=g)
+    xyz[:, 50:80] = xyz[:, 10:40]             # exact duplicates -> ties resolved to the lowest index
+    xyz[:, 100:120] = 0.01 * torch.rand(2, 20, 3, generator=g)   # inside the origin-skip radius
+    ref = pn2.furthest_point_sampling(xyz, 128)
+    idx, _ = ops.fps(xyz.to(DEV), 128)
+    assert torch.equal(idx.cpu(), ref)
+
+
+@pytest.mark.parametrize('N,M,r0,r1', [(2048, 1024, .02, .05), (1024, 512, .05, .1), (512, 256, .1, .2),
+                                       (256, 64, .2, .4), (64, 16, .4, .8), (300, 77, .03, .3)])
+def test_ball_query_bit_exact(ops, N, M, r0, r1):
+    xyz = _clouds(2, N, seed=7 * N + M)
+    new_xyz = torch.gather(xyz, 1, pn2.furthest_point_sampling(xyz, M).long().unsqueeze(-1).expand(-1, -1, 3))
+    i0, i1 = ops.ball_query2(xyz.to(DEV), new_xyz.to(DEV), r0, 16, r1, 32)
+    assert torch.equal(i0.cpu(), pn2.ball_query(r0, 16, xyz, new_xyz))
+    assert torch.equal(i1.cpu(), pn2.ball_query(r1, 32, xyz, new_xyz))
+
+
+def test_ball_query_empty_balls(ops):
+    """Centres far from every point: no hit -> all slots 0 (upstream zero-initialised output)."""
+    xyz = _clouds(1, 128, seed=3)
+    new_xyz = xyz[:, :8] + 10.0
+    i0, i1 = ops.ball_query2(xyz.to(DEV), new_xyz.to(DEV), .02, 16, .05, 32)
+    assert torch.equal(i0.cpu(), pn2.ball_query(.02, 16, xyz, new_xyz))
+    assert int(i1.abs().sum()) == 0
+
+
+def test_group_points_exact(ops):
+    xyz = _clouds(2, 512, seed=11)
+    g = torch.Generator().manual_seed(1)
+    feat = torch.randn(2, 512, 21, generator=g)
+    idx = pn2.furthest_point_sampling(xyz, 128)
+    new_xyz = torch.gather(xyz, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3))
+    bq = pn2.ball_query(0.1, 16, xyz, new_xyz)
+    layer = pn2.PointNet2GroupingLayer(0.1, 16)
+    ref = layer(xyz, new_xyz, feat.transpose(1, 2).contiguous())          # (B,M,3+C,ns)
+    ref_rows = ref.permute(0, 1, 3, 2).reshape(2 * 128 * 16, 24)
+    out = ops.group_points(xyz.to(DEV), new_xyz.to(DEV), feat.to(DEV), bq.to(DEV))
+    assert torch.equal(out.cpu(), ref_rows)
+
+
+@pytest.mark.parametrize('n,m', [(2048, 1024), (1024, 512), (256, 64), (64, 16), (100, 3)])
+def test_three_nn_and_interpolate(ops, n, m):
+    unknown = _clouds(2, n, seed=n)
+    known = unknown[:, :m].contiguous() + 0.001
+    dist_ref, idx_ref = pn2.three_nn(unknown, known)
+    dist, idx = ops.three_nn(unknown.to(DEV), known.to(DEV))
+    assert torch.equal(idx.cpu(), idx_ref)
+    assert torch.equal(dist.cpu(), dist_ref)                              # sqrt of identical fp32 d2
+    g = torch.Generator().manual_seed(2)
+    fprev = torch.randn(2, m, 40, generator=g)
+    skip = torch.randn(2, n, 6, generator=g)
+    inv = 1.0 / (dist_ref + 1e-8)
+    w = inv / inv.sum(2, keepdim=True)
+    ref = pn2.three_interpolate(fprev.transpose(1, 2).contiguous(), idx_ref, w)      # (B,C,n)
+    ref_rows = torch.cat([ref.transpose(1, 2), skip], dim=2).reshape(2 * n, 46)
+    out = ops.three_interp_concat(fprev.to(DEV), idx, dist, skip.to(DEV))
+    assert _rel(out, ref_rows) < 1e-6
+
+
+# ------------------------------------------------------------------------------ dense ops
+@pytest.mark.parametrize('rows,cin,cout', [(1000, 9, 16), (513, 99, 32), (300, 131, 64), (257, 515, 256),
+                                           (129, 1600, 1600), (64, 4, 64), (77, 1600, 4)])
+def test_linear_matches_fp32(ops, rows, cin, cout):
+    g = torch.Generator().manual_seed(rows)
+    x = torch.randn(rows, cin, generator=g)
+    w = torch.randn(cout, cin, generator=g) / cin ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    out = ops.linear(x.to(DEV), w.to(DEV), b.to(DEV))
+    assert _rel(out, ref) < 2e-6
+    out2 = ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), act_in=ops.ACT_RELU, act_out=ops.ACT_SIGMOID)
+    ref2 = torch.sigmoid(torch.nn.functional.linear(x.double().relu(), w.double(), b.double()))
+    assert _rel(out2, ref2) < 2e-6
+
+
+def test_linear_strided_views(ops):
+    g = torch.Generator().manual_seed(5)
+    buf = torch.randn(200, 96, generator=g).to(DEV)
+    w = torch.randn(24, 40, generator=g).to(DEV)
+    out = torch.zeros(200, 64, device=DEV)
+    ops.linear(buf[:, 8:48], w, None, out=out[:, 16:40])
+    ref = buf[:, 8:48].double() @ w.double().t()
+    assert _rel(out[:, 16:40], ref) < 2e-6
+    assert float(out[:, :16].abs().sum()) == 0 and float(out[:, 40:].abs().sum()) == 0
+
+
+@pytest.mark.parametrize('samples,rps,C,relu', [(50, 16, 16, True), (40, 32, 64, True), (9, 32, 512, False),
+                                                (3, 2048, 512, True), (2, 3000, 1600, False), (2, 64, 512, True)])
+def test_groupnorm_matches_torch(ops, samples, rps, C, relu):
+    g = torch.Generator().manual_seed(C + rps)
+    x = torch.randn(samples * rps, C, generator=g) * 2 + 0.5
+    gamma = torch.rand(C, generator=g) + 0.5
+    beta = torch.randn(C, generator=g) * 0.1
+    xin = x.view(samples, rps, C).transpose(1, 2).double()                # (samples, C, rps)
+    ref = torch.nn.functional.group_norm(xin, 16, gamma.double(), beta.double(), eps=1e-5)
+    if relu:
+        ref = ref.relu()
+    ref_rows = ref.transpose(1, 2).reshape(samples * rps, C)
+    xd = x.to(DEV).clone()
+    mx = torch.empty(samples, C, device=DEV)
+    ops.groupnorm(xd, samples, rps, 16, gamma.to(DEV), beta.to(DEV), relu=relu, maxout=mx)
+    assert _rel(xd, ref_rows) < 1e-5
+    assert _rel(mx, ref.max(2)[0]) < 1e-5
+    xd2 = x.to(DEV).clone()
+    mx2 = torch.empty(samples, C, device=DEV)
+    ops.groupnorm(xd2, samples, rps, 16, gamma.to(DEV), beta.to(DEV), relu=relu, write_back=False, maxout=mx2)
+    assert torch.equal(xd2.cpu(), x)                                      # untouched
+    assert _rel(mx2, ref.max(2)[0]) < 1e-5
+
+
+def test_augment_and_broadcast(ops):
+    x, _ = synthetic_sequences(1, 2, 100, seed=0)
+    x4 = x.view(-1, 4)
+    sp = x4[:, :3]
+    ref = torch.cat([sp, sp * sp, sp[:, 0:1] * sp[:, 2:3], sp[:, 0:1] * sp[:, 1:2], sp[:, 2:3] * sp[:, 1:2]], 1)
+    assert torch.equal(ops.augment_xyz(x4.to(DEV)).cpu(), ref)
+    assert torch.equal(ops.strip_time(x4.to(DEV)).cpu(), sp)
+    src = torch.randn(3, 20).to(DEV)
+    dst = torch.zeros(3 * 7, 32, device=DEV)
+    ops.broadcast_rows(src, 7, dst[:, 4:24])
+    assert torch.equal(dst[:, 4:24].view(3, 7, 20), src.unsqueeze(1).expand(3, 7, 20))
+
+
+def test_chamfer(ops):
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.rand(3, 700, 3, generator=g), torch.rand(3, 1500, 3, generator=g)
+    d_ab, d_ba = ops.chamfer(a.to(DEV), b.to(DEV))
+    cd = d_ab.mean(1) + d_ba.mean(1)
+    assert _rel(cd, chamfer_distance(a, b)) < 1e-5
+
+
+# ---------------------------------------------------------------------------- model level
+@pytest.fixture(scope='module', params=['vig', 'def'])
+def case(request, golden_dir, lib_built):
+    from caspr_b200.models import CaSPR
+    tag = request.param
+    gold = dict(np.load(os.path.join(golden_dir, 'caspr_%s.npz' % tag)))
+    sd = synthetic_state_dict(0, cnf_init='vigorous' if tag == 'vig' else 'default')
+    model = CaSPR().to(DEV).eval()
+    model.load_state_dict(sd)
+    x, nocs = synthetic_sequences(1, 3, 1024, seed=1)
+    return tag, gold, model, CasprOracle(sd), x, nocs
+
+
+def test_encoder_indices_and_features(case):
+    """FPS / ball-query indices of every level are bit-exact vs the reference fixture; z0 and T-NOCS
+    within 1e-4 relative."""
+    _, gold, model, _, x, _ = case
+    model.encoder.trace = {}
+    z0, tnocs = model.encode(x.to(DEV))
+    tr = model.encoder.trace
+    model.encoder.trace = None
+    for lvl in range(5):
+        assert np.array_equal(tr['fps_idx'][lvl].cpu().numpy(), gold['fps_idx_%d' % lvl])
+    for lvl in (0, 2, 4):
+        assert np.array_equal(tr['ball_idx'][lvl][1].cpu().numpy(), gold['ball_idx_%d_1' % lvl])
+    assert _rel(z0, gold['z0']) < 1e-4
+    assert _rel(tnocs, gold['tnocs']) < 1e-4
+
+
+def test_latent_ode_matches_oracle(case):
+    _, gold, model, oracle, _, _ = case
+    z0 = torch.from_numpy(gold['z0'])
+    t = torch.tensor([0.0, 0.1, 0.35, 0.5, 1.0])
+    ref = oracle.latent_ode(z0[:, :64], t)
+    out = model.latent_ode(z0[:, :64].to(DEV), t.to(DEV))
+    assert int(model.latent_ode.num_evals()) == oracle.nfe[0]
+    assert _rel(out, ref) < 1e-5
+
+
+def test_cnf_feval_matches_oracle(case, ops):
+    """One dynamics evaluation (dy, -div): forward-mode divergence vs the reference's autograd VJP."""
+    _, gold, model, oracle, _, _ = case
+    g = torch.Generator().manual_seed(3)
+    y = torch.randn(3, 200, 3, generator=g)
+    e = torch.randn(3, 200, 3, generator=g)
+    ctx = 0.5 * torch.randn(3, 1600, generator=g)
+    dy_ref, nd_ref, _ = oracle.odefunc(torch.tensor(0.37), (y, torch.zeros(3, 200, 1), ctx), e)
+    pack = model.point_cnf.chain[1].weight_pack()
+    dy, nd = ops.cnf_feval(y.to(DEV), e.to(DEV), ctx.to(DEV), pack, 0.37)
+    assert _rel(dy, dy_ref) < 1e-5
+    assert _rel(nd, nd_ref.squeeze(-1)) < 1e-4
+
+
+def test_reconstruct_matches_reference_fixture(case):
+    _, gold, model, _, x, _ = case
+    y = torch.from_numpy(gold['rec_y'])
+    e = torch.from_numpy(gold['rec_e']).to(DEV)
+    yy, logp_y, xr, tnocs = model.reconstruct(x.to(DEV), num_points=256, y=y.reshape(3, 256, 3), e=e)
+    assert list(model.get_nfe().astype(int)) == list(gold['rec_nfe'].astype(int))
+    assert _rel(xr, gold['rec_x']) < 1e-4                       # north_star tolerance
+    assert _rel(logp_y, gold['rec_logp_y']) < 1e-5
+    cd = chamfer_distance(xr.cpu().view(3, 256, 3), torch.from_numpy(gold['rec_x']).view(3, 256, 3))
+    assert float(cd.max()) < 1e-8
+
+
+def test_interpolated_reconstruct_matches_reference_fixture(case):
+    _, gold, model, _, x, _ = case
+    y = torch.from_numpy(gold['interp_y'])[:, 0]
+    e = torch.from_numpy(gold['interp_e']).to(DEV)
+    _, _, xr, _ = model.reconstruct(x.to(DEV), num_points=128, constant_in_time=True,
+                                    timestamps=torch.linspace(0, 1, 5).to(DEV), y=y, e=e)
+    assert list(model.get_nfe().astype(int)) == list(gold['interp_nfe'].astype(int))
+    assert _rel(xr, gold['interp_x']) < 1e-4
+
+
+def test_decode_matches_reference_fixture(case):
+    _, gold, model, _, _, _ = case
+    z = torch.from_numpy(gold['dec_z']).to(DEV)
+    _, _, xd = model.decode(z, num_points=512, y=torch.from_numpy(gold['dec_y']).reshape(1, 512, 3),
+                            e=torch.from_numpy(gold['dec_e']).to(DEV))
+    assert int(model.get_nfe()[1]) == int(gold['dec_nfe'][1])
+    assert _rel(xd, gold['dec_x']) < 1e-4
+
+
+def test_forward_nll_matches_reference_fixture(case):
+    _, gold, model, _, x, nocs = case
+    nll, tl = model(x.to(DEV), nocs.to(DEV), e=torch.from_numpy(gold['fwd_e']).to(DEV))
+    assert list(model.get_nfe().astype(int)) == list(gold['fwd_nfe'].astype(int))
+    assert _rel(nll, gold['fwd_nll']) < 1e-3
+    assert abs(float(tl.mean()) - float(gold['fwd_tnocs_l1_mean'])) < 1e-5
+
+
+def test_flow_round_trip(case):
+    """Size-independent property: decode (reverse flow) then encode (forward flow) returns the base
+    samples to solver tolerance, and the log-density change is consistent."""
+    _, _, model, _, _, _ = case
+    g = torch.Generator().manual_seed(8)
+    F, P = 4, 512
+    ctx = (0.5 * torch.randn(F, 1600, generator=g)).to(DEV)
+    y = torch.randn(F, P, 3, generator=g).to(DEV)
+    e = torch.randn(F, P, 3, generator=g).to(DEV)
+    x = model.point_cnf(y, ctx, reverse=True, e=e)
+    y2, dlogp = model.point_cnf(x, ctx, torch.zeros(F, P, 1, device=DEV), e=e)
+    assert _rel(y2, y) < 2e-3
+    assert torch.isfinite(dlogp).all()
+
+
+def test_solver_failure_is_reported(case, ops):
+    """Non-finite inputs surface as the solver's status (torchdiffeq asserts), not as silent garbage."""
+    from caspr_b200._lib import CasprError
+    _, _, model, _, _, _ = case
+    ctx = torch.zeros(1, 1600, device=DEV)
+    y = torch.full((1, 64, 3), float('nan'), device=DEV)
+    with pytest.raises(CasprError):
+        model.point_cnf(y, ctx, reverse=True, e=torch.ones(1, 64, 3, device=DEV))
