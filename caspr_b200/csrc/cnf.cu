@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "dopri5.cuh"
 #include "cnf_state.cuh"
+#include "cnf_tc.cuh"
 
 namespace {
 
@@ -90,8 +91,8 @@ __global__ void __launch_bounds__(256)
 cnf_hyper_stage_kernel(const float* __restrict__ Gc, const float* __restrict__ Bc,
                        const float* __restrict__ wg_t, const float* __restrict__ wb_t,
                        const float* __restrict__ lbias, int frames, int ctot, int ld, int stage,
-                       int reverse, const CnfState* __restrict__ st, float* __restrict__ gate,
-                       float* __restrict__ biasf) {
+                       int reverse, const CnfState* __restrict__ st, const float* __restrict__ col_scale,
+                       float* __restrict__ gate, float* __restrict__ biasf) {
   if (st->done) return;
   // stage time exactly as torchdiffeq forms it: ti = t0.to(fp32) + alpha_i * dt.to(fp32); the
   // dynamics see -ti when integrating backwards (odeint001.odeint negates time).
@@ -104,7 +105,8 @@ cnf_hyper_stage_kernel(const float* __restrict__ Gc, const float* __restrict__ B
   const int j = (int)(i % ld);
   if (j >= ctot) return;
   const float g = 1.f / (1.f + expf(-(Gc[i] + wg_t[j] * t)));
-  gate[i] = g;
+  // the tensor-core engine folds its exact power-of-two operand scales into the gate it reads
+  gate[i] = col_scale ? g * col_scale[j] : g;
   biasf[i] = lbias[j] * g + (Bc[i] + wb_t[j] * t);
 }
 
@@ -538,13 +540,17 @@ struct CnfWorkspace {
   float *Gc, *Bc, *gate, *biasf;       // frames x ctot
   float *wg_t, *wb_t, *lbias;          // ctot
   float4 *y0, *y1, *kbuf;              // n, n, 7n
-  float *Ha, *Va, *Hb, *Vb;            // n x H each
+  float *Ha, *Va, *Hb, *Vb;            // n_pad x H each (the tensor-core engine reuses them as fp16 planes)
+  float* col_scale;                    // ctot (tensor-core engine)
+  int* range_flag;
+  cnf_tc::Weights tcw;
   size_t bytes;
 };
 
 CnfWorkspace carve(void* base, int frames, int pts, int H) {
   CnfWorkspace w;
   const size_t n = (size_t)frames * pts;
+  const size_t n_pad = (n + 63) / 64 * 64;
   const size_t ctot = hyper_ld(H);
   char* p = (char*)base;
   auto take = [&](size_t bytes) { char* r = p; p += align_up(bytes, 256); return r; };
@@ -559,10 +565,18 @@ CnfWorkspace carve(void* base, int frames, int pts, int H) {
   w.y0 = (float4*)take(n * 16);
   w.y1 = (float4*)take(n * 16);
   w.kbuf = (float4*)take(7 * n * 16);
-  w.Ha = (float*)take(n * H * 4);
-  w.Va = (float*)take(n * H * 4);
-  w.Hb = (float*)take(n * H * 4);
-  w.Vb = (float*)take(n * H * 4);
+  w.Ha = (float*)take(n_pad * H * 4);
+  w.Va = (float*)take(n_pad * H * 4);
+  w.Hb = (float*)take(n_pad * H * 4);
+  w.Vb = (float*)take(n_pad * H * 4);
+  w.col_scale = (float*)take(ctot * 4);
+  w.range_flag = (int*)take(256);
+  for (int l = 0; l < 2; ++l) {
+    w.tcw.hi[l] = (__half*)take((size_t)512 * 512 * 2);
+    w.tcw.lo[l] = (__half*)take((size_t)512 * 512 * 2);
+  }
+  w.tcw.scales = (float*)take(256);
+  w.tcw.max_bits = (unsigned*)take(256);
   w.bytes = (size_t)(p - (char*)base);
   return w;
 }
@@ -609,29 +623,62 @@ int prepare_hyper(const CnfWorkspace& w, const caspr_cnf_weights* cw, const floa
 
 // One dynamics evaluation into kbuf[stage] (stage 0 = f at the step start / f0).
 int enqueue_feval(const CnfWorkspace& w, const caspr_cnf_weights* cw, const float* e, int frames,
-                  int pts, int stage, int reverse, cudaStream_t s) {
+                  int pts, int stage, int reverse, int engine, const cnf_tc::Plan* plan, int num_sms,
+                  cudaStream_t s) {
   const int H = cw->hidden;
   const int n = frames * pts;
   const int ctot = hyper_ld(H);
   const long long tot = (long long)frames * ctot;
+  const bool use_tc = engine == CASPR_CNF_TC_FP16X3;
   CASPR_COUNT(); cnf_hyper_stage_kernel<<<(int)((tot + 255) / 256), 256, 0, s>>>(
-      w.Gc, w.Bc, w.wg_t, w.wb_t, w.lbias, frames, 3 * H + 3, ctot, stage, reverse, w.st, w.gate, w.biasf);
-  CASPR_COUNT(); cnf_layer0_kernel<<<blocks_for(n, 8, 148 * 16), 256, 0, s>>>(
-      w.y0, w.kbuf, (size_t)n, e, cw->W[0], H, n, pts, stage, w.gate, w.biasf, ctot, w.st, w.Ha, w.Va);
-  dim3 grid(ceil_div(n, kMidBM), H / kMidBN);
-  caspr_prof_begin(CASPR_PROF_CNF_MID_SIMT, s);
-  CASPR_COUNT(); cnf_mid_layer_kernel<<<grid, 256, 0, s>>>(w.Ha, w.Va, cw->W[1], H, n, pts, w.gate + H, w.biasf + H,
-                                            ctot, w.st, w.Hb, w.Vb);
-  caspr_prof_end(CASPR_PROF_CNF_MID_SIMT, s);
-  caspr_prof_begin(CASPR_PROF_CNF_MID_SIMT, s);
-  CASPR_COUNT(); cnf_mid_layer_kernel<<<grid, 256, 0, s>>>(w.Hb, w.Vb, cw->W[2], H, n, pts, w.gate + 2 * H,
-                                            w.biasf + 2 * H, ctot, w.st, w.Ha, w.Va);
-  caspr_prof_end(CASPR_PROF_CNF_MID_SIMT, s);
+      w.Gc, w.Bc, w.wg_t, w.wb_t, w.lbias, frames, 3 * H + 3, ctot, stage, reverse, w.st,
+      use_tc ? w.col_scale : nullptr, w.gate, w.biasf);
+  if (use_tc) {
+    int rc = cnf_tc::enqueue_layer0(*plan, w.y0, w.kbuf, (size_t)n, e, cw->W[0], n, pts, stage, w.gate, w.biasf,
+                                    ctot, w.st, w.range_flag, s);
+    if (rc) return rc;
+    rc = cnf_tc::enqueue_mid(*plan, 0, w.gate + H, w.biasf + H, ctot, n, pts, w.st, nullptr, nullptr,
+                             w.range_flag, num_sms, s);
+    if (rc) return rc;
+    rc = cnf_tc::enqueue_mid(*plan, 1, w.gate + 2 * H, w.biasf + 2 * H, ctot, n, pts, w.st, w.Ha, w.Va,
+                             w.range_flag, num_sms, s);
+    if (rc) return rc;
+  } else {
+    CASPR_COUNT(); cnf_layer0_kernel<<<blocks_for(n, 8, 148 * 16), 256, 0, s>>>(
+        w.y0, w.kbuf, (size_t)n, e, cw->W[0], H, n, pts, stage, w.gate, w.biasf, ctot, w.st, w.Ha, w.Va);
+    dim3 grid(ceil_div(n, kMidBM), H / kMidBN);
+    caspr_prof_begin(CASPR_PROF_CNF_MID_SIMT, s);
+    CASPR_COUNT(); cnf_mid_layer_kernel<<<grid, 256, 0, s>>>(w.Ha, w.Va, cw->W[1], H, n, pts, w.gate + H, w.biasf + H,
+                                              ctot, w.st, w.Hb, w.Vb);
+    caspr_prof_end(CASPR_PROF_CNF_MID_SIMT, s);
+    caspr_prof_begin(CASPR_PROF_CNF_MID_SIMT, s);
+    CASPR_COUNT(); cnf_mid_layer_kernel<<<grid, 256, 0, s>>>(w.Hb, w.Vb, cw->W[2], H, n, pts, w.gate + 2 * H,
+                                              w.biasf + 2 * H, ctot, w.st, w.Ha, w.Va);
+    caspr_prof_end(CASPR_PROF_CNF_MID_SIMT, s);
+  }
   CASPR_COUNT(); cnf_last_layer_kernel<<<blocks_for(n, 8, 148 * 16), 256, 0, s>>>(
       w.Ha, w.Va, cw->W[3], H, n, pts, e, w.gate + 3 * H, w.biasf + 3 * H, ctot, reverse, w.st,
       w.kbuf + (size_t)stage * n);
   CASPR_CHECK_LAUNCH();
   return CASPR_OK;
+}
+
+// Engine set-up shared by caspr_cnf_flow / caspr_cnf_feval: weight split + tensor maps.
+int prepare_engine(const CnfWorkspace& w, const caspr_cnf_weights* cw, int n, int engine, cnf_tc::Plan* plan,
+                   int* num_sms, cudaStream_t s) {
+  *num_sms = 148;
+  if (engine != CASPR_CNF_TC_FP16X3) return CASPR_OK;
+  if (cw->hidden != 512) return CASPR_EINVAL;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return CASPR_ELAUNCH;
+  if (cudaMemsetAsync(w.range_flag, 0, sizeof(int), s) != cudaSuccess) return CASPR_ELAUNCH;
+  int rc = cnf_tc::prepare_weights(cw->W[1], cw->W[2], w.tcw, s);
+  if (rc) return rc;
+  rc = cnf_tc::fill_col_scale(w.tcw, hyper_ld(cw->hidden), w.col_scale, s);
+  if (rc) return rc;
+  return cnf_tc::make_plan(*plan, w.tcw, (__half*)w.Ha, (__half*)w.Va, (__half*)w.Hb, (__half*)w.Vb, n);
 }
 
 bool weights_ok(const caspr_cnf_weights* cw) {
@@ -659,7 +706,7 @@ extern "C" int caspr_cnf_flow(const float* x_in, const float* logp_in, const flo
   CASPR_REQUIRE(x_in && e && ctx && x_out && info && h_info && workspace);
   CASPR_REQUIRE(frames > 0 && pts > 0 && (long long)frames * pts < (1ll << 30));
   CASPR_REQUIRE(weights_ok(cw));
-  CASPR_REQUIRE(engine == CASPR_CNF_SIMT_FP32);
+  CASPR_REQUIRE(engine == CASPR_CNF_SIMT_FP32 || engine == CASPR_CNF_TC_FP16X3);
   CASPR_REQUIRE(((uintptr_t)workspace & 255) == 0);
   if (workspace_bytes < caspr_cnf_workspace_bytes(frames, pts, cw->hidden, cw->ctx_dim, engine))
     return CASPR_EWORKSPACE;
@@ -685,6 +732,10 @@ extern "C" int caspr_cnf_flow(const float* x_in, const float* logp_in, const flo
 
   int rc = prepare_hyper(w, cw, ctx, frames, s);
   if (rc) return rc;
+  cnf_tc::Plan plan;
+  int num_sms = 148;
+  rc = prepare_engine(w, cw, n, engine, &plan, &num_sms, s);
+  if (rc) return rc;
   const int eb = blocks_for(n, 256, 148 * 8);
   CASPR_COUNT(); cnf_init_state_kernel<<<ceil_div(n, 256), 256, 0, s>>>(x_in, logp_in, n, pre, reverse, w.y0);
   CASPR_CHECK_LAUNCH();
@@ -700,7 +751,7 @@ extern "C" int caspr_cnf_flow(const float* x_in, const float* logp_in, const flo
       return CASPR_ELAUNCH;
     if (cudaStreamSynchronize(s) != cudaSuccess) return CASPR_ELAUNCH;   // h0 is a stack object
   }
-  rc = enqueue_feval(w, cw, e, frames, pts, 0, reverse, s);
+  rc = enqueue_feval(w, cw, e, frames, pts, 0, reverse, engine, &plan, num_sms, s);
   if (rc) return rc;
   CASPR_COUNT(); cnf_init_norm_kernel<<<eb, 256, 0, s>>>(w.y0, w.kbuf, n, rtol, atol, w.st);
   CASPR_COUNT(); cnf_init_controller_kernel<<<1, 1, 0, s>>>(w.st, n, t_start, t_stop);
@@ -717,7 +768,7 @@ extern "C" int caspr_cnf_flow(const float* x_in, const float* logp_in, const flo
   for (;;) {
     for (int b = 0; b < kBatch; ++b, ++step_id) {
       for (int stage = 1; stage <= 6; ++stage) {
-        rc = enqueue_feval(w, cw, e, frames, pts, stage, reverse, s);
+        rc = enqueue_feval(w, cw, e, frames, pts, stage, reverse, engine, &plan, num_sms, s);
         if (rc) return rc;
       }
       CASPR_COUNT(); cnf_error_kernel<<<eb, 256, 0, s>>>(w.y0, w.kbuf, (size_t)n, n, rtol, atol, w.st, w.y1);
@@ -731,6 +782,13 @@ extern "C" int caspr_cnf_flow(const float* x_in, const float* logp_in, const flo
     if (cudaStreamSynchronize(s) != cudaSuccess) return CASPR_ELAUNCH;
     if (hst.done) break;
     if (step_id >= kMaxSteps) { hst.status = CASPR_ESOLVER_MAXSTEPS; break; }
+  }
+  if (engine == CASPR_CNF_TC_FP16X3) {
+    int h_range = 0;
+    if (cudaMemcpyAsync(&h_range, w.range_flag, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess)
+      return CASPR_ELAUNCH;
+    if (h_range) hst.status = CASPR_ERANGE;      // an fp16 operand overflowed: results are not trustworthy
   }
   int32_t first_dt_bits;
   memcpy(&first_dt_bits, &hst.first_dt, 4);
@@ -747,7 +805,8 @@ extern "C" int caspr_cnf_feval(const float* y, const float* e, const float* ctx,
                                const caspr_cnf_weights* cw, float t, int engine, float* dy,
                                float* neg_div, void* workspace, size_t workspace_bytes, void* stream) {
   CASPR_REQUIRE(y && e && ctx && dy && neg_div && workspace);
-  CASPR_REQUIRE(frames > 0 && pts > 0 && weights_ok(cw) && engine == CASPR_CNF_SIMT_FP32);
+  CASPR_REQUIRE(frames > 0 && pts > 0 && weights_ok(cw));
+  CASPR_REQUIRE(engine == CASPR_CNF_SIMT_FP32 || engine == CASPR_CNF_TC_FP16X3);
   CASPR_REQUIRE(((uintptr_t)workspace & 255) == 0);
   if (workspace_bytes < caspr_cnf_workspace_bytes(frames, pts, cw->hidden, cw->ctx_dim, engine))
     return CASPR_EWORKSPACE;
@@ -761,10 +820,14 @@ extern "C" int caspr_cnf_feval(const float* y, const float* e, const float* ctx,
   if (cudaStreamSynchronize(s) != cudaSuccess) return CASPR_ELAUNCH;
   int rc = prepare_hyper(w, cw, ctx, frames, s);
   if (rc) return rc;
+  cnf_tc::Plan plan;
+  int num_sms = 148;
+  rc = prepare_engine(w, cw, n, engine, &plan, &num_sms, s);
+  if (rc) return rc;
   MbnDev none = load_mbn(nullptr, nullptr);
   CASPR_COUNT(); cnf_init_state_kernel<<<ceil_div(n, 256), 256, 0, s>>>(y, nullptr, n, none, 0, w.y0);
   CASPR_CHECK_LAUNCH();
-  rc = enqueue_feval(w, cw, e, frames, pts, 0, 0, s);
+  rc = enqueue_feval(w, cw, e, frames, pts, 0, 0, engine, &plan, num_sms, s);
   if (rc) return rc;
   // unpack k0 -> dy (n,3), neg_div (n)
   if (cudaMemcpy2DAsync(dy, 12, w.kbuf, 16, 12, n, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return CASPR_ELAUNCH;

@@ -1,0 +1,37 @@
+// Interface between the CNF solver (cnf.cu) and its tensor-core engine (cnf_tc.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include "cnf_state.cuh"
+
+namespace cnf_tc {
+
+constexpr float kActScale = 16.f;     // activations / tangents are stored as fp16(x * 2^4)
+
+struct Weights {
+  __half* hi[2];       // W1, W2 split planes [512][512], scaled by scales[2*l]
+  __half* lo[2];
+  float* scales;       // [l] = {w_scale, 1/(act_scale*w_scale)}
+  unsigned* max_bits;  // scratch: max|W| bits per layer
+};
+
+struct Plan {
+  CUtensorMap tm_act[2][2];   // [buffer A/B][hi/lo]
+  CUtensorMap tm_w[2][2];     // [layer][hi/lo]
+  __half *a_hi, *a_lo, *b_hi, *b_lo;
+  int n_tiles;
+};
+
+size_t weights_workspace_bytes();
+int prepare_weights(const float* W1, const float* W2, const Weights& out, cudaStream_t s);
+int fill_col_scale(const Weights& w, int ctot, float* col_scale, cudaStream_t s);
+int make_plan(Plan& plan, const Weights& w, __half* a_hi, __half* a_lo, __half* b_hi, __half* b_lo, int n);
+int enqueue_layer0(const Plan& plan, const float4* y0, const float4* kbuf, size_t kstride, const float* e,
+                   const float* W0, int n, int P, int stage, const float* gate, const float* biasf, int ld_hyper,
+                   const CnfState* st, int* range_flag, cudaStream_t s);
+int enqueue_mid(const Plan& plan, int layer, const float* gate, const float* biasf, int ld_hyper, int n, int P,
+                const CnfState* st, float* out_h, float* out_v, int* range_flag, int num_sms, cudaStream_t s);
+
+}  // namespace cnf_tc

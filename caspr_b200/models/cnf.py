@@ -165,7 +165,7 @@ class CNF(nn.Module):
 class SequentialFlow(nn.Module):
     """chain = [MovingBatchNorm1d, CNF x num_blocks, MovingBatchNorm1d] (flow.py:67-74)."""
 
-    engine = ops.CNF_SIMT_FP32
+    engine = ops.CNF_TC_FP16X3      # tcgen05 fp16x3 engine; ops.CNF_SIMT_FP32 is the exact-fp32 SIMT engine
 
     def __init__(self, layer_list, use_bn=True):
         super(SequentialFlow, self).__init__()

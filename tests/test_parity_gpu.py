@@ -221,21 +221,41 @@ def test_latent_ode_matches_oracle(case):
     assert _rel(out, ref) < 1e-5
 
 
-def test_cnf_feval_matches_oracle(case, ops):
-    """One dynamics evaluation (dy, -div): forward-mode divergence vs the reference's autograd VJP."""
+ENGINES = ['simt', 'tc']
+
+
+def _engine_id(ops, name):
+    return ops.CNF_TC_FP16X3 if name == 'tc' else ops.CNF_SIMT_FP32
+
+
+@pytest.fixture(params=ENGINES)
+def engine(request, ops):
+    """Runs a model-level test once per CNF engine (exact-fp32 SIMT and tcgen05 fp16x3)."""
+    from caspr_b200.models.cnf import SequentialFlow
+    old = SequentialFlow.engine
+    SequentialFlow.engine = _engine_id(ops, request.param)
+    yield request.param
+    SequentialFlow.engine = old
+
+
+@pytest.mark.parametrize('eng', ENGINES)
+@pytest.mark.parametrize('frames,pts', [(3, 200), (2, 64), (5, 1000)])
+def test_cnf_feval_matches_oracle(case, ops, eng, frames, pts):
+    """One dynamics evaluation (dy, -div): forward-mode divergence vs the reference's autograd VJP.
+    Ragged sizes exercise partial 64-point tiles and tiles straddling frames."""
     _, gold, model, oracle, _, _ = case
     g = torch.Generator().manual_seed(3)
-    y = torch.randn(3, 200, 3, generator=g)
-    e = torch.randn(3, 200, 3, generator=g)
-    ctx = 0.5 * torch.randn(3, 1600, generator=g)
-    dy_ref, nd_ref, _ = oracle.odefunc(torch.tensor(0.37), (y, torch.zeros(3, 200, 1), ctx), e)
+    y = torch.randn(frames, pts, 3, generator=g)
+    e = torch.randn(frames, pts, 3, generator=g)
+    ctx = 0.5 * torch.randn(frames, 1600, generator=g)
+    dy_ref, nd_ref, _ = oracle.odefunc(torch.tensor(0.37), (y, torch.zeros(frames, pts, 1), ctx), e)
     pack = model.point_cnf.chain[1].weight_pack()
-    dy, nd = ops.cnf_feval(y.to(DEV), e.to(DEV), ctx.to(DEV), pack, 0.37)
+    dy, nd = ops.cnf_feval(y.to(DEV), e.to(DEV), ctx.to(DEV), pack, 0.37, engine=_engine_id(ops, eng))
     assert _rel(dy, dy_ref) < 1e-5
     assert _rel(nd, nd_ref.squeeze(-1)) < 1e-4
 
 
-def test_reconstruct_matches_reference_fixture(case):
+def test_reconstruct_matches_reference_fixture(case, engine):
     _, gold, model, _, x, _ = case
     y = torch.from_numpy(gold['rec_y'])
     e = torch.from_numpy(gold['rec_e']).to(DEV)
@@ -247,7 +267,7 @@ def test_reconstruct_matches_reference_fixture(case):
     assert float(cd.max()) < 1e-8
 
 
-def test_interpolated_reconstruct_matches_reference_fixture(case):
+def test_interpolated_reconstruct_matches_reference_fixture(case, engine):
     _, gold, model, _, x, _ = case
     y = torch.from_numpy(gold['interp_y'])[:, 0]
     e = torch.from_numpy(gold['interp_e']).to(DEV)
@@ -257,7 +277,7 @@ def test_interpolated_reconstruct_matches_reference_fixture(case):
     assert _rel(xr, gold['interp_x']) < 1e-4
 
 
-def test_decode_matches_reference_fixture(case):
+def test_decode_matches_reference_fixture(case, engine):
     _, gold, model, _, _, _ = case
     z = torch.from_numpy(gold['dec_z']).to(DEV)
     _, _, xd = model.decode(z, num_points=512, y=torch.from_numpy(gold['dec_y']).reshape(1, 512, 3),
@@ -266,7 +286,7 @@ def test_decode_matches_reference_fixture(case):
     assert _rel(xd, gold['dec_x']) < 1e-4
 
 
-def test_forward_nll_matches_reference_fixture(case):
+def test_forward_nll_matches_reference_fixture(case, engine):
     _, gold, model, _, x, nocs = case
     nll, tl = model(x.to(DEV), nocs.to(DEV), e=torch.from_numpy(gold['fwd_e']).to(DEV))
     assert list(model.get_nfe().astype(int)) == list(gold['fwd_nfe'].astype(int))
@@ -274,7 +294,7 @@ def test_forward_nll_matches_reference_fixture(case):
     assert abs(float(tl.mean()) - float(gold['fwd_tnocs_l1_mean'])) < 1e-5
 
 
-def test_flow_round_trip(case):
+def test_flow_round_trip(case, engine):
     """Size-independent property: decode (reverse flow) then encode (forward flow) returns the base
     samples to solver tolerance, and the log-density change is consistent."""
     _, _, model, _, _, _ = case
@@ -289,7 +309,7 @@ def test_flow_round_trip(case):
     assert torch.isfinite(dlogp).all()
 
 
-def test_solver_failure_is_reported(case, ops):
+def test_solver_failure_is_reported(case, ops, engine):
     """Non-finite inputs surface as the solver's status (torchdiffeq asserts), not as silent garbage."""
     from caspr_b200._lib import CasprError
     _, _, model, _, _, _ = case
