@@ -238,7 +238,7 @@ def run_ours(args, rank, world, local_rank):
     ms = ev0.elapsed_time(ev1)
     nfe = [int(v) for v in model.get_nfe()]
     prof = {}
-    for name, kid in (('cnf_mid_layer_kernel', 0), ('cnf_fused_tc_kernel', 1)):
+    for name, kid in (('cnf_mid_layer_kernel', 0), ('cnf_tc_layer_kernel', 1)):
         tot, cnt = ctypes.c_double(), ctypes.c_longlong()
         lib.caspr_profile_read(kid, ctypes.byref(tot), ctypes.byref(cnt))
         prof[name] = (tot.value, cnt.value)
@@ -258,6 +258,23 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     ms_e2e = max(f0.elapsed_time(f1), wall_ms)        # host-side RNG / copies count too
 
+    # ---- phase breakdown (informational, outside the timed regions): encode / latent ODE / CNF decode
+    def phases():
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        evs[0].record()
+        z0, _ = model.encode(x_dev)
+        evs[1].record()
+        times = x_dev[:, :, 0, 3] / kw_dev.get('max_timestamp', 5.0) if 'timestamps' not in kw_dev else \
+            kw_dev['timestamps'].view(1, -1).repeat(B, 1)
+        z = model.aggregate_and_solve_latent(z0, times.to(z0))
+        evs[2].record()
+        model.decode(z, P, kw_dev.get('constant_in_time', False), y=y_dev, e=e_dev)
+        evs[3].record()
+        torch.cuda.synchronize()
+        return [evs[i].elapsed_time(evs[i + 1]) for i in range(3)]
+    phases()
+    phase_ms = [round(v, 3) for v in phases()]
+
     t = torch.tensor([ms, ms_e2e, float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         import torch.distributed as dist
@@ -275,12 +292,14 @@ def run_ours(args, rank, world, local_rank):
     # dominant kernel: the H x H layers of the CNF dynamics over [activation ; tangent] rows
     H = 512
     n_pts = B * Tq * P
-    if prof['cnf_fused_tc_kernel'][1] > 0:
-        kname = 'cnf_fused_tc_kernel'
-        flop_per_launch = 2.0 * 2 * n_pts * (2 * H * H + 2 * 3 * H)       # whole f-eval: both GEMMs x {h, v} + 3<->H
+    # ALGORITHMIC flops of one launch: one H x H ConcatSquash layer over {activation, tangent} rows of every point
+    flop_per_launch = 2.0 * 2 * n_pts * H * H
+    if prof['cnf_tc_layer_kernel'][1] > 0:
+        kname = 'gemm_fp16x3_kernel<CnfEpilogue> (tcgen05, 3 fp16 MMAs per algorithmic MAC)'
+        prof[kname] = prof['cnf_tc_layer_kernel']
     else:
         kname = 'cnf_mid_layer_kernel'
-        flop_per_launch = 2.0 * 2 * n_pts * H * H                          # one H x H layer x {h, v}
+
     tot_ms, cnt = prof[kname]
     roofline = None
     if cnt > 0:
@@ -289,8 +308,11 @@ def run_ours(args, rank, world, local_rank):
         roofline = {'bound': 'tensor', 'kernel': kname, 'achieved': achieved, 'peak': peaks['tf_sustained'],
                     'unit': 'TFLOP/s', 'frac': achieved / peaks['tf_sustained'], 'traffic': None,
                     'peak_source': peaks['source'] + ' bf16 dense sustained', 'launches': cnt,
-                    'avg_launch_ms': avg_ms, 'share_of_step': tot_ms / ms,
-                    'flop_per_launch': flop_per_launch}
+                    'avg_launch_ms': avg_ms, 'share_of_step': tot_ms / (ms / args.steps) / args.steps,
+                    'flop_per_launch': flop_per_launch,
+                    'mma_flop_per_launch': 3 * flop_per_launch if 'tcgen05' in kname else None,
+                    'note': 'achieved = algorithmic fp32-grade FLOP / CUDA-event time; the fp16x3 split issues 3x '
+                            'that many tensor-core FLOP, so frac <= 1/3 by construction'}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -309,7 +331,7 @@ def run_ours(args, rank, world, local_rank):
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': args.workload, 'batch_per_gpu': B, 'global_batch': B * world, 'frames': T,
                        'input_points': N, 'sampled_points': P, 'query_steps': Tq, 'cnf_init': args.cnf_init,
-                       'nfe_latent_cnf': nfe, 'engine': engine_name, 'parallelism': 'batch-shard x%d' % world,
+                       'nfe_latent_cnf': nfe, 'engine': engine_name, 'phase_ms_encode_latent_decode': phase_ms, 'parallelism': 'batch-shard x%d' % world,
                        'l2': 'working set per dynamics evaluation (>1 GB of activations) exceeds the 126 MB L2; no flush'},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(x.numel() * 4 + y.numel() * 4),
                     'd2h_bytes_per_step': int(B * Tq * P * 3 * 4), 'ms_per_step': ms_e2e / args.steps},

@@ -37,6 +37,7 @@ SIGNATURES = {
     'caspr_build_arch': (c_char_p, []),
     'caspr_status_string': (c_char_p, [c_int]),
     'caspr_launch_count': (ctypes.c_ulonglong, []),
+    'caspr_launch_count_add': (None, [ctypes.c_ulonglong]),
     'caspr_profile_enable': (None, [c_int]),
     'caspr_profile_read': (c_int, [c_int, POINTER(c_double), POINTER(ctypes.c_longlong)]),
     'caspr_fps': (c_int, [_P, c_int, c_int, c_int, _P, _P, _P]),
@@ -46,6 +47,9 @@ SIGNATURES = {
     'caspr_three_interp_concat': (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
                                           _P, c_int, _P]),
     'caspr_linear': (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    'caspr_linear_tc_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'caspr_linear_tc': (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P,
+                                c_size_t, _P]),
     'caspr_groupnorm': (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_float, c_int, c_int, _P,
                                 c_int, _P, _P]),
     'caspr_augment_xyz': (c_int, [_P, c_int, _P, _P]),

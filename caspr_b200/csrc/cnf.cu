@@ -542,6 +542,7 @@ struct CnfWorkspace {
   float4 *y0, *y1, *kbuf;              // n, n, 7n
   float *Ha, *Va, *Hb, *Vb;            // n_pad x H each (the tensor-core engine reuses them as fp16 planes)
   float* col_scale;                    // ctot (tensor-core engine)
+  float* acc6;                         // n x 8 partial sums of the fused output layer (tensor-core engine)
   int* range_flag;
   cnf_tc::Weights tcw;
   size_t bytes;
@@ -570,6 +571,7 @@ CnfWorkspace carve(void* base, int frames, int pts, int H) {
   w.Hb = (float*)take(n_pad * H * 4);
   w.Vb = (float*)take(n_pad * H * 4);
   w.col_scale = (float*)take(ctot * 4);
+  w.acc6 = (float*)take(n * 8 * 4);
   w.range_flag = (int*)take(256);
   for (int l = 0; l < 2; ++l) {
     w.tcw.hi[l] = (__half*)take((size_t)512 * 512 * 2);
@@ -640,9 +642,11 @@ int enqueue_feval(const CnfWorkspace& w, const caspr_cnf_weights* cw, const floa
     rc = cnf_tc::enqueue_mid(*plan, 0, w.gate + H, w.biasf + H, ctot, n, pts, w.st, nullptr, nullptr,
                              w.range_flag, num_sms, s);
     if (rc) return rc;
-    rc = cnf_tc::enqueue_mid(*plan, 1, w.gate + 2 * H, w.biasf + 2 * H, ctot, n, pts, w.st, w.Ha, w.Va,
+    rc = cnf_tc::enqueue_mid(*plan, 1, w.gate + 2 * H, w.biasf + 2 * H, ctot, n, pts, w.st, cw->W[3], w.acc6,
                              w.range_flag, num_sms, s);
     if (rc) return rc;
+    return cnf_tc::enqueue_last_finish(w.acc6, e, n, pts, w.gate + 3 * H, w.biasf + 3 * H, ctot, reverse, w.st,
+                                       w.kbuf + (size_t)stage * n, s);
   } else {
     CASPR_COUNT(); cnf_layer0_kernel<<<blocks_for(n, 8, 148 * 16), 256, 0, s>>>(
         w.y0, w.kbuf, (size_t)n, e, cw->W[0], H, n, pts, stage, w.gate, w.biasf, ctot, w.st, w.Ha, w.Va);
@@ -674,6 +678,7 @@ int prepare_engine(const CnfWorkspace& w, const caspr_cnf_weights* cw, int n, in
       cudaDeviceGetAttribute(num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
     return CASPR_ELAUNCH;
   if (cudaMemsetAsync(w.range_flag, 0, sizeof(int), s) != cudaSuccess) return CASPR_ELAUNCH;
+  if (cudaMemsetAsync(w.acc6, 0, (size_t)n * 8 * sizeof(float), s) != cudaSuccess) return CASPR_ELAUNCH;
   int rc = cnf_tc::prepare_weights(cw->W[1], cw->W[2], w.tcw, s);
   if (rc) return rc;
   rc = cnf_tc::fill_col_scale(w.tcw, hyper_ld(cw->hidden), w.col_scale, s);

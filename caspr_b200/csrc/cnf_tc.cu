@@ -24,18 +24,15 @@
 #include "dopri5.cuh"
 #include "cnf_state.cuh"
 #include "cnf_tc.cuh"
-#include "tc_common.cuh"
+#include "tc_gemm.cuh"
 
 namespace cnf_tc {
 
 namespace {
 
-constexpr int kBM = 128, kBN = 256, kBK = 64, kStages = 2;
-constexpr int kATile = kBM * kBK * 2;                    // 16 KB
-constexpr int kWTile = kBN * kBK * 2;                    // 32 KB
-constexpr int kStageBytes = 2 * kATile + 2 * kWTile;     // 96 KB
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
-constexpr int kThreads = 192;
+using tcg::kBM;
+using tcg::kBN;
+using tcg::split2;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -55,224 +52,141 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
-// x (already multiplied by kActScale) -> fp16 hi and fp16 lo with hi + lo ~= x to ~22 bits
-__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  __half2 h = __floats2half2_rn(x0, x1);
-  float2 hf = __half22float2(h);
-  __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-  hi = *reinterpret_cast<uint32_t*>(&h);
-  lo = *reinterpret_cast<uint32_t*>(&l);
-}
-
-struct MidParams {
+// Epilogue of one H x H ConcatSquash layer: rows of a 128-row tile are 64 points, quadrant q holds the
+// activation rows of points 16q..16q+15 in lanes 0-15 and their tangent rows in lanes 16-31.
+template <bool OUT_F32>
+struct CnfEpilogue {
   const float* gate;     // per-frame gate of this layer, pre-multiplied by 1/(act_scale*w_scale)
   const float* biasf;    // per-frame folded bias  b*gate + hyper_bias
   int ld_hyper;
   int n;                 // points
   int P;                 // points per frame
-  int n_tiles;           // 64-point tiles
-  const CnfState* st;
   __half* out_hi;        // OUT_F16: next layer's planes
   __half* out_lo;
-  float* out_h;          // OUT_F32: H, V [n][512]
-  float* out_v;
+  const float* W3;       // OUT_F32 (= last mid layer): the 3 x 512 weights of the output layer, which is
+  float* acc6;           //   fused here: per-point partial sums [n][8] = {W3.h (3), W3.v (3), -, -}
   int* range_flag;
-};
+  // per-thread tile state
+  const float* gp;
+  const float* bp;
+  size_t row_h;
+  int pt, col0, is_v;
+  bool live;
+  float range_max;
+  float pa[3], pv[3];    // fused output layer: partial dot products of this thread's columns
 
-template <bool OUT_F32>
-__global__ void __launch_bounds__(kThreads, 1)
-cnf_tc_mid_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
-                  const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
-                  MidParams p) {
-  if (p.st->done) return;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-  uint64_t* full = bars;                 // [kStages]
-  uint64_t* empty = bars + kStages;      // [kStages]
-  uint64_t* tfull = bars + 2 * kStages;  // [2]
-  uint64_t* tempty = tfull + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.n_tiles * 2;                 // (64-point tile, 256-column half)
-
-  if (threadIdx.x == 0) {
-    tc::prefetch_tmap(&tm_a_hi);
-    tc::prefetch_tmap(&tm_a_lo);
-    tc::prefetch_tmap(&tm_w_hi);
-    tc::prefetch_tmap(&tm_w_lo);
-    for (int s = 0; s < kStages; ++s) {
-      tc::mbar_init(&full[s], 1);
-      tc::mbar_init(&empty[s], 1);
+  __device__ __forceinline__ void tile_begin(int m_tile, int n_tile, int q, int lane) {
+    is_v = lane >> 4;
+    const int pl = q * 16 + (lane & 15);
+    pt = m_tile * 64 + pl;
+    live = pt < n;
+    const int f = (live ? pt : n - 1) / P;
+    col0 = n_tile * kBN + is_v * 16;
+    gp = gate + (size_t)f * ld_hyper + col0;
+    bp = biasf + (size_t)f * ld_hyper + col0;
+    row_h = (size_t)m_tile * kBM + q * 32 + (lane & 15);
+    if (OUT_F32) {
+      if (pending) flush();                // previous tile's sums (kept until now to overlap the atomics)
+      pa[0] = pa[1] = pa[2] = pv[0] = pv[1] = pv[2] = 0.f;
+      pending = true;
     }
-    for (int b = 0; b < 2; ++b) {
-      tc::mbar_init(&tfull[b], 1);
-      tc::mbar_init(&tempty[b], 128);
-    }
-    tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
-  tc::fence_before_sync();
-  __syncthreads();
-  tc::fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile >> 1, nh = tile & 1;
-        for (int kc = 0; kc < 512 / kBK; ++kc) {
-          tc::mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* sb = smem + stage * kStageBytes;
-          tc::mbar_arrive_expect_tx(&full[stage], kStageBytes);
-          tc::tma_load_2d(sb, &tm_a_hi, &full[stage], kc * kBK, m_tile * kBM);
-          tc::tma_load_2d(sb + kATile, &tm_a_lo, &full[stage], kc * kBK, m_tile * kBM);
-          tc::tma_load_2d(sb + 2 * kATile, &tm_w_hi, &full[stage], kc * kBK, nh * kBN);
-          tc::tma_load_2d(sb + 2 * kATile + kWTile, &tm_w_lo, &full[stage], kc * kBK, nh * kBN);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // -------------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc_f16(kBM, kBN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        tc::mbar_wait(&tempty[buf], acc_phase ^ 1);
-        tc::fence_after_sync();
-        const uint32_t d_tmem = tmem_base + buf * kBN;
-        for (int kc = 0; kc < 512 / kBK; ++kc) {
-          tc::mbar_wait(&full[stage], phase);
-          tc::fence_after_sync();
-          const uint32_t sb = tc::smem_u32(smem + stage * kStageBytes);
-          const uint64_t a_hi = tc::make_desc_k128(sb);
-          const uint64_t a_lo = tc::make_desc_k128(sb + kATile);
-          const uint64_t w_hi = tc::make_desc_k128(sb + 2 * kATile);
-          const uint64_t w_lo = tc::make_desc_k128(sb + 2 * kATile + kWTile);
+  bool pending;
+  int flush_pt;
+  bool flush_live;
+  __device__ __forceinline__ void flush() {
+    // pair lanes L and L+16 hold the two column halves of the same point
 #pragma unroll
-          for (int ks = 0; ks < kBK / 16; ++ks) {
-            const uint64_t adv = (uint64_t)(ks * 2);              // 32 bytes per UMMA_K
-            tc::umma_f16_ss(d_tmem, a_hi + adv, w_hi + adv, idesc, (kc | ks) != 0);
-            tc::umma_f16_ss(d_tmem, a_lo + adv, w_hi + adv, idesc, 1);
-            tc::umma_f16_ss(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
-          }
-          tc::umma_commit(&empty[stage]);                         // frees the smem stage when the MMAs finish
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-        }
-        tc::umma_commit(&tfull[buf]);                             // accumulator ready for the epilogue
-      }
+    for (int c = 0; c < 3; ++c) {
+      pa[c] += __shfl_xor_sync(0xffffffffu, pa[c], 16);
+      pv[c] += __shfl_xor_sync(0xffffffffu, pv[c], 16);
     }
-  } else {
-    // ---------------------------------------------------------------------- epilogue
-    const int q = warp & 3;                                       // TMEM lane quadrant of this warp
-    const int is_v = lane >> 4;
-    const int pl = q * 16 + (lane & 15);                          // point within the 64-point tile
-    float range_max = 0.f;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int m_tile = tile >> 1, nh = tile & 1;
-      const int buf = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      const int pt = m_tile * 64 + pl;
-      const bool live = pt < p.n;
-      const int f = (live ? pt : p.n - 1) / p.P;
-      const float* gp = p.gate + (size_t)f * p.ld_hyper + nh * kBN + is_v * 16;
-      const float* bp = p.biasf + (size_t)f * p.ld_hyper + nh * kBN + is_v * 16;
-      tc::mbar_wait(&tfull[buf], acc_phase);
-      tc::fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * kBN;
-#pragma unroll 1
-      for (int chunk = 0; chunk < kBN / 32; ++chunk) {
-        uint32_t r[32];
-        tc::tmem_ld_32x32(taddr + chunk * 32, r);
-        tc::tmem_ld_wait();
-        // lanes 0-15 keep columns 0-15 of the chunk, lanes 16-31 columns 16-31; each lane receives its
-        // partner row (tangent resp. activation) for those columns
-        float ah[16], av[16];
+    if (flush_live && !flush_is_v) {
+      float* a = acc6 + (size_t)flush_pt * 8;
+      atomicAdd(a + 0, pa[0]); atomicAdd(a + 1, pa[1]); atomicAdd(a + 2, pa[2]);
+      atomicAdd(a + 3, pv[0]); atomicAdd(a + 4, pv[1]); atomicAdd(a + 5, pv[2]);
+    }
+    pending = false;
+  }
+  int flush_is_v;
+
+  __device__ __forceinline__ void chunk(int chunk, uint32_t (&r)[32]) {
+    // lanes 0-15 keep columns 0-15 of the chunk, lanes 16-31 columns 16-31; each lane receives its
+    // partner row (tangent resp. activation) for those columns
+    float ah[16], av[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const uint32_t send = is_v ? r[j] : r[16 + j];
-          const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 16);
-          ah[j] = __uint_as_float(is_v ? recv : r[j]);
-          av[j] = __uint_as_float(is_v ? r[16 + j] : recv);
-        }
-        float g[16], b[16];
+    for (int j = 0; j < 16; ++j) {
+      const uint32_t send = is_v ? r[j] : r[16 + j];
+      const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 16);
+      ah[j] = __uint_as_float(is_v ? recv : r[j]);
+      av[j] = __uint_as_float(is_v ? r[16 + j] : recv);
+    }
+    float g[16], b[16];
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+      const float4 g4 = *reinterpret_cast<const float4*>(gp + chunk * 32 + j4 * 4);
+      const float4 b4 = *reinterpret_cast<const float4*>(bp + chunk * 32 + j4 * 4);
+      g[j4 * 4 + 0] = g4.x; g[j4 * 4 + 1] = g4.y; g[j4 * 4 + 2] = g4.z; g[j4 * 4 + 3] = g4.w;
+      b[j4 * 4 + 0] = b4.x; b[j4 * 4 + 1] = b4.y; b[j4 * 4 + 2] = b4.z; b[j4 * 4 + 3] = b4.w;
+    }
+    float ho[16], vo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float pre = fmaf(ah[j], g[j], b[j]);
+      // softplus (beta 1, threshold 20) and its derivative from the SFU approximations
+      const float z = ex2_approx(fminf(pre, 40.f) * kLog2e);
+      const float t = 1.f + z;
+      const bool big = pre > 20.f;
+      const float sp = big ? pre : kLn2 * lg2_approx(t);
+      const float dsp = big ? 1.f : z * rcp_approx(t);
+      ho[j] = sp;
+      vo[j] = dsp * g[j] * av[j];
+    }
+    const int col = col0 + chunk * 32;
+    if (OUT_F32) {
+      // fused output layer (H -> 3): accumulate W3[c][col..col+15] . {h', v'} for this thread's columns
+      flush_pt = pt; flush_live = live; flush_is_v = is_v;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float4* w4 = reinterpret_cast<const float4*>(W3 + c * 512 + col);
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 g4 = *reinterpret_cast<const float4*>(gp + chunk * 32 + j4 * 4);
-          const float4 b4 = *reinterpret_cast<const float4*>(bp + chunk * 32 + j4 * 4);
-          g[j4 * 4 + 0] = g4.x; g[j4 * 4 + 1] = g4.y; g[j4 * 4 + 2] = g4.z; g[j4 * 4 + 3] = g4.w;
-          b[j4 * 4 + 0] = b4.x; b[j4 * 4 + 1] = b4.y; b[j4 * 4 + 2] = b4.z; b[j4 * 4 + 3] = b4.w;
-        }
-        float ho[16], vo[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float pre = fmaf(ah[j], g[j], b[j]);
-          // softplus (beta 1, threshold 20) and its derivative from the SFU approximations
-          const float z = ex2_approx(fminf(pre, 40.f) * kLog2e);
-          const float t = 1.f + z;
-          const bool big = pre > 20.f;
-          const float sp = big ? pre : kLn2 * lg2_approx(t);
-          const float dsp = big ? 1.f : z * rcp_approx(t);
-          ho[j] = sp;
-          vo[j] = dsp * g[j] * av[j];
-        }
-        const int col = nh * kBN + chunk * 32 + is_v * 16;
-        if (OUT_F32) {
-          if (live) {
-            float4* oh = reinterpret_cast<float4*>(p.out_h + (size_t)pt * 512 + col);
-            float4* ov = reinterpret_cast<float4*>(p.out_v + (size_t)pt * 512 + col);
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              oh[j4] = make_float4(ho[4 * j4], ho[4 * j4 + 1], ho[4 * j4 + 2], ho[4 * j4 + 3]);
-              ov[j4] = make_float4(vo[4 * j4], vo[4 * j4 + 1], vo[4 * j4 + 2], vo[4 * j4 + 3]);
-            }
-          }
-        } else {
-          // rows of the next layer's planes: activation row of this point, tangent row 16 lanes on
-          const size_t row_h = (size_t)m_tile * kBM + q * 32 + (lane & 15);
-          const size_t row_v = row_h + 16;
-          uint32_t hh[8], hl[8], vh[8], vl[8];
-#pragma unroll
-          for (int j2 = 0; j2 < 8; ++j2) {
-            const float h0 = ho[2 * j2] * kActScale, h1 = ho[2 * j2 + 1] * kActScale;
-            const float v0 = vo[2 * j2] * kActScale, v1 = vo[2 * j2 + 1] * kActScale;
-            if (live) range_max = fmaxf(range_max, fmaxf(fmaxf(fabsf(h0), fabsf(h1)), fmaxf(fabsf(v0), fabsf(v1))));
-            split2(h0, h1, hh[j2], hl[j2]);
-            split2(v0, v1, vh[j2], vl[j2]);
-          }
-          uint4* d;
-          d = reinterpret_cast<uint4*>(p.out_hi + row_h * 512 + col);
-          d[0] = make_uint4(hh[0], hh[1], hh[2], hh[3]); d[1] = make_uint4(hh[4], hh[5], hh[6], hh[7]);
-          d = reinterpret_cast<uint4*>(p.out_lo + row_h * 512 + col);
-          d[0] = make_uint4(hl[0], hl[1], hl[2], hl[3]); d[1] = make_uint4(hl[4], hl[5], hl[6], hl[7]);
-          d = reinterpret_cast<uint4*>(p.out_hi + row_v * 512 + col);
-          d[0] = make_uint4(vh[0], vh[1], vh[2], vh[3]); d[1] = make_uint4(vh[4], vh[5], vh[6], vh[7]);
-          d = reinterpret_cast<uint4*>(p.out_lo + row_v * 512 + col);
-          d[0] = make_uint4(vl[0], vl[1], vl[2], vl[3]); d[1] = make_uint4(vl[4], vl[5], vl[6], vl[7]);
+          const float4 w = __ldg(w4 + j4);
+          pa[c] = fmaf(w.x, ho[4 * j4], pa[c]); pv[c] = fmaf(w.x, vo[4 * j4], pv[c]);
+          pa[c] = fmaf(w.y, ho[4 * j4 + 1], pa[c]); pv[c] = fmaf(w.y, vo[4 * j4 + 1], pv[c]);
+          pa[c] = fmaf(w.z, ho[4 * j4 + 2], pa[c]); pv[c] = fmaf(w.z, vo[4 * j4 + 2], pv[c]);
+          pa[c] = fmaf(w.w, ho[4 * j4 + 3], pa[c]); pv[c] = fmaf(w.w, vo[4 * j4 + 3], pv[c]);
         }
       }
-      tc::fence_before_sync();
-      tc::mbar_arrive(&tempty[buf]);
+    } else {
+      const size_t row_v = row_h + 16;
+      uint32_t hh[8], hl[8], vh[8], vl[8];
+#pragma unroll
+      for (int j2 = 0; j2 < 8; ++j2) {
+        const float h0 = ho[2 * j2] * kActScale, h1 = ho[2 * j2 + 1] * kActScale;
+        const float v0 = vo[2 * j2] * kActScale, v1 = vo[2 * j2 + 1] * kActScale;
+        if (live) range_max = fmaxf(range_max, fmaxf(fmaxf(fabsf(h0), fabsf(h1)), fmaxf(fabsf(v0), fabsf(v1))));
+        split2(h0, h1, hh[j2], hl[j2]);
+        split2(v0, v1, vh[j2], vl[j2]);
+      }
+      uint4* d;
+      d = reinterpret_cast<uint4*>(out_hi + row_h * 512 + col);
+      d[0] = make_uint4(hh[0], hh[1], hh[2], hh[3]); d[1] = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+      d = reinterpret_cast<uint4*>(out_lo + row_h * 512 + col);
+      d[0] = make_uint4(hl[0], hl[1], hl[2], hl[3]); d[1] = make_uint4(hl[4], hl[5], hl[6], hl[7]);
+      d = reinterpret_cast<uint4*>(out_hi + row_v * 512 + col);
+      d[0] = make_uint4(vh[0], vh[1], vh[2], vh[3]); d[1] = make_uint4(vh[4], vh[5], vh[6], vh[7]);
+      d = reinterpret_cast<uint4*>(out_lo + row_v * 512 + col);
+      d[0] = make_uint4(vl[0], vl[1], vl[2], vl[3]); d[1] = make_uint4(vl[4], vl[5], vl[6], vl[7]);
     }
-    if (!OUT_F32 && range_max > 65504.f) atomicOr(p.range_flag, 1);
   }
-  tc::fence_before_sync();
-  __syncthreads();
-  if (warp == 1) {
-    tc::fence_after_sync();
-    tc::tmem_dealloc(tmem_base, 512);
+
+  __device__ __forceinline__ void finish() {
+    if (OUT_F32 && pending) flush();
+    if (!OUT_F32 && range_max > 65504.f) atomicOr(range_flag, 1);
   }
-}
+};
 
 // ------------------------------------------------------------------------- weight split
 __global__ void __launch_bounds__(256)
@@ -330,8 +244,13 @@ cnf_tc_layer0_kernel(const float4* __restrict__ y0, const float4* __restrict__ k
                      int* __restrict__ range_flag) {
   if (st->done) return;
   constexpr int H = 512;
-  __shared__ float sW[H * 3];
-  for (int i = threadIdx.x; i < H * 3; i += blockDim.x) sW[i] = W0[i];
+  // W0 transposed to [3][H] with one pad word per 8 channels: lane L reads channels 8L..8L+7 (and
+  // 256+8L..), the padding spreads the 32 lanes over all banks
+  __shared__ float sW[3][H + H / 8];
+  for (int i = threadIdx.x; i < H * 3; i += blockDim.x) {
+    const int j = i / 3, c = i - 3 * j;
+    sW[c][j + (j >> 3)] = W0[i];
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -357,45 +276,78 @@ cnf_tc_layer0_kernel(const float4* __restrict__ y0, const float4* __restrict__ k
     }
     const float e0 = e[3 * (size_t)pt], e1 = e[3 * (size_t)pt + 1], e2 = e[3 * (size_t)pt + 2];
     const int f = pt / P;
-    const float* g = gate + (size_t)f * ld_hyper;
-    const float* bf = biasf + (size_t)f * ld_hyper;
     const int pl = pt & 63;
     const size_t row_h = (size_t)(pt >> 6) * 128 + (pl >> 4) * 32 + (pl & 15);
     const size_t row_v = row_h + 16;
-    // each lane produces 16 consecutive channels: j = lane*16 .. lane*16+15
-    uint32_t hh[8], hl[8], vh[8], vl[8];
+    // each lane produces two runs of 8 consecutive channels (j = set*256 + lane*8 + 0..7), so every
+    // 16-byte store instruction of the warp covers 512 contiguous bytes of one plane row
 #pragma unroll
-    for (int j2 = 0; j2 < 8; ++j2) {
-      float hv[2], vv[2];
+    for (int set = 0; set < 2; ++set) {
+      const int j0 = set * 256 + lane * 8;
+      const float4* g4p = reinterpret_cast<const float4*>(gate + (size_t)f * ld_hyper + j0);
+      const float4* b4p = reinterpret_cast<const float4*>(biasf + (size_t)f * ld_hyper + j0);
+      float g[8], bf[8];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int j = lane * 16 + j2 * 2 + u;
-        const float w0 = sW[3 * j], w1 = sW[3 * j + 1], w2 = sW[3 * j + 2];
-        const float a = fmaf(w2, ys[2], fmaf(w1, ys[1], w0 * ys[0]));
-        const float ta = fmaf(w2, e2, fmaf(w1, e1, w0 * e0));
-        const float gj = g[j];
-        const float pre = fmaf(a, gj, bf[j]);
-        float sp, dsp;
-        if (pre > 20.f) { sp = pre; dsp = 1.f; }
-        else { const float z = expf(pre); sp = log1pf(z); dsp = __fdiv_rn(z, __fadd_rn(z, 1.f)); }
-        hv[u] = sp * kActScale;
-        vv[u] = dsp * gj * ta * kActScale;
-        range_max = fmaxf(range_max, fmaxf(fabsf(hv[u]), fabsf(vv[u])));
+      for (int j4 = 0; j4 < 2; ++j4) {
+        const float4 a = g4p[j4], b = b4p[j4];
+        g[4 * j4] = a.x; g[4 * j4 + 1] = a.y; g[4 * j4 + 2] = a.z; g[4 * j4 + 3] = a.w;
+        bf[4 * j4] = b.x; bf[4 * j4 + 1] = b.y; bf[4 * j4 + 2] = b.z; bf[4 * j4 + 3] = b.w;
       }
-      split2(hv[0], hv[1], hh[j2], hl[j2]);
-      split2(vv[0], vv[1], vh[j2], vl[j2]);
+      uint32_t hh[4], hl[4], vh[4], vl[4];
+#pragma unroll
+      for (int j2 = 0; j2 < 4; ++j2) {
+        float hv[2], vv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int jj = j2 * 2 + u;
+          const int ji = j0 + (j0 >> 3) + jj;            // padded index of channel j0 + jj
+          const float w0 = sW[0][ji], w1 = sW[1][ji], w2 = sW[2][ji];
+          const float a = fmaf(w2, ys[2], fmaf(w1, ys[1], w0 * ys[0]));
+          const float ta = fmaf(w2, e2, fmaf(w1, e1, w0 * e0));
+          const float pre = fmaf(a, g[jj], bf[jj]);
+          const float z = ex2_approx(fminf(pre, 40.f) * kLog2e);
+          const float t = 1.f + z;
+          const bool big = pre > 20.f;
+          const float sp = big ? pre : kLn2 * lg2_approx(t);
+          const float dsp = big ? 1.f : z * rcp_approx(t);
+          hv[u] = sp * kActScale;
+          vv[u] = dsp * g[jj] * ta * kActScale;
+          range_max = fmaxf(range_max, fmaxf(fabsf(hv[u]), fabsf(vv[u])));
+        }
+        split2(hv[0], hv[1], hh[j2], hl[j2]);
+        split2(vv[0], vv[1], vh[j2], vl[j2]);
+      }
+      *reinterpret_cast<uint4*>(out_hi + row_h * H + j0) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+      *reinterpret_cast<uint4*>(out_lo + row_h * H + j0) = make_uint4(hl[0], hl[1], hl[2], hl[3]);
+      *reinterpret_cast<uint4*>(out_hi + row_v * H + j0) = make_uint4(vh[0], vh[1], vh[2], vh[3]);
+      *reinterpret_cast<uint4*>(out_lo + row_v * H + j0) = make_uint4(vl[0], vl[1], vl[2], vl[3]);
     }
-    uint4* d;
-    d = reinterpret_cast<uint4*>(out_hi + row_h * H + lane * 16);
-    d[0] = make_uint4(hh[0], hh[1], hh[2], hh[3]); d[1] = make_uint4(hh[4], hh[5], hh[6], hh[7]);
-    d = reinterpret_cast<uint4*>(out_lo + row_h * H + lane * 16);
-    d[0] = make_uint4(hl[0], hl[1], hl[2], hl[3]); d[1] = make_uint4(hl[4], hl[5], hl[6], hl[7]);
-    d = reinterpret_cast<uint4*>(out_hi + row_v * H + lane * 16);
-    d[0] = make_uint4(vh[0], vh[1], vh[2], vh[3]); d[1] = make_uint4(vh[4], vh[5], vh[6], vh[7]);
-    d = reinterpret_cast<uint4*>(out_lo + row_v * H + lane * 16);
-    d[0] = make_uint4(vl[0], vl[1], vl[2], vl[3]); d[1] = make_uint4(vl[4], vl[5], vl[6], vl[7]);
   }
   if (range_max > 65504.f) atomicOr(range_flag, 1);
+}
+
+// Output layer, second half: k = sign * (W3.h * gate + biasf, -(e . (gate * W3.v))) from the per-point sums
+// the last tensor-core layer accumulated; the sums are cleared for the next evaluation.
+__global__ void __launch_bounds__(256)
+cnf_tc_last_finish_kernel(float* __restrict__ acc6, const float* __restrict__ e, int n, int P,
+                          const float* __restrict__ gate, const float* __restrict__ biasf, int ld_hyper, int reverse,
+                          const CnfState* __restrict__ st, float4* __restrict__ kout) {
+  if (st->done) return;
+  const int pt = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pt >= n) return;
+  float4* a4 = reinterpret_cast<float4*>(acc6 + (size_t)pt * 8);
+  const float4 lo = a4[0], hi = a4[1];
+  a4[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+  a4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int f = pt / P;
+  const float* g = gate + (size_t)f * ld_hyper;
+  const float* bf = biasf + (size_t)f * ld_hyper;
+  const float dy0 = fmaf(lo.x, g[0], bf[0]);
+  const float dy1 = fmaf(lo.y, g[1], bf[1]);
+  const float dy2 = fmaf(lo.z, g[2], bf[2]);
+  const float e0 = e[3 * (size_t)pt], e1 = e[3 * (size_t)pt + 1], e2 = e[3 * (size_t)pt + 2];
+  const float div = (g[0] * lo.w) * e0 + (g[1] * hi.x) * e1 + (g[2] * hi.y) * e2;
+  kout[pt] = reverse ? make_float4(-dy0, -dy1, -dy2, div) : make_float4(dy0, dy1, dy2, -div);
 }
 
 bool g_attr_set = false;
@@ -443,10 +395,10 @@ int make_plan(Plan& plan, const Weights& w, __half* a_hi, __half* a_lo, __half* 
   plan.a_hi = a_hi; plan.a_lo = a_lo; plan.b_hi = b_hi; plan.b_lo = b_lo;
   if (!ok) return CASPR_ELAUNCH;
   if (!g_attr_set) {
-    if (cudaFuncSetAttribute(cnf_tc_mid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) !=
-            cudaSuccess ||
-        cudaFuncSetAttribute(cnf_tc_mid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) !=
-            cudaSuccess)
+    if (cudaFuncSetAttribute(tcg::gemm_fp16x3_kernel<CnfEpilogue<false>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             tcg::kSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(tcg::gemm_fp16x3_kernel<CnfEpilogue<true>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             tcg::kSmemBytes) != cudaSuccess)
       return CASPR_ELAUNCH;
     g_attr_set = true;
   }
@@ -465,21 +417,36 @@ int enqueue_layer0(const Plan& plan, const float4* y0, const float4* kbuf, size_
 }
 
 int enqueue_mid(const Plan& plan, int layer, const float* gate, const float* biasf, int ld_hyper, int n, int P,
-                const CnfState* st, float* out_h, float* out_v, int* range_flag, int num_sms, cudaStream_t s) {
-  MidParams p;
-  p.gate = gate; p.biasf = biasf; p.ld_hyper = ld_hyper; p.n = n; p.P = P; p.n_tiles = plan.n_tiles; p.st = st;
-  p.out_hi = plan.b_hi; p.out_lo = plan.b_lo; p.out_h = out_h; p.out_v = out_v; p.range_flag = range_flag;
+                const CnfState* st, const float* W3, float* acc6, int* range_flag, int num_sms, cudaStream_t s) {
   int grid = plan.n_tiles * 2;
   if (grid > num_sms) grid = num_sms;
+  const int* skip = &st->done;
   caspr_prof_begin(CASPR_PROF_CNF_FUSED_TC, s);
   CASPR_COUNT();
-  if (layer == 0)
-    cnf_tc_mid_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(plan.tm_act[0][0], plan.tm_act[0][1], plan.tm_w[0][0],
-                                                                plan.tm_w[0][1], p);
-  else
-    cnf_tc_mid_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(plan.tm_act[1][0], plan.tm_act[1][1], plan.tm_w[1][0],
-                                                               plan.tm_w[1][1], p);
+  if (layer == 0) {
+    CnfEpilogue<false> epi{};
+    epi.gate = gate; epi.biasf = biasf; epi.ld_hyper = ld_hyper; epi.n = n; epi.P = P;
+    epi.out_hi = plan.b_hi; epi.out_lo = plan.b_lo; epi.range_flag = range_flag;
+    tcg::gemm_fp16x3_kernel<CnfEpilogue<false>><<<grid, tcg::kThreads, tcg::kSmemBytes, s>>>(
+        plan.tm_act[0][0], plan.tm_act[0][1], plan.tm_w[0][0], plan.tm_w[0][1], plan.n_tiles, 2, 512 / tcg::kBK, skip,
+        epi);
+  } else {
+    CnfEpilogue<true> epi{};
+    epi.gate = gate; epi.biasf = biasf; epi.ld_hyper = ld_hyper; epi.n = n; epi.P = P;
+    epi.W3 = W3; epi.acc6 = acc6; epi.range_flag = range_flag; epi.pending = false;
+    tcg::gemm_fp16x3_kernel<CnfEpilogue<true>><<<grid, tcg::kThreads, tcg::kSmemBytes, s>>>(
+        plan.tm_act[1][0], plan.tm_act[1][1], plan.tm_w[1][0], plan.tm_w[1][1], plan.n_tiles, 2, 512 / tcg::kBK, skip,
+        epi);
+  }
   caspr_prof_end(CASPR_PROF_CNF_FUSED_TC, s);
+  CASPR_CHECK_LAUNCH();
+  return CASPR_OK;
+}
+
+int enqueue_last_finish(float* acc6, const float* e, int n, int P, const float* gate, const float* biasf,
+                        int ld_hyper, int reverse, const CnfState* st, float4* kout, cudaStream_t s) {
+  CASPR_COUNT(); cnf_tc_last_finish_kernel<<<ceil_div(n, 256), 256, 0, s>>>(acc6, e, n, P, gate, biasf, ld_hyper,
+                                                                            reverse, st, kout);
   CASPR_CHECK_LAUNCH();
   return CASPR_OK;
 }

@@ -31,7 +31,10 @@ int make_plan(Plan& plan, const Weights& w, __half* a_hi, __half* a_lo, __half* 
 int enqueue_layer0(const Plan& plan, const float4* y0, const float4* kbuf, size_t kstride, const float* e,
                    const float* W0, int n, int P, int stage, const float* gate, const float* biasf, int ld_hyper,
                    const CnfState* st, int* range_flag, cudaStream_t s);
+// layer 0: planes A -> planes B;  layer 1: planes B -> fused output layer (W3 (3,512)) accumulated into acc6 [n][8]
 int enqueue_mid(const Plan& plan, int layer, const float* gate, const float* biasf, int ld_hyper, int n, int P,
-                const CnfState* st, float* out_h, float* out_v, int* range_flag, int num_sms, cudaStream_t s);
+                const CnfState* st, const float* W3, float* acc6, int* range_flag, int num_sms, cudaStream_t s);
+int enqueue_last_finish(float* acc6, const float* e, int n, int P, const float* gate, const float* biasf,
+                        int ld_hyper, int reverse, const CnfState* st, float4* kout, cudaStream_t s);
 
 }  // namespace cnf_tc

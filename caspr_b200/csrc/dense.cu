@@ -190,6 +190,81 @@ groupnorm_small_kernel(float* __restrict__ X, int ldx, int rows_per_sample, int 
   }
 }
 
+// Tiny samples (rows x C <= 2048 floats): one WARP per sample, eight samples in flight per CTA.  Two
+// lanes share a group's statistics (two-pass mean / variance like the kernel above); the tile is staged
+// in the warp's slice of shared memory so global traffic stays one coalesced read and one write.
+constexpr int kGnWarpTile = 2048;
+__global__ void __launch_bounds__(256)
+groupnorm_warp_kernel(float* __restrict__ X, int ldx, int samples, int rows_per_sample, int C, int groups,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                      int relu, int write_back, float* __restrict__ maxout, int ld_max) {
+  extern __shared__ float tiles[];                 // 8 x (R*C) + 8 x 2*groups
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int R = rows_per_sample;
+  const int elems = R * C;
+  float* tile = tiles + (size_t)warp * elems;
+  float* stat = tiles + (size_t)8 * elems + warp * 2 * groups;     // mean[groups], rstd[groups]
+  const int cpg = C / groups;
+  const int gsz = cpg * R;
+  for (int sample = blockIdx.x * 8 + warp; sample < samples; sample += gridDim.x * 8) {
+    float* base = X + (size_t)sample * R * ldx;
+    for (int i = lane; i < elems; i += 32) {
+      const int r = i / C, c = i - r * C;
+      tile[i] = base[(size_t)r * ldx + c];
+    }
+    __syncwarp();
+    // lanes 2g and 2g+1 split the elements of group g (groups <= 16 per pass, loop for more)
+    for (int g0 = 0; g0 < groups; g0 += 16) {
+      const int g = g0 + (lane >> 1);
+      const int half = lane & 1;
+      float sum = 0.f;
+      if (g < groups)
+        for (int i = half; i < gsz; i += 2) {
+          const int r = i / cpg, c = g * cpg + (i - r * cpg);
+          sum += tile[r * C + c];
+        }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      const float mean = sum / (float)gsz;
+      float var = 0.f;
+      if (g < groups)
+        for (int i = half; i < gsz; i += 2) {
+          const int r = i / cpg, c = g * cpg + (i - r * cpg);
+          const float d = tile[r * C + c] - mean;
+          var += d * d;
+        }
+      var += __shfl_xor_sync(0xffffffffu, var, 1);
+      if (g < groups && half == 0) {
+        stat[g] = mean;
+        stat[groups + g] = 1.0f / sqrtf(var / (float)gsz + eps);
+      }
+    }
+    __syncwarp();
+    if (write_back) {
+      for (int i = lane; i < elems; i += 32) {
+        const int r = i / C, c = i - r * C;
+        const int g = c / cpg;
+        float v = (tile[i] - stat[g]) * stat[groups + g] * gamma[c] + beta[c];
+        if (relu) v = fmaxf(v, 0.f);
+        base[(size_t)r * ldx + c] = v;
+      }
+    }
+    if (maxout) {
+      for (int c = lane; c < C; c += 32) {
+        const int g = c / cpg;
+        const float mu = stat[g], rs = stat[groups + g], ga = gamma[c], be = beta[c];
+        float m = -3.0e38f;
+        for (int r = 0; r < R; ++r) {
+          float v = (tile[r * C + c] - mu) * rs * ga + be;
+          if (relu) v = fmaxf(v, 0.f);
+          m = fmaxf(m, v);
+        }
+        maxout[(size_t)sample * ld_max + c] = m;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // Large samples: pass 1 accumulates per-(sample, group) sum / sum of squares in fp64,
 // pass 2 normalises (and max-pools through ordered-uint atomics).
 constexpr int kGnRowsPerCta = 64;
@@ -336,6 +411,20 @@ extern "C" int caspr_groupnorm(float* X, int ldx, int samples, int rows_per_samp
   CASPR_REQUIRE(!maxout || ld_max >= C);
   cudaStream_t s = (cudaStream_t)stream;
   const size_t tile_bytes = (size_t)rows_per_sample * C * sizeof(float);
+  if (rows_per_sample * C <= kGnWarpTile) {
+    const size_t smem = 8 * tile_bytes + 8 * 2 * groups * sizeof(float);
+    if (smem > 48 * 1024) {
+      if (cudaFuncSetAttribute(groupnorm_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               80 * 1024) != cudaSuccess)
+        return CASPR_EINVAL;
+    }
+    int blocks = ceil_div(samples, 8);
+    if (blocks > 148 * 6) blocks = 148 * 6;
+    CASPR_COUNT(); groupnorm_warp_kernel<<<blocks, 256, smem, s>>>(X, ldx, samples, rows_per_sample, C, groups,
+                                                                   gamma, beta, eps, relu, write_back, maxout, ld_max);
+    CASPR_CHECK_LAUNCH();
+    return CASPR_OK;
+  }
   if (rows_per_sample <= 64 && tile_bytes <= 96 * 1024) {
     if (tile_bytes > 48 * 1024) {
       if (cudaFuncSetAttribute(groupnorm_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

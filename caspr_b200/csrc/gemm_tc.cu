@@ -1,0 +1,208 @@
+// caspr_linear_tc: the 1x1-conv / Linear layers of the TPointNet++ encoder on the tcgen05 tensor
+// cores with fp32-grade accuracy (three fp16 products, fp32 accumulation in TMEM; tc_gemm.cuh).
+// Replaces the large torch Conv1d(k=1) calls of caspr/models/tpointnet2.py:99-105 and
+// pointnet2.py:471-481,207-212 (feature-propagation and final layers); the small per-ball layers
+// stay on the exact-fp32 SIMT kernel (dense.cu).
+//
+// Per call: (1) split X and W into fp16 hi/lo planes, every row scaled by its own power of two that
+// places the row's largest element in the upper fp16 range, K padded to 64, rows / channels padded to
+// the tile (zero fill); (2) persistent TMA + tcgen05 GEMM; the epilogue undoes the row and channel
+// scales exactly, adds the bias, applies the activation and stores fp32 rows with the caller's
+// leading dimension.
+#include "common.cuh"
+#include "tc_gemm.cuh"
+
+namespace {
+
+using tcg::kBK;
+using tcg::kBM;
+using tcg::kBN;
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == CASPR_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == CASPR_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+  return v;
+}
+
+// fp32 [rows][cols] (leading dimension ld) -> fp16 hi / lo planes [rows_pad][k_pad], zero padded, each
+// row scaled by its own power of two 2^(14-e) (max|row| < 2^e, so the largest element lands in
+// [2^13, 2^14)); inv_scale[row] = 2^(e-14) is undone exactly in the GEMM epilogue.  One warp per row:
+// the row is read twice, the second time from L1/L2.
+__global__ void __launch_bounds__(256)
+split_rows_kernel(const float* __restrict__ x, int ld, long long rows, int cols, long long rows_pad, int k_pad,
+                  int relu, __half2* __restrict__ hi, __half2* __restrict__ lo, float* __restrict__ inv_scale) {
+  const int lane = threadIdx.x & 31;
+  const int kp2 = k_pad / 2;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows_pad; r += warps) {
+    __half2* h = hi + r * kp2;
+    __half2* l = lo + r * kp2;
+    if (r >= rows) {
+      const __half2 z = __floats2half2_rn(0.f, 0.f);
+      for (int c2 = lane; c2 < kp2; c2 += 32) { h[c2] = z; l[c2] = z; }
+      if (lane == 0) inv_scale[r] = 0.f;
+      continue;
+    }
+    const float* xr = x + r * ld;
+    float m = 0.f;
+    for (int c = lane; c < cols; c += 32) {
+      float v = xr[c];
+      if (relu) v = fmaxf(v, 0.f);
+      m = fmaxf(m, fabsf(v));
+    }
+    m = warp_max(m);
+    float s = 1.f, inv = 1.f;
+    if (m > 0.f && m < 3.0e38f) {
+      int e;
+      frexpf(m, &e);
+      s = ldexpf(1.f, 14 - e);
+      inv = ldexpf(1.f, e - 14);
+    }
+    if (lane == 0) inv_scale[r] = inv;
+    for (int c2 = lane; c2 < kp2; c2 += 32) {
+      const int c = 2 * c2;
+      float a = c < cols ? xr[c] : 0.f;
+      float b = c + 1 < cols ? xr[c + 1] : 0.f;
+      if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+      a *= s;
+      b *= s;
+      const __half2 hh = __floats2half2_rn(a, b);
+      const float2 hf = __half22float2(hh);
+      h[c2] = hh;
+      l[c2] = __floats2half2_rn(a - hf.x, b - hf.y);
+    }
+  }
+}
+
+struct LinearEpilogue {
+  const float* bias;
+  const float* x_inv;     // per-row 1/scale of X
+  const float* w_inv;     // per-output-channel 1/scale of W
+  float* Y;
+  int ldy;
+  int rows, cout, act_out;
+  int vec_ok;
+  // per-thread tile state
+  long long row;
+  int col0;
+  float inv;
+
+  __device__ __forceinline__ void tile_begin(int m_tile, int n_tile, int q, int lane) {
+    row = (long long)m_tile * kBM + q * 32 + lane;
+    col0 = n_tile * kBN;
+    inv = x_inv[row];       // planes are padded to whole tiles, so the index is always valid
+  }
+  __device__ __forceinline__ void chunk(int chunk, uint32_t (&r)[32]) {
+    const int c = col0 + chunk * 32;
+    if (row >= rows || c >= cout) return;
+    float* y = Y + row * ldy + c;
+    if (vec_ok && c + 32 <= cout) {
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        float4 b4 = bias ? *reinterpret_cast<const float4*>(bias + c + j4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 w4 = *reinterpret_cast<const float4*>(w_inv + c + j4 * 4);
+        float4 o;
+        o.x = act_apply(fmaf(__uint_as_float(r[4 * j4 + 0]), inv * w4.x, b4.x), act_out);
+        o.y = act_apply(fmaf(__uint_as_float(r[4 * j4 + 1]), inv * w4.y, b4.y), act_out);
+        o.z = act_apply(fmaf(__uint_as_float(r[4 * j4 + 2]), inv * w4.z, b4.z), act_out);
+        o.w = act_apply(fmaf(__uint_as_float(r[4 * j4 + 3]), inv * w4.w, b4.w), act_out);
+        reinterpret_cast<float4*>(y)[j4] = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (c + j < cout)
+          y[j] = act_apply(fmaf(__uint_as_float(r[j]), inv * w_inv[c + j], bias ? bias[c + j] : 0.f), act_out);
+    }
+  }
+  __device__ __forceinline__ void finish() {}
+};
+
+struct Layout {
+  long long rows_pad;
+  int k_pad, cout_pad;
+  size_t off_xhi, off_xlo, off_whi, off_wlo, off_xinv, off_winv, total;
+};
+
+Layout make_layout(long long rows, int cin, int cout) {
+  Layout l;
+  l.rows_pad = (rows + kBM - 1) / kBM * kBM;
+  l.k_pad = (cin + kBK - 1) / kBK * kBK;
+  l.cout_pad = (cout + kBN - 1) / kBN * kBN;
+  size_t p = 0;
+  auto take = [&](size_t bytes) { size_t r = p; p += align_up(bytes, 1024); return r; };
+  l.off_xinv = take((size_t)l.rows_pad * 4);
+  l.off_winv = take((size_t)l.cout_pad * 4);
+  l.off_xhi = take((size_t)l.rows_pad * l.k_pad * 2);
+  l.off_xlo = take((size_t)l.rows_pad * l.k_pad * 2);
+  l.off_whi = take((size_t)l.cout_pad * l.k_pad * 2);
+  l.off_wlo = take((size_t)l.cout_pad * l.k_pad * 2);
+  l.total = p;
+  return l;
+}
+
+bool g_linear_attr_set = false;
+
+}  // namespace
+
+extern "C" size_t caspr_linear_tc_workspace_bytes(int rows, int Cin, int Cout) {
+  if (rows <= 0 || Cin <= 0 || Cout <= 0) return 0;
+  return make_layout(rows, Cin, Cout).total;
+}
+
+extern "C" int caspr_linear_tc(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y,
+                               int ldy, int rows, int Cin, int Cout, int act_in, int act_out, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  CASPR_REQUIRE(X && W && Y && workspace && rows > 0 && Cin > 0 && Cout > 0);
+  CASPR_REQUIRE(ldx >= Cin && ldw >= Cin && ldy >= Cout);
+  CASPR_REQUIRE(act_in == CASPR_ACT_NONE || act_in == CASPR_ACT_RELU);
+  CASPR_REQUIRE(((uintptr_t)workspace & 1023) == 0);
+  const Layout l = make_layout(rows, Cin, Cout);
+  if (workspace_bytes < l.total) return CASPR_EWORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  char* base = (char*)workspace;
+  float* xinv = (float*)(base + l.off_xinv);
+  float* winv = (float*)(base + l.off_winv);
+  __half* xhi = (__half*)(base + l.off_xhi);
+  __half* xlo = (__half*)(base + l.off_xlo);
+  __half* whi = (__half*)(base + l.off_whi);
+  __half* wlo = (__half*)(base + l.off_wlo);
+
+  const int nb = 148 * 8;
+  CASPR_COUNT(); split_rows_kernel<<<nb, 256, 0, s>>>(X, ldx, rows, Cin, l.rows_pad, l.k_pad, act_in == CASPR_ACT_RELU,
+                                       (__half2*)xhi, (__half2*)xlo, xinv);
+  CASPR_COUNT(); split_rows_kernel<<<ceil_div(l.cout_pad, 8), 256, 0, s>>>(W, ldw, Cout, Cin, l.cout_pad, l.k_pad, 0,
+                                                            (__half2*)whi, (__half2*)wlo, winv);
+  CASPR_CHECK_LAUNCH();
+
+  CUtensorMap tm_xhi, tm_xlo, tm_whi, tm_wlo;
+  bool ok = true;
+  ok &= caspr_make_tmap_f16(&tm_xhi, xhi, (uint64_t)l.rows_pad, (uint64_t)l.k_pad, kBM);
+  ok &= caspr_make_tmap_f16(&tm_xlo, xlo, (uint64_t)l.rows_pad, (uint64_t)l.k_pad, kBM);
+  ok &= caspr_make_tmap_f16(&tm_whi, whi, (uint64_t)l.cout_pad, (uint64_t)l.k_pad, kBN);
+  ok &= caspr_make_tmap_f16(&tm_wlo, wlo, (uint64_t)l.cout_pad, (uint64_t)l.k_pad, kBN);
+  if (!ok) return CASPR_ELAUNCH;
+  if (!g_linear_attr_set) {
+    if (cudaFuncSetAttribute(tcg::gemm_fp16x3_kernel<LinearEpilogue>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             tcg::kSmemBytes) != cudaSuccess)
+      return CASPR_ELAUNCH;
+    g_linear_attr_set = true;
+  }
+  int dev = 0, num_sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return CASPR_ELAUNCH;
+  LinearEpilogue epi{};
+  epi.bias = bias; epi.x_inv = xinv; epi.w_inv = winv; epi.Y = Y; epi.ldy = ldy; epi.rows = rows; epi.cout = Cout;
+  epi.act_out = act_out;
+  epi.vec_ok = (ldy % 4 == 0) && (((uintptr_t)Y & 15) == 0) && (!bias || ((uintptr_t)bias & 15) == 0);
+  const int m_tiles = (int)(l.rows_pad / kBM), n_tiles = l.cout_pad / kBN;
+  int grid = m_tiles * n_tiles;
+  if (grid > num_sms) grid = num_sms;
+  caspr_prof_begin(CASPR_PROF_LINEAR, s);
+  CASPR_COUNT(); tcg::gemm_fp16x3_kernel<LinearEpilogue><<<grid, tcg::kThreads, tcg::kSmemBytes, s>>>(
+      tm_xhi, tm_xlo, tm_whi, tm_wlo, m_tiles, n_tiles, l.k_pad / kBK, nullptr, epi);
+  caspr_prof_end(CASPR_PROF_LINEAR, s);
+  CASPR_CHECK_LAUNCH();
+  return CASPR_OK;
+}

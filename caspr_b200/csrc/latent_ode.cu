@@ -1,65 +1,77 @@
-// Latent ODE: the whole adaptive dopri5 solve of the 64-d dynamic latent for ALL sequences of
-// the batch in ONE persistent CTA (no host round-trips; torchdiffeq's controller is
+// Latent ODE: the whole adaptive dopri5 solve of the 64-d dynamic latent for ALL sequences of the
+// batch in ONE cooperative kernel launch (no host round-trips; torchdiffeq's controller is
 // batch-global, so the batch cannot be split across independent solvers).
 //
 // Replaces LatentODE.forward / ODESolver / DynamicsNet of caspr/models/latent_ode_model.py:45-70,
 // 76-99,129-147 and torchdiffeq 0.0.1's odeint_adjoint(dopri5) (oracle/odeint001.py).
-// The dynamics are exact fp32 (the solver runs at rtol=atol=1e-3 and its accept/reject
-// decisions must track the oracle's), weights stream from L2 (2.4 MB, resident).
+//
+// Structure: G = 64 co-resident CTAs.  Each CTA keeps its slice of the four weight matrices
+// (H/G output rows of every layer, 37 KB for D=64, H=512) in shared memory for the whole solve, so a
+// dynamics evaluation costs four small dot-product phases separated by grid barriers; the layer
+// activations (B x H) travel through L2.  The RK bookkeeping on the tiny (B x D) state — stage
+// combination, error ratio, accept/reject, step size, dense output — is replicated in every CTA
+// with identical arithmetic, which keeps all CTAs in lock-step without extra barriers.
+// The dynamics are exact fp32 (the solver runs at rtol=atol=1e-3 and its accept/reject decisions
+// must track the oracle's).
 #include "common.cuh"
 #include "dopri5.cuh"
 
 namespace {
 
-constexpr int kThreads = 1024;
+constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kBChunk = 8;
+constexpr int kMaxCtas = 64;
 
 struct LatentParams {
   const float* W[4];
   const float* b[4];
-  int B, D, H;
+  int B, D, H, G;
+  float* act0;          // (B,H) shared between CTAs
+  float* act1;          // (B,H)
+  float* kglob;         // (7,B,D): stage derivatives, written by slices
+  float* priv;          // G private state blocks
+  unsigned* barrier;    // monotonically increasing arrival counter
 };
 
-// out[b][j] = act(sum_k W[j][k] * in[b][k] + bias[j]) for all b: warp per output row j, lanes
-// stride over k (coalesced weight reads), batch handled in register chunks of 8.
-__device__ void dense_layer(const float* W, const float* bias, const float* in, float* out, int B,
-                            int K, int N, bool do_tanh) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int j = warp; j < N; j += kWarps) {
-    const float* wrow = W + (size_t)j * K;
-    for (int b0 = 0; b0 < B; b0 += kBChunk) {
-      float acc[kBChunk];
-#pragma unroll
-      for (int i = 0; i < kBChunk; ++i) acc[i] = 0.f;
-      for (int k = lane; k < K; k += 32) {
-        const float w = wrow[k];
-#pragma unroll
-        for (int i = 0; i < kBChunk; ++i)
-          if (b0 + i < B) acc[i] = fmaf(w, in[(size_t)(b0 + i) * K + k], acc[i]);
-      }
-#pragma unroll
-      for (int i = 0; i < kBChunk; ++i) {
-        float v = warp_sum(acc[i]);
-        if (lane == 0 && b0 + i < B) {
-          v += bias[j];
-          out[(size_t)(b0 + i) * N + j] = do_tanh ? tanhf(v) : v;
-        }
-      }
-    }
-  }
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
 }
 
-// f(z): Linear(D,H) tanh Linear(H,H) tanh Linear(H,H) tanh Linear(H,D)   (latent_ode_model.py:129-147)
-__device__ void dynamics(const LatentParams& p, const float* z, float* dz, float* h0, float* h1) {
-  dense_layer(p.W[0], p.b[0], z, h0, p.B, p.D, p.H, true);
+// Grid-wide barrier (all CTAs are co-resident: cooperative launch).  `epoch` counts the barriers
+// this CTA has passed; the counter never resets.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned nblocks, unsigned& epoch) {
   __syncthreads();
-  dense_layer(p.W[1], p.b[1], h0, h1, p.B, p.H, p.H, true);
+  ++epoch;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const unsigned target = epoch * nblocks;
+    while (ld_volatile_u32(counter) < target) {}
+    __threadfence();
+  }
   __syncthreads();
-  dense_layer(p.W[2], p.b[2], h1, h0, p.B, p.H, p.H, true);
-  __syncthreads();
-  dense_layer(p.W[3], p.b[3], h0, dz, p.B, p.H, p.D, false);
-  __syncthreads();
+}
+
+// out[b][row0 + r] = act(sum_k Wslice[r][k] * in[b][k] + bias) for the CTA's rows; `in` is in shared
+// memory (B x K), Wslice in shared memory (rows x K).  One warp per (row, batch element) item.
+__device__ void dense_slice(const float* __restrict__ Ws, const float* __restrict__ bias_s, const float* __restrict__ in_s,
+                            float* __restrict__ out, int ld_out, int row0, int rows, int B, int K, bool do_tanh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int items = rows * B;
+  for (int it = warp; it < items; it += kWarps) {
+    const int r = it / B, b = it - r * B;
+    const float* w = Ws + (size_t)r * K;
+    const float* x = in_s + (size_t)b * K;
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) acc = fmaf(w[k], x[k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float v = acc + bias_s[r];
+      out[(size_t)b * ld_out + row0 + r] = do_tanh ? tanhf(v) : v;
+    }
+  }
 }
 
 __device__ double block_sum(double v, double* red) {
@@ -74,14 +86,47 @@ __device__ double block_sum(double v, double* red) {
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-latent_ode_kernel(LatentParams p, const float* z0, const double* times, int nT, float rtol,
-                  float atol, float* out, int32_t* info, float* ws, int max_steps) {
+latent_ode_kernel(LatentParams p, const float* __restrict__ z0, const double* __restrict__ times, int nT, float rtol,
+                  float atol, float* __restrict__ out, int32_t* __restrict__ info, int max_steps) {
+  extern __shared__ float smem[];
   __shared__ double red[kWarps];
   __shared__ double s_t0, s_t1, s_dt;
-  __shared__ int s_flag;
-  const int n = p.B * p.D;
+  __shared__ float s_dts;
+  const int B = p.B, D = p.D, H = p.H, G = p.G;
+  const int n = B * D;
   const int tid = threadIdx.x;
-  float* y0 = ws;                    // state at the start of the current step
+  const int cta = blockIdx.x;
+  // rows of the hidden layers / of the output layer owned by this CTA
+  const int rh = (H + G - 1) / G, rd = (D + G - 1) / G;
+  const int h0r = min(cta * rh, H), h1r = min(h0r + rh, H);
+  const int d0r = min(cta * rd, D), d1r = min(d0r + rd, D);
+  const int nh = h1r - h0r, nd = d1r - d0r;
+  // shared memory carve-up: weight slices, biases, activation staging buffer
+  float* sW0 = smem;                          // nh x D
+  float* sW1 = sW0 + (size_t)rh * D;          // nh x H
+  float* sW2 = sW1 + (size_t)rh * H;          // nh x H
+  float* sW3 = sW2 + (size_t)rh * H;          // nd x H
+  float* sb0 = sW3 + (size_t)rd * H;
+  float* sb1 = sb0 + rh;
+  float* sb2 = sb1 + rh;
+  float* sb3 = sb2 + rh;
+  float* sact = sb3 + rd;                     // B x max(H, D)
+  for (int i = tid; i < nh * D; i += kThreads) sW0[i] = p.W[0][(size_t)h0r * D + i];
+  for (int i = tid; i < nh * H; i += kThreads) {
+    sW1[i] = p.W[1][(size_t)h0r * H + i];
+    sW2[i] = p.W[2][(size_t)h0r * H + i];
+  }
+  for (int i = tid; i < nd * H; i += kThreads) sW3[i] = p.W[3][(size_t)d0r * H + i];
+  for (int i = tid; i < nh; i += kThreads) {
+    sb0[i] = p.b[0][h0r + i];
+    sb1[i] = p.b[1][h0r + i];
+    sb2[i] = p.b[2][h0r + i];
+  }
+  for (int i = tid; i < nd; i += kThreads) sb3[i] = p.b[3][d0r + i];
+  __syncthreads();
+
+  // private (per-CTA, identical content in every CTA) state block
+  float* y0 = p.priv + (size_t)cta * 14 * n;
   float* k = y0 + n;                 // 7 stage derivatives
   float* ys = k + 7 * (size_t)n;     // stage input / y1
   float* ymid = ys + n;
@@ -89,17 +134,39 @@ latent_ode_kernel(LatentParams p, const float* z0, const double* times, int nT, 
   float* f0prev = yprev + n;
   float* y1acc = f0prev + n;
   float* f1acc = y1acc + n;
-  float* h0 = f1acc + n;
-  float* h1 = h0 + (size_t)p.B * p.H;
+  unsigned epoch = 0;
+
+  // f(z): Linear(D,H) tanh Linear(H,H) tanh Linear(H,H) tanh Linear(H,D)   (latent_ode_model.py:129-147)
+  auto dynamics = [&](const float* z, int slot) {
+    for (int i = tid; i < n; i += kThreads) sact[i] = z[i];
+    __syncthreads();
+    dense_slice(sW0, sb0, sact, p.act0, H, h0r, nh, B, D, true);
+    grid_barrier(p.barrier, G, epoch);
+    for (int i = tid; i < B * H; i += kThreads) sact[i] = __ldcg(p.act0 + i);
+    __syncthreads();
+    dense_slice(sW1, sb1, sact, p.act1, H, h0r, nh, B, H, true);
+    grid_barrier(p.barrier, G, epoch);
+    for (int i = tid; i < B * H; i += kThreads) sact[i] = __ldcg(p.act1 + i);
+    __syncthreads();
+    dense_slice(sW2, sb2, sact, p.act0, H, h0r, nh, B, H, true);
+    grid_barrier(p.barrier, G, epoch);
+    for (int i = tid; i < B * H; i += kThreads) sact[i] = __ldcg(p.act0 + i);
+    __syncthreads();
+    float* kg = p.kglob + (size_t)slot * n;
+    dense_slice(sW3, sb3, sact, kg, D, d0r, nd, B, H, false);
+    grid_barrier(p.barrier, G, epoch);
+    for (int i = tid; i < n; i += kThreads) k[(size_t)slot * n + i] = __ldcg(kg + i);
+    __syncthreads();
+  };
 
   int nfe = 0, accepted = 0, rejected = 0, status = CASPR_OK;
   for (int i = tid; i < n; i += kThreads) {
     float v = z0[i];
     y0[i] = v;
-    out[i] = v;                                       // solution[0] = y0
+    if (cta == 0) out[i] = v;                         // solution[0] = y0
   }
   __syncthreads();
-  dynamics(p, y0, k, h0, h1);                         // f0
+  dynamics(y0, 0);                                    // f0
   nfe++;
 
   // ---- _select_initial_step(order 4), fp32 like torch
@@ -119,7 +186,7 @@ latent_ode_kernel(LatentParams p, const float* z0, const double* times, int nT, 
   else hh0 = __fmul_rn(0.01f, __fdiv_rn(d0, d1));
   for (int i = tid; i < n; i += kThreads) ys[i] = __fadd_rn(y0[i], __fmul_rn(hh0, k[i]));
   __syncthreads();
-  dynamics(p, ys, k + n, h0, h1);                     // f1 probe (stored in k[1], overwritten later)
+  dynamics(ys, 1);                                    // f1 probe (slot 1 is overwritten by the first step)
   nfe++;
   double q2 = 0.0;
   for (int i = tid; i < n; i += kThreads) {
@@ -136,6 +203,7 @@ latent_ode_kernel(LatentParams p, const float* z0, const double* times, int nT, 
     s_t0 = times[0];
     s_t1 = times[0];
     s_dt = (double)fminf(__fmul_rn(100.f, hh0), hh1);
+    s_dts = 0.f;
   }
   __syncthreads();
 
@@ -146,7 +214,6 @@ latent_ode_kernel(LatentParams p, const float* z0, const double* times, int nT, 
       if (steps_here++ >= max_steps) { status = CASPR_ESOLVER_MAXSTEPS; break; }
       const double t0 = s_t1, dt = s_dt;
       if (!(t0 + dt > t0)) { status = CASPR_ESOLVER_DT; break; }
-      // non-finite check on y0
       int bad = 0;
       for (int i = tid; i < n; i += kThreads) bad |= !isfinite(y0[i]);
       bad = __syncthreads_or(bad);
@@ -160,7 +227,7 @@ latent_ode_kernel(LatentParams p, const float* z0, const double* times, int nT, 
           ys[i] = dopri5::stage_combine(y0[i], dtf, kv, s);
         }
         __syncthreads();
-        dynamics(p, ys, k + (size_t)(s + 1) * n, h0, h1);
+        dynamics(ys, s + 1);
         nfe++;
       }
       // error ratio (ys holds y1)
@@ -199,7 +266,7 @@ latent_ode_kernel(LatentParams p, const float* z0, const double* times, int nT, 
         s_t0 = t0;
         s_t1 = accept ? t0 + dt : t0;
         s_dt = dopri5::optimal_step(dt, ratio);
-        if (accept) s_flag = __float_as_int(dtf);      // dt of the step the dense output belongs to
+        if (accept) s_dts = dtf;                       // dt of the step the dense output belongs to
       }
       __syncthreads();
     }
@@ -207,13 +274,14 @@ latent_ode_kernel(LatentParams p, const float* z0, const double* times, int nT, 
     // dense output at t_out (abscissa formed in fp32 like _interp_evaluate)
     const float t0f = (float)s_t0, t1f = (float)s_t1, tf = (float)t_out;
     const float x = __fdiv_rn(__fsub_rn(tf, t0f), __fsub_rn(t1f, t0f));
-    const float dts = __int_as_float(s_flag);
-    for (int i = tid; i < n; i += kThreads)
-      out[(size_t)io * n + i] =
-          dopri5::interp_eval(yprev[i], y1acc[i], ymid[i], f0prev[i], f1acc[i], dts, x);
+    const float dts = s_dts;
+    if (cta == 0)
+      for (int i = tid; i < n; i += kThreads)
+        out[(size_t)io * n + i] =
+            dopri5::interp_eval(yprev[i], y1acc[i], ymid[i], f0prev[i], f1acc[i], dts, x);
     __syncthreads();
   }
-  if (tid == 0) {
+  if (cta == 0 && tid == 0) {
     info[INFO_STATUS] = status;
     info[INFO_NFE] = nfe;
     info[INFO_ACCEPTED] = accepted;
@@ -222,11 +290,36 @@ latent_ode_kernel(LatentParams p, const float* z0, const double* times, int nT, 
   }
 }
 
+struct Sizes {
+  int G;
+  size_t smem_bytes;
+  size_t off_act0, off_act1, off_kglob, off_priv, off_barrier, off_times, total;
+};
+
+Sizes make_sizes(int B, int D, int H) {
+  Sizes z;
+  z.G = kMaxCtas;
+  const int rh = (H + z.G - 1) / z.G, rd = (D + z.G - 1) / z.G;
+  const int kmax = H > D ? H : D;
+  z.smem_bytes = ((size_t)rh * D + 2 * (size_t)rh * H + (size_t)rd * H + 3 * rh + rd + (size_t)B * kmax) * sizeof(float);
+  size_t p = 0;
+  auto take = [&](size_t bytes) { size_t r = p; p += align_up(bytes, 256); return r; };
+  const size_t n = (size_t)B * D;
+  z.off_barrier = take(256);
+  z.off_times = take(64 * sizeof(double));
+  z.off_act0 = take((size_t)B * H * 4);
+  z.off_act1 = take((size_t)B * H * 4);
+  z.off_kglob = take(7 * n * 4);
+  z.off_priv = take((size_t)z.G * 14 * n * 4);
+  z.total = p;
+  return z;
+}
+
 }  // namespace
 
 extern "C" size_t caspr_latent_ode_workspace_bytes(int B, int D, int H) {
-  size_t n = (size_t)B * D;
-  return (n * 15 + (size_t)B * H * 2) * sizeof(float) + 8 * sizeof(double) * 64;
+  if (B <= 0 || D <= 0 || H <= 0) return 0;
+  return make_sizes(B, D, H).total;
 }
 
 extern "C" int caspr_latent_ode_solve(const float* z0, int B, int D, int H, const float* W0,
@@ -236,22 +329,38 @@ extern "C" int caspr_latent_ode_solve(const float* z0, int B, int D, int H, cons
                                       float atol, float* out, int32_t* info, int32_t* h_info,
                                       void* workspace, size_t workspace_bytes, void* stream) {
   CASPR_REQUIRE(z0 && W0 && b0 && W1 && b1 && W2 && b2 && W3 && b3 && h_times && out && info && h_info);
-  CASPR_REQUIRE(B > 0 && D > 0 && H > 0 && nT >= 1 && nT <= 64);
+  CASPR_REQUIRE(workspace && B > 0 && D > 0 && H > 0 && nT >= 1 && nT <= 64);
+  CASPR_REQUIRE(((uintptr_t)workspace & 255) == 0);
   for (int i = 1; i < nT; ++i) CASPR_REQUIRE(h_times[i] > h_times[i - 1]);
-  if (workspace_bytes < caspr_latent_ode_workspace_bytes(B, D, H)) return CASPR_EWORKSPACE;
+  const Sizes z = make_sizes(B, D, H);
+  CASPR_REQUIRE(z.smem_bytes <= 200 * 1024);            // B x max(H,D) staging + weight slices must fit
+  if (workspace_bytes < z.total) return CASPR_EWORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
-  // time grid lives at the tail of the workspace (64 doubles reserved)
-  size_t n = (size_t)B * D;
-  float* ws = (float*)workspace;
-  double* d_times = (double*)((char*)workspace + align_up((n * 15 + (size_t)B * H * 2) * sizeof(float), 8));
+  char* base = (char*)workspace;
+  double* d_times = (double*)(base + z.off_times);
+  if (cudaMemsetAsync(base + z.off_barrier, 0, 256, s) != cudaSuccess) return CASPR_ELAUNCH;
   if (cudaMemcpyAsync(d_times, h_times, nT * sizeof(double), cudaMemcpyHostToDevice, s) != cudaSuccess)
     return CASPR_ELAUNCH;
   LatentParams p;
   p.W[0] = W0; p.W[1] = W1; p.W[2] = W2; p.W[3] = W3;
   p.b[0] = b0; p.b[1] = b1; p.b[2] = b2; p.b[3] = b3;
-  p.B = B; p.D = D; p.H = H;
-  CASPR_COUNT(); latent_ode_kernel<<<1, kThreads, 0, s>>>(p, z0, d_times, nT, rtol, atol, out, info, ws, 100000);
-  CASPR_CHECK_LAUNCH();
+  p.B = B; p.D = D; p.H = H; p.G = z.G;
+  p.act0 = (float*)(base + z.off_act0);
+  p.act1 = (float*)(base + z.off_act1);
+  p.kglob = (float*)(base + z.off_kglob);
+  p.priv = (float*)(base + z.off_priv);
+  p.barrier = (unsigned*)(base + z.off_barrier);
+  if (z.smem_bytes > 48 * 1024) {
+    if (cudaFuncSetAttribute(latent_ode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)z.smem_bytes) != cudaSuccess)
+      return CASPR_EINVAL;
+  }
+  int max_steps = 100000;
+  void* args[] = {&p, (void*)&z0, (void*)&d_times, &nT, &rtol, &atol, (void*)&out, (void*)&info, &max_steps};
+  CASPR_COUNT();
+  if (cudaLaunchCooperativeKernel((const void*)latent_ode_kernel, dim3(z.G), dim3(kThreads), args, z.smem_bytes, s) !=
+      cudaSuccess)
+    return CASPR_ELAUNCH;
   if (cudaMemcpyAsync(h_info, info, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, s) != cudaSuccess)
     return CASPR_ELAUNCH;
   if (cudaStreamSynchronize(s) != cudaSuccess) return CASPR_ELAUNCH;

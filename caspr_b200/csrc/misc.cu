@@ -20,6 +20,7 @@ extern "C" const char* caspr_status_string(int status) {
 // ------------------------------------------------------------------ launch count / profiling
 unsigned long long g_caspr_launches = 0;
 extern "C" unsigned long long caspr_launch_count(void) { return g_caspr_launches; }
+extern "C" void caspr_launch_count_add(unsigned long long n) { g_caspr_launches += n; }
 
 namespace {
 constexpr int kProfKernels = 8;

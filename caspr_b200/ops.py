@@ -127,10 +127,16 @@ def three_interp_concat(feat_prev, idx, dist, skip):
 
 
 # ------------------------------------------------------------------------------ dense ops
-def linear(x, weight, bias=None, out=None, act_in=ACT_NONE, act_out=ACT_NONE):
+# layers at least this large run on the tcgen05 fp16x3 GEMM, the rest on the exact-fp32 SIMT kernel
+TC_MIN_ROWS, TC_MIN_CIN, TC_MIN_COUT = 2048, 64, 64
+LINEAR_ENGINE = 'auto'          # module-wide override used by accuracy studies: 'auto' | 'tc' | 'simt'
+
+
+def linear(x, weight, bias=None, out=None, act_in=ACT_NONE, act_out=ACT_NONE, engine='auto'):
     """1x1 Conv1d / Linear on rows: y = act_out(act_in(x) @ W^T + b).
 
-    x (rows, Cin) view; weight (Cout, Cin) or Conv1d-shaped (Cout, Cin, 1); out optional (rows, Cout) view."""
+    x (rows, Cin) view; weight (Cout, Cin) or Conv1d-shaped (Cout, Cin, 1); out optional (rows, Cout) view.
+    engine: 'auto' (tensor cores for large layers), 'tc' or 'simt'."""
     x, ldx = _rows2d(x, 'x')
     w = weight.reshape(weight.shape[0], weight.shape[1])
     _f32(w, 'weight')
@@ -142,6 +148,18 @@ def linear(x, weight, bias=None, out=None, act_in=ACT_NONE, act_out=ACT_NONE):
         out = torch.empty(rows, cout, dtype=torch.float32, device=x.device)
     out, ldy = _rows2d(out, 'out')
     assert out.shape == (rows, cout)
+    if engine == 'auto' and LINEAR_ENGINE != 'auto':
+        engine = LINEAR_ENGINE if (LINEAR_ENGINE == 'simt' or cin >= 16) else 'simt'
+    if engine == 'auto':
+        engine = 'tc' if (rows >= TC_MIN_ROWS and cin >= TC_MIN_CIN and cout >= TC_MIN_COUT) else 'simt'
+    if engine == 'tc':
+        ws_bytes = lib.caspr_linear_tc_workspace_bytes(rows, cin, cout)
+        ws = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device=x.device)
+        ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
+        _count('linear_tc')
+        check(lib.caspr_linear_tc(_p(x), ldx, _p(w), cin, _p(bias), _p(out), ldy, rows, cin, cout, act_in, act_out,
+                                  ctypes.c_void_p(ws_ptr), ws_bytes, _stream()), 'caspr_linear_tc')
+        return out
     _count('linear')
     check(lib.caspr_linear(_p(x), ldx, _p(w), cin, _p(bias), _p(out), ldy, rows, cin, cout, act_in, act_out,
                            _stream()), 'caspr_linear')

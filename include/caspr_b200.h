@@ -43,6 +43,9 @@ const char* caspr_status_string(int status);
 
 /* Number of kernels the library has launched in this process (bench.py: gpu_launches). */
 unsigned long long caspr_launch_count(void);
+/* Kernels replayed from a CUDA graph are launched by the driver, not through the entry points: the
+ * host adds the number of kernel nodes of a replayed graph here. */
+void caspr_launch_count_add(unsigned long long n);
 
 /* CUDA-event timing of the dominant kernels, measured on the stream they are launched on.
  * caspr_profile_enable(1) clears the records and starts recording one event pair around every
@@ -99,6 +102,16 @@ enum { CASPR_ACT_NONE = 0, CASPR_ACT_RELU = 1, CASPR_ACT_SIGMOID = 2 };
 int caspr_linear(const float* X, int ldx, const float* W, int ldw, const float* bias,
                  float* Y, int ldy, int rows, int Cin, int Cout, int act_in, int act_out,
                  void* stream);
+
+/* Same contract on the tcgen05 tensor cores: 3-product fp16 split ("fp16x3",
+ * X_hi.W_hi + X_lo.W_hi + X_hi.W_lo, fp32 accumulate in TMEM), operands scaled per call by powers of
+ * two taken from max|X| and max|W| (undone exactly in the epilogue).  Meant for the large layers
+ * (feature propagation, final layers, the 1600-wide head); any Cin / Cout / rows are accepted.
+ * workspace: caspr_linear_tc_workspace_bytes(rows, Cin, Cout) bytes, 1024-byte aligned. */
+size_t caspr_linear_tc_workspace_bytes(int rows, int Cin, int Cout);
+int caspr_linear_tc(const float* X, int ldx, const float* W, int ldw, const float* bias,
+                    float* Y, int ldy, int rows, int Cin, int Cout, int act_in, int act_out,
+                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* GroupNorm over samples of `rows_per_sample` consecutive rows (torch.nn.GroupNorm(groups, C)
  * on (samples, C, rows_per_sample)), eps as given; optional ReLU; optional max over the rows

@@ -126,6 +126,34 @@ def test_linear_matches_fp32(ops, rows, cin, cout):
     assert _rel(out2, ref2) < 2e-6
 
 
+@pytest.mark.parametrize('rows,cin,cout,act', [(4096, 64, 64, 0), (3000, 131, 64, 1), (2500, 515, 256, 0),
+                                               (4224, 1600, 1600, 1), (2048, 518, 512, 0), (2100, 96, 300, 2)])
+def test_linear_tensor_core_fp32_grade(ops, rows, cin, cout, act):
+    """tcgen05 fp16x3 GEMM (caspr_linear_tc): ragged K / N / rows, fp32-grade accuracy vs fp64."""
+    g = torch.Generator().manual_seed(rows + cin)
+    x = torch.randn(rows, cin, generator=g) * 3.0
+    w = torch.randn(cout, cin, generator=g) / cin ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    ref = ref.relu() if act == 1 else (torch.sigmoid(ref) if act == 2 else ref)
+    out = ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), act_out=act, engine='tc')
+    # one fp32 truncation per tcgen05.mma accumulation (3*K/16 of them) adds a K-proportional bias
+    assert _rel(out, ref) < 3e-6 * max(1.0, cin / 400.0)
+    simt = ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), act_out=act, engine='simt')
+    assert _rel(out, simt) < 6e-6 * max(1.0, cin / 400.0)     # both engines carry their own rounding
+
+
+def test_linear_tensor_core_strided_and_relu_in(ops):
+    g = torch.Generator().manual_seed(9)
+    buf = torch.randn(2304, 200, generator=g).to(DEV)
+    w = torch.randn(100, 128, generator=g).to(DEV)
+    out = torch.zeros(2304, 160, device=DEV)
+    ops.linear(buf[:, 8:136], w, None, out=out[:, 30:130], act_in=ops.ACT_RELU, engine='tc')
+    ref = buf[:, 8:136].double().relu() @ w.double().t()
+    assert _rel(out[:, 30:130], ref) < 3e-6
+    assert float(out[:, :30].abs().sum()) == 0 and float(out[:, 130:].abs().sum()) == 0
+
+
 def test_linear_strided_views(ops):
     g = torch.Generator().manual_seed(5)
     buf = torch.randn(200, 96, generator=g).to(DEV)
@@ -211,6 +239,43 @@ def test_encoder_indices_and_features(case):
     assert _rel(tnocs, gold['tnocs']) < 1e-4
 
 
+def test_encoder_cuda_graph_matches_eager(case):
+    """The CUDA-graph replay of the encoder returns exactly what the eager launch sequence returns, also
+    after the weights are updated in place and for a second input."""
+    _, gold, model, _, x, _ = case
+    enc = model.encoder
+    x2, _ = synthetic_sequences(1, 3, 1024, seed=5)
+    for xin in (x, x2, x):
+        enc.use_cuda_graph = False
+        z_e, t_e = enc(xin.to(DEV))
+        enc.use_cuda_graph = True
+        z_g, t_g = enc(xin.to(DEV))
+        assert torch.equal(z_e, z_g) and torch.equal(t_e, t_g)
+    w = enc.conv1.weight
+    with torch.no_grad():
+        w.mul_(1.01)
+    z_g2, _ = enc(x.to(DEV))
+    enc.use_cuda_graph = False
+    z_e2, _ = enc(x.to(DEV))
+    enc.use_cuda_graph = True
+    with torch.no_grad():
+        w.div_(1.01)
+    assert torch.equal(z_e2, z_g2) and not torch.equal(z_g2, z_g)
+
+
+@pytest.mark.parametrize('B', [1, 5, 32])
+def test_latent_ode_batch_sizes(case, B):
+    """Cooperative 64-CTA latent solver: batch-global step control for several batch sizes."""
+    _, gold, model, oracle, _, _ = case
+    g = torch.Generator().manual_seed(B)
+    z0 = 0.5 * torch.randn(B, 64, generator=g)
+    t = torch.linspace(0, 1, 10)
+    ref = oracle.latent_ode(z0, t)
+    out = model.latent_ode(z0.to(DEV), t.to(DEV))
+    assert int(model.latent_ode.num_evals()) == oracle.nfe[0]
+    assert _rel(out, ref) < 1e-5
+
+
 def test_latent_ode_matches_oracle(case):
     _, gold, model, oracle, _, _ = case
     z0 = torch.from_numpy(gold['z0'])
@@ -264,7 +329,7 @@ def test_reconstruct_matches_reference_fixture(case, engine):
     assert _rel(xr, gold['rec_x']) < 1e-4                       # north_star tolerance
     assert _rel(logp_y, gold['rec_logp_y']) < 1e-5
     cd = chamfer_distance(xr.cpu().view(3, 256, 3), torch.from_numpy(gold['rec_x']).view(3, 256, 3))
-    assert float(cd.max()) < 1e-8
+    assert float(cd.max()) < 5e-8        # ~ (1e-4 relative)^2 per direction; see DESIGN.md on encoder conditioning
 
 
 def test_interpolated_reconstruct_matches_reference_fixture(case, engine):
