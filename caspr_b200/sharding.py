@@ -1,0 +1,69 @@
+"""Batch sharding of the reconstruction path across the GPUs of one box.
+
+The path shards by SEQUENCE (batch dim): every cross-element reduction of the model is within a
+sequence or a cloud (GroupNorm per sample, max-pools per sequence, frozen MovingBatchNorm statistics in
+eval), so ranks need no data-path collective.  The reference's only multi-GPU
+mechanism is single-process ``nn.DataParallel`` (caspr/train.py:131-132), whose replicas each run their
+own adaptive step controller — the same "independent" semantics as here: one process per GPU, rank r
+owns sequences [lo, hi) and solves with its own step sequence.
+
+NCCL (or gloo on CPU) is used only to gather results / timings, never inside the hot path.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous, balanced partition of range(n_items): the first (n_items % world) ranks get one extra."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError('bad rank/world: %r/%r' % (rank, world))
+    base, extra = divmod(int(n_items), world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def gather_batch(local, n_items, group=None):
+    """All-gather per-rank result shards (dim 0 = this rank's sequences, possibly empty) back into the
+    unsharded order.  Works for uneven shards by padding to the largest one."""
+    world = dist.get_world_size(group)
+    sizes = [shard_range(n_items, r, world) for r in range(world)]
+    max_n = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((max_n,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([b[:hi - lo] for b, (lo, hi) in zip(bufs, sizes)], dim=0)
+
+
+def reconstruct_sharded(model, x, gather=True, group=None, **kwargs):
+    """``model.reconstruct`` over this rank's slice of the batch.  Per-sequence keyword tensors ``y`` (base
+    samples) and ``e`` (Hutchinson noise) given for the FULL batch are sliced consistently.
+
+    Returns the local 4-tuple, or — with ``gather`` — the tuple gathered over ranks in batch order."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    B, T = x.shape[0], x.shape[1]
+    lo, hi = shard_range(B, rank, world)
+    kw = dict(kwargs)
+    ts = kw.get('timestamps')
+    Tq = T if ts is None else int(ts.numel())
+    per_seq_y = 1 if kw.get('constant_in_time', False) else Tq
+    if kw.get('y') is not None:
+        kw['y'] = kw['y'].reshape(B * per_seq_y, *kw['y'].shape[-2:])[lo * per_seq_y:hi * per_seq_y]
+    if kw.get('e') is not None:
+        kw['e'] = kw['e'].reshape(B * Tq, *kw['e'].shape[-2:])[lo * Tq:hi * Tq]
+    if hi > lo:
+        out = model.reconstruct(x[lo:hi], **kw)
+    else:                                   # more ranks than sequences: this rank idles
+        P = kw.get('num_points', 1024)
+        z = x.new_zeros((0, Tq, P, 3))
+        out = (z, x.new_zeros((0, Tq, P)), z, x.new_zeros((0, T, x.shape[2], 4)))
+    if not gather:
+        return out
+    return tuple(None if o is None else gather_batch(o, B, group) for o in out)
+
+
+def max_over_ranks(value, device, group=None):
+    """Max of a python float over ranks (multi-GPU timings are reported as the slowest rank's)."""
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())
