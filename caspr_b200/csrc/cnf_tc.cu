@@ -74,6 +74,16 @@ struct CnfEpilogue {
   bool live;
   float range_max;
   float pa[3], pv[3];    // fused output layer: partial dot products of this thread's columns
+  // TMA-store staging (OUT_F16): hi box at staging, lo box 16 KB behind it
+  uint8_t* stg;
+  const CUtensorMap* tm_hi;
+  const CUtensorMap* tm_lo;
+  int etid, m_tile_cur, n_tile_cur, box_row;
+  bool stores_in_flight;
+
+  __device__ __forceinline__ void setup(uint8_t* staging, const CUtensorMap* o_hi, const CUtensorMap* o_lo, int epi_tid) {
+    stg = staging; tm_hi = o_hi; tm_lo = o_lo; etid = epi_tid; stores_in_flight = false;
+  }
 
   __device__ __forceinline__ void tile_begin(int m_tile, int n_tile, int q, int lane) {
     is_v = lane >> 4;
@@ -85,6 +95,7 @@ struct CnfEpilogue {
     gp = gate + (size_t)f * ld_hyper + col0;
     bp = biasf + (size_t)f * ld_hyper + col0;
     row_h = (size_t)m_tile * kBM + q * 32 + (lane & 15);
+    m_tile_cur = m_tile; n_tile_cur = n_tile; box_row = q * 32 + (lane & 15);
     if (OUT_F32) {
       if (pending) flush();                // previous tile's sums (kept until now to overlap the atomics)
       pa[0] = pa[1] = pa[2] = pv[0] = pv[1] = pv[2] = 0.f;
@@ -160,7 +171,9 @@ struct CnfEpilogue {
         }
       }
     } else {
-      const size_t row_v = row_h + 16;
+      // Stage 64 columns (two chunks) of the hi / lo planes in shared memory in the 128-byte-swizzled
+      // box layout of the tensor map, then one thread stores both boxes with TMA (full 128-byte lines
+      // instead of 16-byte scattered stores).
       uint32_t hh[8], hl[8], vh[8], vl[8];
 #pragma unroll
       for (int j2 = 0; j2 < 8; ++j2) {
@@ -170,19 +183,40 @@ struct CnfEpilogue {
         split2(h0, h1, hh[j2], hl[j2]);
         split2(v0, v1, vh[j2], vl[j2]);
       }
-      uint4* d;
-      d = reinterpret_cast<uint4*>(out_hi + row_h * 512 + col);
-      d[0] = make_uint4(hh[0], hh[1], hh[2], hh[3]); d[1] = make_uint4(hh[4], hh[5], hh[6], hh[7]);
-      d = reinterpret_cast<uint4*>(out_lo + row_h * 512 + col);
-      d[0] = make_uint4(hl[0], hl[1], hl[2], hl[3]); d[1] = make_uint4(hl[4], hl[5], hl[6], hl[7]);
-      d = reinterpret_cast<uint4*>(out_hi + row_v * 512 + col);
-      d[0] = make_uint4(vh[0], vh[1], vh[2], vh[3]); d[1] = make_uint4(vh[4], vh[5], vh[6], vh[7]);
-      d = reinterpret_cast<uint4*>(out_lo + row_v * 512 + col);
-      d[0] = make_uint4(vl[0], vl[1], vl[2], vl[3]); d[1] = make_uint4(vl[4], vl[5], vl[6], vl[7]);
+      const int odd = chunk & 1;
+      if (!odd && stores_in_flight) {
+        if (etid == 0) tc::tma_store_wait_read();          // previous boxes have left shared memory
+        tc::named_bar_sync(1, 128);
+      }
+      // 16-byte chunk index inside the 128-byte box row, XOR-swizzled with the row
+      const int cc0 = odd * 4 + is_v * 2;
+      uint8_t* hi_box = stg;
+      uint8_t* lo_box = stg + kBM * 128;
+      const int rh = box_row, rv = box_row + 16;
+      *reinterpret_cast<uint4*>(hi_box + rh * 128 + (((cc0) ^ (rh & 7)) << 4)) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+      *reinterpret_cast<uint4*>(hi_box + rh * 128 + (((cc0 + 1) ^ (rh & 7)) << 4)) = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+      *reinterpret_cast<uint4*>(lo_box + rh * 128 + (((cc0) ^ (rh & 7)) << 4)) = make_uint4(hl[0], hl[1], hl[2], hl[3]);
+      *reinterpret_cast<uint4*>(lo_box + rh * 128 + (((cc0 + 1) ^ (rh & 7)) << 4)) = make_uint4(hl[4], hl[5], hl[6], hl[7]);
+      *reinterpret_cast<uint4*>(hi_box + rv * 128 + (((cc0) ^ (rv & 7)) << 4)) = make_uint4(vh[0], vh[1], vh[2], vh[3]);
+      *reinterpret_cast<uint4*>(hi_box + rv * 128 + (((cc0 + 1) ^ (rv & 7)) << 4)) = make_uint4(vh[4], vh[5], vh[6], vh[7]);
+      *reinterpret_cast<uint4*>(lo_box + rv * 128 + (((cc0) ^ (rv & 7)) << 4)) = make_uint4(vl[0], vl[1], vl[2], vl[3]);
+      *reinterpret_cast<uint4*>(lo_box + rv * 128 + (((cc0 + 1) ^ (rv & 7)) << 4)) = make_uint4(vl[4], vl[5], vl[6], vl[7]);
+      if (odd) {
+        tc::fence_proxy_async_smem();
+        tc::named_bar_sync(1, 128);
+        if (etid == 0) {
+          const int c_out = n_tile_cur * kBN + (chunk >> 1) * 64;
+          tc::tma_store_2d(tm_hi, hi_box, c_out, m_tile_cur * kBM);
+          tc::tma_store_2d(tm_lo, lo_box, c_out, m_tile_cur * kBM);
+          tc::tma_store_commit();
+        }
+        stores_in_flight = true;
+      }
     }
   }
 
   __device__ __forceinline__ void finish() {
+    if (!OUT_F32 && stores_in_flight && etid == 0) tc::tma_store_wait_all();
     if (OUT_F32 && pending) flush();
     if (!OUT_F32 && range_max > 65504.f) atomicOr(range_flag, 1);
   }
@@ -428,15 +462,15 @@ int enqueue_mid(const Plan& plan, int layer, const float* gate, const float* bia
     epi.gate = gate; epi.biasf = biasf; epi.ld_hyper = ld_hyper; epi.n = n; epi.P = P;
     epi.out_hi = plan.b_hi; epi.out_lo = plan.b_lo; epi.range_flag = range_flag;
     tcg::gemm_fp16x3_kernel<CnfEpilogue<false>><<<grid, tcg::kThreads, tcg::kSmemBytes, s>>>(
-        plan.tm_act[0][0], plan.tm_act[0][1], plan.tm_w[0][0], plan.tm_w[0][1], plan.n_tiles, 2, 512 / tcg::kBK, skip,
-        epi);
+        plan.tm_act[0][0], plan.tm_act[0][1], plan.tm_w[0][0], plan.tm_w[0][1], plan.tm_act[1][0], plan.tm_act[1][1],
+        plan.n_tiles, 2, 512 / tcg::kBK, skip, epi);
   } else {
     CnfEpilogue<true> epi{};
     epi.gate = gate; epi.biasf = biasf; epi.ld_hyper = ld_hyper; epi.n = n; epi.P = P;
     epi.W3 = W3; epi.acc6 = acc6; epi.range_flag = range_flag; epi.pending = false;
     tcg::gemm_fp16x3_kernel<CnfEpilogue<true>><<<grid, tcg::kThreads, tcg::kSmemBytes, s>>>(
-        plan.tm_act[1][0], plan.tm_act[1][1], plan.tm_w[1][0], plan.tm_w[1][1], plan.n_tiles, 2, 512 / tcg::kBK, skip,
-        epi);
+        plan.tm_act[1][0], plan.tm_act[1][1], plan.tm_w[1][0], plan.tm_w[1][1], plan.tm_act[1][0], plan.tm_act[1][1],
+        plan.n_tiles, 2, 512 / tcg::kBK, skip, epi);
   }
   caspr_prof_end(CASPR_PROF_CNF_FUSED_TC, s);
   CASPR_CHECK_LAUNCH();

@@ -15,6 +15,9 @@
 // CTAs working on the same rows run together and share the A tile through L2.
 //
 // Epilogue functor interface (all calls are made by the 128 epilogue threads):
+//   void setup(uint8_t* staging, const CUtensorMap* out_hi, const CUtensorMap* out_lo, int epi_tid);
+//        staging: 32 KB of shared memory (two 128 x 64 fp16 boxes) for epilogues that store through TMA
+//        (tm_o_hi / tm_o_lo are kernel parameters; epilogues that store directly ignore them)
 //   void tile_begin(int m_tile, int n_tile, int quadrant, int lane);
 //   void chunk(int chunk_idx, uint32_t (&acc)[32]);   // fp32 bits of columns chunk*32 .. +31 of this thread's row
 //   void finish();                                     // once, after the last tile
@@ -27,18 +30,21 @@ constexpr int kBM = 128, kBN = 256, kBK = 64, kStages = 2;
 constexpr int kATile = kBM * kBK * 2;                    // 16 KB
 constexpr int kWTile = kBN * kBK * 2;                    // 32 KB
 constexpr int kStageBytes = 2 * kATile + 2 * kWTile;     // 96 KB
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+constexpr int kStagingBytes = 2 * kBM * 64 * 2;          // epilogue staging: hi and lo boxes of 128 rows x 64 fp16
+constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + 256;
 constexpr int kThreads = 192;
 
 template <class Epilogue>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_fp16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                   const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
                    int m_tiles, int n_tiles, int k_chunks, const int* __restrict__ skip_flag, Epilogue epi) {
   if (skip_flag && *skip_flag) return;       // device-side "solve finished" flag (CNF solver)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint8_t* staging = smem + kStages * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
   uint64_t* full = bars;                 // [kStages]
   uint64_t* empty = bars + kStages;      // [kStages]
   uint64_t* tfull = bars + 2 * kStages;  // [2]
@@ -122,6 +128,7 @@ gemm_fp16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     }
   } else {
     const int q = warp & 3;                                       // TMEM lane quadrant of this warp
+    epi.setup(staging, &tm_o_hi, &tm_o_lo, (int)threadIdx.x - 64);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
