@@ -47,6 +47,8 @@ SIGNATURES = {
     'caspr_three_interp_concat': (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
                                           _P, c_int, _P]),
     'caspr_linear': (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    'caspr_linear_gn_ball': (c_int, [_P, c_int, _P, c_int, _P, _P, _P, c_float, c_int, c_int, c_int, c_int, c_int,
+                                     _P, c_int, _P, c_int, _P]),
     'caspr_linear_tc_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'caspr_linear_tc': (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P,
                                 c_size_t, _P]),

@@ -21,11 +21,26 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // 256 threads as 16x16; CTA tile BM x BN, k-slab 16; thread tile TM x TN with
 // TM = BM/16, TN = BN/16.  Operands are staged k-major in shared memory so the inner loop
 // reads are conflict-free broadcasts.
-template <int BM, int BN>
+// Optional fused epilogue for the per-ball layers of a set-abstraction scale (pointnet2.py:637-642,
+// 677-699 on (B'*M, C, ns)): GroupNorm(16, Cout) over each ball of `ns` consecutive rows, ReLU, and
+// the max over the ball, all inside the CTA that computed the rows (a 128-row tile holds 8 or 4 whole
+// balls; Cout <= BN so every group's channels are in the tile).
+struct GnBallArgs {
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int ns;          // rows per ball: 16 or 32
+  int relu;
+  int write_y;     // store the normalised rows to Y
+  float* maxout;   // (balls, Cout) max over each ball, or nullptr
+  int ld_max;
+};
+
+template <int BM, int BN, bool GN_BALL = false>
 __global__ void __launch_bounds__(256)
 linear_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
               const float* __restrict__ bias, float* __restrict__ Y, int ldy, int rows, int Cin,
-              int Cout, int act_in, int act_out) {
+              int Cout, int act_in, int act_out, GnBallArgs gn = GnBallArgs()) {
   constexpr int BK = 16;
   constexpr int TM = BM / 16, TN = BN / 16;
   __shared__ __align__(16) float As[2][BK][BM + 4];
@@ -110,6 +125,77 @@ linear_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W,
       store_tiles(buf ^ 1);
       __syncthreads();
     }
+  }
+  if constexpr (GN_BALL) {
+    extern __shared__ float dyn_smem[];
+    float* T = dyn_smem;                               // BM x (BN+1) pre-normalisation rows
+    float* S = dyn_smem + BM * (BN + 1);               // (ball, group) -> mean, rstd
+    constexpr int LD = BN + 1;
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        const int c = colmap(j);
+        acc[i][j] += (bias && c < Cout) ? bias[c] : 0.f;
+        T[rowmap(i) * LD + c] = acc[i][j];
+      }
+    __syncthreads();
+    const int ns = gn.ns;
+    const int balls = BM / ns;                          // 8 (ns 16) or 4 (ns 32)
+    const int tpp = 256 / (balls * 16);                 // threads per (ball, group): 2 or 4
+    const int cpg = Cout / 16;
+    const int gsz = ns * cpg;
+    {
+      const int pair = tid / tpp, sub = tid - pair * tpp;
+      const int ball = pair >> 4, g = pair & 15;
+      float s1 = 0.f;
+      for (int e = sub; e < gsz; e += tpp) {
+        const int r = ball * ns + e / cpg, c = g * cpg + e % cpg;
+        s1 += T[r * LD + c];
+      }
+      for (int o = 1; o < tpp; o <<= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      const float mean = s1 / (float)gsz;
+      float s2 = 0.f;
+      for (int e = sub; e < gsz; e += tpp) {
+        const int r = ball * ns + e / cpg, c = g * cpg + e % cpg;
+        const float d = T[r * LD + c] - mean;
+        s2 += d * d;
+      }
+      for (int o = 1; o < tpp; o <<= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      if (sub == 0) {
+        S[2 * pair] = mean;
+        S[2 * pair + 1] = 1.0f / sqrtf(s2 / (float)gsz + gn.eps);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int rl = rowmap(i);
+      const long long r = row0 + rl;
+      const int ball = rl / ns;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        const int c = colmap(j);
+        if (c >= Cout) continue;
+        const int pair = ball * 16 + c / cpg;
+        float v = (acc[i][j] - S[2 * pair]) * S[2 * pair + 1] * gn.gamma[c] + gn.beta[c];
+        if (gn.relu) v = fmaxf(v, 0.f);
+        if (gn.write_y && r < rows) Y[r * ldy + c] = v;
+        if (gn.maxout) T[rl * LD + c] = v;
+      }
+    }
+    if (gn.maxout) {
+      __syncthreads();
+      for (int it = tid; it < balls * Cout; it += 256) {
+        const int ball = it / Cout, c = it - ball * Cout;
+        const long long gball = row0 / ns + ball;
+        if (gball * ns >= rows) continue;
+        float m = -3.0e38f;
+        for (int rr = 0; rr < ns; ++rr) m = fmaxf(m, T[(ball * ns + rr) * LD + c]);
+        gn.maxout[gball * gn.ld_max + c] = m;
+      }
+    }
+    return;
   }
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
@@ -399,6 +485,40 @@ extern "C" int caspr_linear(const float* X, int ldx, const float* W, int ldw, co
   }
   CASPR_CHECK_LAUNCH();
   return CASPR_OK;
+}
+
+namespace {
+template <int BN>
+int launch_linear_gn_ball(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y, int ldy,
+                          int rows, int Cin, int Cout, const GnBallArgs& gn, cudaStream_t s) {
+  const size_t smem = ((size_t)128 * (BN + 1) + 256) * sizeof(float);
+  static bool attr_set = false;            // static + dynamic shared memory exceeds the 48 KB default for BN = 64
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(linear_kernel<128, BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess)
+      return CASPR_ELAUNCH;
+    attr_set = true;
+  }
+  CASPR_COUNT(); linear_kernel<128, BN, true><<<ceil_div(rows, 128), 256, smem, s>>>(
+      X, ldx, W, ldw, bias, Y, ldy, rows, Cin, Cout, CASPR_ACT_NONE, CASPR_ACT_NONE, gn);
+  CASPR_CHECK_LAUNCH();
+  return CASPR_OK;
+}
+}  // namespace
+
+extern "C" int caspr_linear_gn_ball(const float* X, int ldx, const float* W, int ldw, const float* bias,
+                                    const float* gamma, const float* beta, float eps, int rows, int Cin, int Cout,
+                                    int ns, int relu, float* Y, int ldy, float* maxout, int ld_max, void* stream) {
+  CASPR_REQUIRE(X && W && gamma && beta && rows > 0 && Cin > 0 && Cout > 0 && (Y || maxout));
+  CASPR_REQUIRE(ldx >= Cin && ldw >= Cin && (!Y || ldy >= Cout) && (!maxout || ld_max >= Cout));
+  CASPR_REQUIRE((ns == 16 || ns == 32) && rows % ns == 0 && Cout % 16 == 0 && Cout <= 64);
+  GnBallArgs gn;
+  gn.gamma = gamma; gn.beta = beta; gn.eps = eps; gn.ns = ns; gn.relu = relu; gn.write_y = Y != nullptr;
+  gn.maxout = maxout; gn.ld_max = ld_max;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (Cout <= 16) return launch_linear_gn_ball<16>(X, ldx, W, ldw, bias, Y, ldy, rows, Cin, Cout, gn, s);
+  if (Cout <= 32) return launch_linear_gn_ball<32>(X, ldx, W, ldw, bias, Y, ldy, rows, Cin, Cout, gn, s);
+  return launch_linear_gn_ball<64>(X, ldx, W, ldw, bias, Y, ldy, rows, Cin, Cout, gn, s);
 }
 
 extern "C" int caspr_groupnorm(float* X, int ldx, int samples, int rows_per_sample, int C, int groups,

@@ -42,6 +42,15 @@ class PointNetFeatureExtractor(nn.Module):
         """rows (balls*ns, C_in) grouped points -> out (balls, feat_size) view (may be a column slice)."""
         h = rows
         last = len(self.conv_layers) - 1
+        if ns in (16, 32) and all(c.weight.shape[0] <= 64 for c in self.conv_layers):
+            # small per-ball layers (SA levels 1-2): linear + per-ball GroupNorm + ReLU (+ max) in one kernel each
+            for i, (conv, gn) in enumerate(zip(self.conv_layers, self.bn_layers)):
+                if i < last:
+                    h = ops.linear_gn_ball(h, conv.weight, conv.bias, gn.weight, gn.bias, ns, relu=True)
+                else:
+                    ops.linear_gn_ball(h, conv.weight, conv.bias, gn.weight, gn.bias, ns, relu=False,
+                                       want_rows=False, maxout=out)
+            return out
         for i, (conv, gn) in enumerate(zip(self.conv_layers, self.bn_layers)):
             h = ops.linear(h, conv.weight, conv.bias)
             if i < last:

@@ -166,6 +166,27 @@ def linear(x, weight, bias=None, out=None, act_in=ACT_NONE, act_out=ACT_NONE, en
     return out
 
 
+def linear_gn_ball(x, weight, bias, gamma, beta, ns, relu, want_rows=True, maxout=None, eps=1e-5):
+    """Fused per-ball layer: GroupNorm(16) over balls of `ns` rows (+ReLU) of x @ W^T + b; returns the
+    normalised rows (want_rows) and/or writes the per-ball max into `maxout` (balls, Cout) view."""
+    x, ldx = _rows2d(x, 'x')
+    w = weight.reshape(weight.shape[0], weight.shape[1])
+    rows, cin = x.shape
+    cout = w.shape[0]
+    y, ldy = None, 0
+    if want_rows:
+        y = torch.empty(rows, cout, dtype=torch.float32, device=x.device)
+        ldy = cout
+    ld_max = 0
+    if maxout is not None:
+        maxout, ld_max = _rows2d(maxout, 'maxout')
+        assert maxout.shape == (rows // ns, cout)
+    _count('linear_gn_ball')
+    check(lib.caspr_linear_gn_ball(_p(x), ldx, _p(w), cin, _p(bias), _p(gamma), _p(beta), float(eps), rows, cin, cout,
+                                   ns, int(relu), _p(y), ldy, _p(maxout), ld_max, _stream()), 'caspr_linear_gn_ball')
+    return y
+
+
 def groupnorm(x, samples, rows_per_sample, groups, gamma, beta, eps=1e-5, relu=False, write_back=True,
               maxout=None):
     """In-place GroupNorm(groups, C) over `samples` blocks of consecutive rows, fused ReLU / max-pool.

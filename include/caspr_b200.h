@@ -103,6 +103,14 @@ int caspr_linear(const float* X, int ldx, const float* W, int ldw, const float* 
                  float* Y, int ldy, int rows, int Cin, int Cout, int act_in, int act_out,
                  void* stream);
 
+/* One per-ball layer of a set-abstraction scale in a single kernel (pointnet2.py:637-642,677-699 applied to
+ * (B'*M, C, ns)): Y = ReLU?(GroupNorm(16, Cout)(X.W^T + b)) with the statistics taken over each ball of `ns`
+ * (16 or 32) consecutive rows, and optionally maxout[ball, :] = max over the ball's rows of that result
+ * (the max-pool of pointnet2.py:698).  Cout <= 64, Cout % 16 == 0, rows % ns == 0.  Y and/or maxout. */
+int caspr_linear_gn_ball(const float* X, int ldx, const float* W, int ldw, const float* bias,
+                         const float* gamma, const float* beta, float eps, int rows, int Cin, int Cout,
+                         int ns, int relu, float* Y, int ldy, float* maxout, int ld_max, void* stream);
+
 /* Same contract on the tcgen05 tensor cores: 3-product fp16 split ("fp16x3",
  * X_hi.W_hi + X_lo.W_hi + X_hi.W_lo, fp32 accumulate in TMEM), operands scaled per call by powers of
  * two taken from max|X| and max|W| (undone exactly in the epilogue).  Meant for the large layers

@@ -189,6 +189,29 @@ def test_groupnorm_matches_torch(ops, samples, rps, C, relu):
     assert _rel(mx2, ref.max(2)[0]) < 1e-5
 
 
+@pytest.mark.parametrize('balls,ns,cin,cout,relu', [(100, 16, 9, 16, True), (37, 32, 9, 32, True), (64, 32, 32, 64, False),
+                                                     (9, 16, 99, 32, True), (200, 16, 16, 16, False)])
+def test_linear_gn_ball_fused(ops, balls, ns, cin, cout, relu):
+    """Fused per-ball layer (linear + GroupNorm(16) over each ball + ReLU + max) vs torch in fp64."""
+    g = torch.Generator().manual_seed(balls + cout)
+    x = torch.randn(balls * ns, cin, generator=g)
+    w = torch.randn(cout, cin, generator=g) / cin ** 0.5
+    b = torch.randn(cout, generator=g)
+    gamma = torch.rand(cout, generator=g) + 0.5
+    beta = 0.1 * torch.randn(cout, generator=g)
+    lin = torch.nn.functional.linear(x.double(), w.double(), b.double())              # (balls*ns, cout)
+    ref = torch.nn.functional.group_norm(lin.view(balls, ns, cout).transpose(1, 2), 16, gamma.double(),
+                                         beta.double(), eps=1e-5)                      # (balls, cout, ns)
+    if relu:
+        ref = ref.relu()
+    mx = torch.zeros(balls, cout + 8, device=DEV)
+    y = ops.linear_gn_ball(x.to(DEV), w.to(DEV), b.to(DEV), gamma.to(DEV), beta.to(DEV), ns, relu,
+                           want_rows=True, maxout=mx[:, 4:4 + cout])
+    assert _rel(y, ref.transpose(1, 2).reshape(balls * ns, cout)) < 2e-5
+    assert _rel(mx[:, 4:4 + cout], ref.max(2)[0]) < 2e-5
+    assert float(mx[:, :4].abs().sum()) == 0 and float(mx[:, 4 + cout:].abs().sum()) == 0
+
+
 def test_augment_and_broadcast(ops):
     x, _ = synthetic_sequences(1, 2, 100, seed=0)
     x4 = x.view(-1, 4)
