@@ -420,6 +420,125 @@ groupnorm_apply_kernel(float* __restrict__ X, int ldx, int rows_per_sample, int 
   }
 }
 
+// float4 variants of the two passes (C/groups % 4 == 0, ldx % 4 == 0, 16-byte aligned rows): a warp
+// walks one row at a time, lane L owns the channel quads L, L+32, ... whose group index does not depend
+// on the row, so statistics accumulate in registers and every load / store is a full 128-byte line.
+constexpr int kGnMaxQuadsPerLane = 16;          // C <= 2048
+
+__global__ void __launch_bounds__(256)
+groupnorm_stats_vec_kernel(const float* __restrict__ X, int ldx, int rows_per_sample, int C, int groups,
+                           double* __restrict__ stats) {
+  const int sample = blockIdx.y;
+  const int r0 = blockIdx.x * kGnRowsPerCta;
+  const int r1 = min(rows_per_sample, r0 + kGnRowsPerCta);
+  const int cpg = C / groups, Q = C >> 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* base = X + (size_t)sample * rows_per_sample * ldx;
+  __shared__ double sh_s[64], sh_q[64];
+  for (int g = threadIdx.x; g < groups; g += 256) { sh_s[g] = 0.0; sh_q[g] = 0.0; }
+  __syncthreads();
+  float s[kGnMaxQuadsPerLane], q[kGnMaxQuadsPerLane];
+#pragma unroll
+  for (int k = 0; k < kGnMaxQuadsPerLane; ++k) { s[k] = 0.f; q[k] = 0.f; }
+  for (int r = r0 + warp; r < r1; r += 8) {
+    const float4* row = reinterpret_cast<const float4*>(base + (size_t)r * ldx);
+#pragma unroll
+    for (int k = 0; k < kGnMaxQuadsPerLane; ++k) {
+      const int qi = lane + 32 * k;
+      if (qi < Q) {
+        const float4 v = row[qi];
+        s[k] += (v.x + v.y) + (v.z + v.w);
+        q[k] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, q[k]))));
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kGnMaxQuadsPerLane; ++k) {
+    const int qi = lane + 32 * k;
+    if (qi < Q) {
+      const int g = (qi * 4) / cpg;
+      atomicAdd(&sh_s[g], (double)s[k]);
+      atomicAdd(&sh_q[g], (double)q[k]);
+    }
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < groups; g += 256) {
+    atomicAdd(&stats[((size_t)sample * groups + g) * 2 + 0], sh_s[g]);
+    atomicAdd(&stats[((size_t)sample * groups + g) * 2 + 1], sh_q[g]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+groupnorm_apply_vec_kernel(float* __restrict__ X, int ldx, int rows_per_sample, int C, int groups,
+                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                           int relu, int write_back, const double* __restrict__ stats,
+                           unsigned* __restrict__ maxout_ordered, int ld_max) {
+  const int sample = blockIdx.y;
+  const int r0 = blockIdx.x * kGnRowsPerCta;
+  const int r1 = min(rows_per_sample, r0 + kGnRowsPerCta);
+  const int cpg = C / groups, Q = C >> 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double cnt = (double)cpg * (double)rows_per_sample;
+  float* base = X + (size_t)sample * rows_per_sample * ldx;
+  __shared__ float s_mean[64], s_rstd[64];
+  for (int g = threadIdx.x; g < groups; g += 256) {
+    double s = stats[((size_t)sample * groups + g) * 2 + 0];
+    double q = stats[((size_t)sample * groups + g) * 2 + 1];
+    double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[g] = (float)mean;
+    s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  // per-quad scale / shift: v*sc + sh with sc = rstd*gamma, sh = beta - mean*rstd*gamma would change the
+  // rounding of (x - mean)*rstd*gamma + beta; keep the reference's operation order instead
+  float mu[kGnMaxQuadsPerLane], rs[kGnMaxQuadsPerLane];
+  float4 mx[kGnMaxQuadsPerLane];
+#pragma unroll
+  for (int k = 0; k < kGnMaxQuadsPerLane; ++k) {
+    const int qi = lane + 32 * k;
+    const int g = qi < Q ? (qi * 4) / cpg : 0;
+    mu[k] = s_mean[g];
+    rs[k] = s_rstd[g];
+    mx[k] = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f);
+  }
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  for (int r = r0 + warp; r < r1; r += 8) {
+    float4* row = reinterpret_cast<float4*>(base + (size_t)r * ldx);
+#pragma unroll
+    for (int k = 0; k < kGnMaxQuadsPerLane; ++k) {
+      const int qi = lane + 32 * k;
+      if (qi < Q) {
+        float4 v = row[qi];
+        const float4 ga = __ldg(g4 + qi), be = __ldg(b4 + qi);
+        v.x = (v.x - mu[k]) * rs[k] * ga.x + be.x;
+        v.y = (v.y - mu[k]) * rs[k] * ga.y + be.y;
+        v.z = (v.z - mu[k]) * rs[k] * ga.z + be.z;
+        v.w = (v.w - mu[k]) * rs[k] * ga.w + be.w;
+        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        if (write_back) row[qi] = v;
+        mx[k].x = fmaxf(mx[k].x, v.x); mx[k].y = fmaxf(mx[k].y, v.y);
+        mx[k].z = fmaxf(mx[k].z, v.z); mx[k].w = fmaxf(mx[k].w, v.w);
+      }
+    }
+  }
+  if (maxout_ordered) {
+#pragma unroll
+    for (int k = 0; k < kGnMaxQuadsPerLane; ++k) {
+      const int qi = lane + 32 * k;
+      if (qi < Q && r0 + warp < r1) {
+        unsigned* o = maxout_ordered + (size_t)sample * ld_max + qi * 4;
+        atomicMax(o + 0, float_to_ordered(mx[k].x));
+        atomicMax(o + 1, float_to_ordered(mx[k].y));
+        atomicMax(o + 2, float_to_ordered(mx[k].z));
+        atomicMax(o + 3, float_to_ordered(mx[k].w));
+      }
+    }
+  }
+}
+
 __global__ void fill_u32_kernel(unsigned* p, int samples, int C, int ld, unsigned v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < samples * C) p[(size_t)(i / C) * ld + (i % C)] = v;
@@ -560,15 +679,26 @@ extern "C" int caspr_groupnorm(float* X, int ldx, int samples, int rows_per_samp
   if (cudaMemsetAsync(stats_ws, 0, (size_t)samples * groups * 2 * sizeof(double), s) != cudaSuccess)
     return CASPR_ELAUNCH;
   dim3 grid(ceil_div(rows_per_sample, kGnRowsPerCta), samples);
-  CASPR_COUNT(); groupnorm_stats_kernel<<<grid, 256, 0, s>>>(X, ldx, rows_per_sample, C, groups, stats_ws);
+  const bool vec = (C / groups) % 4 == 0 && ldx % 4 == 0 && ((uintptr_t)X & 15) == 0 &&
+                   ((uintptr_t)gamma & 15) == 0 && ((uintptr_t)beta & 15) == 0 && C <= 128 * kGnMaxQuadsPerLane;
+  if (vec) {
+    CASPR_COUNT(); groupnorm_stats_vec_kernel<<<grid, 256, 0, s>>>(X, ldx, rows_per_sample, C, groups, stats_ws);
+  } else {
+    CASPR_COUNT(); groupnorm_stats_kernel<<<grid, 256, 0, s>>>(X, ldx, rows_per_sample, C, groups, stats_ws);
+  }
   CASPR_CHECK_LAUNCH();
   unsigned* mo = reinterpret_cast<unsigned*>(maxout);
   if (mo) {
     CASPR_COUNT(); fill_u32_kernel<<<ceil_div(samples * C, 256), 256, 0, s>>>(mo, samples, C, ld_max, 0u);
     CASPR_CHECK_LAUNCH();
   }
-  CASPR_COUNT(); groupnorm_apply_kernel<<<grid, 256, 0, s>>>(X, ldx, rows_per_sample, C, groups, gamma, beta, eps, relu,
-                                             write_back, stats_ws, mo, ld_max);
+  if (vec) {
+    CASPR_COUNT(); groupnorm_apply_vec_kernel<<<grid, 256, 0, s>>>(X, ldx, rows_per_sample, C, groups, gamma, beta, eps,
+                                                                   relu, write_back, stats_ws, mo, ld_max);
+  } else {
+    CASPR_COUNT(); groupnorm_apply_kernel<<<grid, 256, 0, s>>>(X, ldx, rows_per_sample, C, groups, gamma, beta, eps, relu,
+                                               write_back, stats_ws, mo, ld_max);
+  }
   CASPR_CHECK_LAUNCH();
   if (mo) {
     CASPR_COUNT(); decode_ordered_kernel<<<ceil_div(samples * C, 256), 256, 0, s>>>(mo, samples, C, ld_max);

@@ -122,8 +122,27 @@ struct LinearEpilogue {
 struct Layout {
   long long rows_pad;
   int k_pad, cout_pad;
-  size_t off_xhi, off_xlo, off_whi, off_wlo, off_xinv, off_winv, total;
+  size_t off_xhi, off_xlo, off_xinv, off_w, total;     // off_w: start of an embedded WeightLayout block
 };
+
+// Split weights (reusable across calls while the weights do not change): [w_inv | W_hi | W_lo]
+struct WeightLayout {
+  int k_pad, cout_pad;
+  size_t off_winv, off_whi, off_wlo, total;
+};
+
+WeightLayout make_weight_layout(int cin, int cout) {
+  WeightLayout l;
+  l.k_pad = (cin + kBK - 1) / kBK * kBK;
+  l.cout_pad = (cout + kBN - 1) / kBN * kBN;
+  size_t p = 0;
+  auto take = [&](size_t bytes) { size_t r = p; p += align_up(bytes, 1024); return r; };
+  l.off_winv = take((size_t)l.cout_pad * 4);
+  l.off_whi = take((size_t)l.cout_pad * l.k_pad * 2);
+  l.off_wlo = take((size_t)l.cout_pad * l.k_pad * 2);
+  l.total = p;
+  return l;
+}
 
 Layout make_layout(long long rows, int cin, int cout) {
   Layout l;
@@ -133,11 +152,9 @@ Layout make_layout(long long rows, int cin, int cout) {
   size_t p = 0;
   auto take = [&](size_t bytes) { size_t r = p; p += align_up(bytes, 1024); return r; };
   l.off_xinv = take((size_t)l.rows_pad * 4);
-  l.off_winv = take((size_t)l.cout_pad * 4);
   l.off_xhi = take((size_t)l.rows_pad * l.k_pad * 2);
   l.off_xlo = take((size_t)l.rows_pad * l.k_pad * 2);
-  l.off_whi = take((size_t)l.cout_pad * l.k_pad * 2);
-  l.off_wlo = take((size_t)l.cout_pad * l.k_pad * 2);
+  l.off_w = take(make_weight_layout(cin, cout).total);
   l.total = p;
   return l;
 }
@@ -151,29 +168,53 @@ extern "C" size_t caspr_linear_tc_workspace_bytes(int rows, int Cin, int Cout) {
   return make_layout(rows, Cin, Cout).total;
 }
 
+extern "C" size_t caspr_linear_tc_weight_bytes(int Cin, int Cout) {
+  if (Cin <= 0 || Cout <= 0) return 0;
+  return make_weight_layout(Cin, Cout).total;
+}
+
+extern "C" int caspr_linear_tc_prepare_weights(const float* W, int ldw, int Cin, int Cout, void* prepared,
+                                               size_t prepared_bytes, void* stream) {
+  CASPR_REQUIRE(W && prepared && Cin > 0 && Cout > 0 && ldw >= Cin && ((uintptr_t)prepared & 1023) == 0);
+  const WeightLayout wl = make_weight_layout(Cin, Cout);
+  if (prepared_bytes < wl.total) return CASPR_EWORKSPACE;
+  char* base = (char*)prepared;
+  CASPR_COUNT(); split_rows_kernel<<<ceil_div(wl.cout_pad, 8), 256, 0, (cudaStream_t)stream>>>(
+      W, ldw, Cout, Cin, wl.cout_pad, wl.k_pad, 0, (__half2*)(base + wl.off_whi), (__half2*)(base + wl.off_wlo),
+      (float*)(base + wl.off_winv));
+  CASPR_CHECK_LAUNCH();
+  return CASPR_OK;
+}
+
 extern "C" int caspr_linear_tc(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y,
-                               int ldy, int rows, int Cin, int Cout, int act_in, int act_out, void* workspace,
-                               size_t workspace_bytes, void* stream) {
-  CASPR_REQUIRE(X && W && Y && workspace && rows > 0 && Cin > 0 && Cout > 0);
-  CASPR_REQUIRE(ldx >= Cin && ldw >= Cin && ldy >= Cout);
+                               int ldy, int rows, int Cin, int Cout, int act_in, int act_out,
+                               const void* prepared_weights, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  CASPR_REQUIRE(X && (W || prepared_weights) && Y && workspace && rows > 0 && Cin > 0 && Cout > 0);
+  CASPR_REQUIRE(ldx >= Cin && (!W || ldw >= Cin) && ldy >= Cout);
   CASPR_REQUIRE(act_in == CASPR_ACT_NONE || act_in == CASPR_ACT_RELU);
-  CASPR_REQUIRE(((uintptr_t)workspace & 1023) == 0);
+  CASPR_REQUIRE(((uintptr_t)workspace & 1023) == 0 && ((uintptr_t)prepared_weights & 1023) == 0);
   const Layout l = make_layout(rows, Cin, Cout);
+  const WeightLayout wl = make_weight_layout(Cin, Cout);
   if (workspace_bytes < l.total) return CASPR_EWORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
   char* base = (char*)workspace;
   float* xinv = (float*)(base + l.off_xinv);
-  float* winv = (float*)(base + l.off_winv);
   __half* xhi = (__half*)(base + l.off_xhi);
   __half* xlo = (__half*)(base + l.off_xlo);
-  __half* whi = (__half*)(base + l.off_whi);
-  __half* wlo = (__half*)(base + l.off_wlo);
+  const char* wbase = (const char*)prepared_weights;
+  if (!wbase) {
+    int rc = caspr_linear_tc_prepare_weights(W, ldw, Cin, Cout, base + l.off_w, wl.total, stream);
+    if (rc) return rc;
+    wbase = base + l.off_w;
+  }
+  const float* winv = (const float*)(wbase + wl.off_winv);
+  const __half* whi = (const __half*)(wbase + wl.off_whi);
+  const __half* wlo = (const __half*)(wbase + wl.off_wlo);
 
   const int nb = 148 * 8;
   CASPR_COUNT(); split_rows_kernel<<<nb, 256, 0, s>>>(X, ldx, rows, Cin, l.rows_pad, l.k_pad, act_in == CASPR_ACT_RELU,
                                        (__half2*)xhi, (__half2*)xlo, xinv);
-  CASPR_COUNT(); split_rows_kernel<<<ceil_div(l.cout_pad, 8), 256, 0, s>>>(W, ldw, Cout, Cin, l.cout_pad, l.k_pad, 0,
-                                                            (__half2*)whi, (__half2*)wlo, winv);
   CASPR_CHECK_LAUNCH();
 
   CUtensorMap tm_xhi, tm_xlo, tm_whi, tm_wlo;

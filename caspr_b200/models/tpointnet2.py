@@ -86,10 +86,10 @@ class TPointNet2(nn.Module):
         return z0_s.clone(), (None if tnocs_s is None else tnocs_s.clone())
 
     def _param_key(self):
-        """Identity of the parameter storage the captured kernels read (in-place updates such as
-        load_state_dict / optimizer steps keep it; .to() / .half() change it)."""
-        ptrs = [p.data_ptr() for p in self.parameters()]
-        return (len(ptrs), hash(tuple(ptrs)))
+        """Identity of the parameter storage the captured kernels read plus the in-place version counters
+        (the graph references fp16 weight planes derived from the values: ops._prepared_weights)."""
+        params = list(self.parameters())
+        return (len(params), hash(tuple(p.data_ptr() for p in params)), sum(p._version for p in params))
 
     def _forward_eager(self, x):
         B, T, N, _ = x.shape

@@ -11,6 +11,7 @@ Conv1d/GroupNorm calls around them, and torchdiffeq's odeint (latent_ode_model.p
 cnf.py:102-119).
 """
 import ctypes
+import weakref
 
 import torch
 
@@ -132,6 +133,36 @@ TC_MIN_ROWS, TC_MIN_CIN, TC_MIN_COUT = 2048, 64, 64
 LINEAR_ENGINE = 'auto'          # module-wide override used by accuracy studies: 'auto' | 'tc' | 'simt'
 
 
+# fp16 hi/lo planes of layer weights, keyed by the weight tensor's storage and in-place version counter
+_WEIGHT_PLANES = {}
+
+
+def _aligned_bytes(nbytes, device):
+    """uint8 buffer and a 1024-byte aligned pointer into it."""
+    buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+    return buf, (buf.data_ptr() + 1023) // 1024 * 1024
+
+
+def _prepared_weights(weight, w2d):
+    """fp16 hi/lo planes of `weight`, cached per tensor OBJECT (weak reference: recycled storage addresses of
+    a freed model never alias), storage pointer and in-place version counter."""
+    key = id(weight)
+    hit = _WEIGHT_PLANES.get(key)
+    if hit is not None:
+        ref, ptr, version, buf, planes_ptr = hit
+        if ref() is weight and ptr == w2d.data_ptr() and version == weight._version:
+            return planes_ptr
+    cout, cin = w2d.shape
+    nbytes = lib.caspr_linear_tc_weight_bytes(cin, cout)
+    buf, planes_ptr = _aligned_bytes(nbytes, w2d.device)
+    _count('linear_tc_prepare_weights')
+    check(lib.caspr_linear_tc_prepare_weights(_p(w2d), cin, cin, cout, ctypes.c_void_p(planes_ptr), nbytes, _stream()),
+          'caspr_linear_tc_prepare_weights')
+    ref = weakref.ref(weight, lambda _r, k=key: _WEIGHT_PLANES.pop(k, None))
+    _WEIGHT_PLANES[key] = (ref, w2d.data_ptr(), weight._version, buf, planes_ptr)
+    return planes_ptr
+
+
 def linear(x, weight, bias=None, out=None, act_in=ACT_NONE, act_out=ACT_NONE, engine='auto'):
     """1x1 Conv1d / Linear on rows: y = act_out(act_in(x) @ W^T + b).
 
@@ -154,11 +185,14 @@ def linear(x, weight, bias=None, out=None, act_in=ACT_NONE, act_out=ACT_NONE, en
         engine = 'tc' if (rows >= TC_MIN_ROWS and cin >= TC_MIN_CIN and cout >= TC_MIN_COUT) else 'simt'
     if engine == 'tc':
         ws_bytes = lib.caspr_linear_tc_workspace_bytes(rows, cin, cout)
-        ws = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device=x.device)
-        ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
+        ws, ws_ptr = _aligned_bytes(ws_bytes, x.device)
+        # weights are split once per (storage, in-place version); CUDA graphs that captured a call are keyed
+        # by the same versions (TPointNet2._param_key), so a weight update re-captures with fresh planes
+        prepared = _prepared_weights(weight, w)
         _count('linear_tc')
         check(lib.caspr_linear_tc(_p(x), ldx, _p(w), cin, _p(bias), _p(out), ldy, rows, cin, cout, act_in, act_out,
-                                  ctypes.c_void_p(ws_ptr), ws_bytes, _stream()), 'caspr_linear_tc')
+                                  ctypes.c_void_p(prepared) if prepared else None, ctypes.c_void_p(ws_ptr), ws_bytes,
+                                  _stream()), 'caspr_linear_tc')
         return out
     _count('linear')
     check(lib.caspr_linear(_p(x), ldx, _p(w), cin, _p(bias), _p(out), ldy, rows, cin, cout, act_in, act_out,

@@ -117,9 +117,15 @@ int caspr_linear_gn_ball(const float* X, int ldx, const float* W, int ldw, const
  * (feature propagation, final layers, the 1600-wide head); any Cin / Cout / rows are accepted.
  * workspace: caspr_linear_tc_workspace_bytes(rows, Cin, Cout) bytes, 1024-byte aligned. */
 size_t caspr_linear_tc_workspace_bytes(int rows, int Cin, int Cout);
+/* Optional: split the weights once (caspr_linear_tc_weight_bytes bytes, 1024-byte aligned) and pass the
+ * block as `prepared_weights` for as long as W does not change; with prepared_weights == NULL the split
+ * is redone inside every call (W must then be non-NULL). */
+size_t caspr_linear_tc_weight_bytes(int Cin, int Cout);
+int caspr_linear_tc_prepare_weights(const float* W, int ldw, int Cin, int Cout, void* prepared,
+                                    size_t prepared_bytes, void* stream);
 int caspr_linear_tc(const float* X, int ldx, const float* W, int ldw, const float* bias,
                     float* Y, int ldy, int rows, int Cin, int Cout, int act_in, int act_out,
-                    void* workspace, size_t workspace_bytes, void* stream);
+                    const void* prepared_weights, void* workspace, size_t workspace_bytes, void* stream);
 
 /* GroupNorm over samples of `rows_per_sample` consecutive rows (torch.nn.GroupNorm(groups, C)
  * on (samples, C, rows_per_sample)), eps as given; optional ReLU; optional max over the rows
