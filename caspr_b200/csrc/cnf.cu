@@ -522,6 +522,37 @@ cnf_passthrough_kernel(const float4* __restrict__ y0, int n, MbnDev post, int re
   if (logp_out && have_logp) logp_out[i] = lp;
 }
 
+// Hyper-network hoist: out[f][j] = W[j][1:1+C] . ctx[f] (+ bias[j]) for a handful of frames.  A skinny GEMM
+// (frames x C x D with frames ~ 80): one warp per output channel keeps its weight row in registers and
+// streams the contexts from L2, instead of a tiled GEMM that would run on four CTAs.
+constexpr int kHoistMaxC = 2048;
+__global__ void __launch_bounds__(256)
+cnf_hyper_hoist_kernel(const float* __restrict__ ctx, int C, const float* __restrict__ W, int ldw,
+                       const float* __restrict__ bias, int frames, int D, float* __restrict__ out, int ld_out) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (j >= D) return;
+  const float* wrow = W + (size_t)j * ldw + 1;                 // column 0 multiplies t
+  float w[kHoistMaxC / 32];
+#pragma unroll
+  for (int i = 0; i < kHoistMaxC / 32; ++i) {
+    const int k = lane + 32 * i;
+    w[i] = k < C ? wrow[k] : 0.f;
+  }
+  const float b = bias ? bias[j] : 0.f;
+  for (int f = 0; f < frames; ++f) {
+    const float* c = ctx + (size_t)f * C;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < kHoistMaxC / 32; ++i) {
+      const int k = lane + 32 * i;
+      if (k < C) acc = fmaf(w[i], c[k], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[(size_t)f * ld_out + j] = acc + b;
+  }
+}
+
 __global__ void gather_col0_kernel(const float* __restrict__ W, int ldw, int rows, float* __restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < rows) out[i] = W[(size_t)i * ldw];
@@ -608,12 +639,19 @@ int prepare_hyper(const CnfWorkspace& w, const caspr_cnf_weights* cw, const floa
   int off = 0;
   for (int l = 0; l < 4; ++l) {
     const int D = l < 3 ? H : 3;
-    int rc = caspr_linear(ctx, C, cw->Wgate[l] + 1, C + 1, cw->bgate[l], w.Gc + off, ctot, frames, C, D,
-                          CASPR_ACT_NONE, CASPR_ACT_NONE, s);
-    if (rc) return rc;
-    rc = caspr_linear(ctx, C, cw->Wbias[l] + 1, C + 1, nullptr, w.Bc + off, ctot, frames, C, D,
-                      CASPR_ACT_NONE, CASPR_ACT_NONE, s);
-    if (rc) return rc;
+    if (C <= kHoistMaxC) {
+      CASPR_COUNT(); cnf_hyper_hoist_kernel<<<ceil_div(D, 8), 256, 0, s>>>(ctx, C, cw->Wgate[l], C + 1, cw->bgate[l],
+                                                                          frames, D, w.Gc + off, ctot);
+      CASPR_COUNT(); cnf_hyper_hoist_kernel<<<ceil_div(D, 8), 256, 0, s>>>(ctx, C, cw->Wbias[l], C + 1, nullptr,
+                                                                          frames, D, w.Bc + off, ctot);
+    } else {
+      int rc = caspr_linear(ctx, C, cw->Wgate[l] + 1, C + 1, cw->bgate[l], w.Gc + off, ctot, frames, C, D,
+                            CASPR_ACT_NONE, CASPR_ACT_NONE, s);
+      if (rc) return rc;
+      rc = caspr_linear(ctx, C, cw->Wbias[l] + 1, C + 1, nullptr, w.Bc + off, ctot, frames, C, D,
+                        CASPR_ACT_NONE, CASPR_ACT_NONE, s);
+      if (rc) return rc;
+    }
     CASPR_COUNT(); gather_col0_kernel<<<ceil_div(D, 128), 128, 0, s>>>(cw->Wgate[l], C + 1, D, w.wg_t + off);
     CASPR_COUNT(); gather_col0_kernel<<<ceil_div(D, 128), 128, 0, s>>>(cw->Wbias[l], C + 1, D, w.wb_t + off);
     CASPR_COUNT(); copy_f32_kernel<<<ceil_div(D, 128), 128, 0, s>>>(cw->b[l], D, w.lbias + off);
