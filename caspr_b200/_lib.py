@@ -25,6 +25,14 @@ class CnfWeights(Structure):
                 ('ctx_dim', c_int)]
 
 
+class GnFold(Structure):
+    _fields_ = [('table', c_void_p), ('rows_per_sample', c_int), ('relu', c_int)]
+
+
+class GnStats(Structure):
+    _fields_ = [('stats', c_void_p), ('rows_per_sample', c_int), ('groups', c_int)]
+
+
 class MbnParams(Structure):
     _fields_ = [('weight', c_void_p), ('bias', c_void_p), ('running_mean', c_void_p),
                 ('running_var', c_void_p)]
@@ -52,10 +60,11 @@ SIGNATURES = {
     'caspr_linear_tc_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'caspr_linear_tc_weight_bytes': (c_size_t, [c_int, c_int]),
     'caspr_linear_tc_prepare_weights': (c_int, [_P, c_int, c_int, c_int, _P, c_size_t, _P]),
-    'caspr_linear_tc': (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P,
-                                c_size_t, _P]),
+    'caspr_gn_table': (c_int, [_P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P]),
+    'caspr_linear_tc': (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P,
+                                POINTER(GnFold), POINTER(GnStats), _P, c_size_t, _P]),
     'caspr_groupnorm': (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_float, c_int, c_int, _P,
-                                c_int, _P, _P]),
+                                c_int, _P, c_int, _P]),
     'caspr_augment_xyz': (c_int, [_P, c_int, _P, _P]),
     'caspr_strip_time': (c_int, [_P, c_int, _P, _P]),
     'caspr_broadcast_rows': (c_int, [_P, c_int, c_int, c_int, c_int, _P, c_int, _P]),

@@ -426,49 +426,6 @@ groupnorm_apply_kernel(float* __restrict__ X, int ldx, int rows_per_sample, int 
 constexpr int kGnMaxQuadsPerLane = 16;          // C <= 2048
 
 __global__ void __launch_bounds__(256)
-groupnorm_stats_vec_kernel(const float* __restrict__ X, int ldx, int rows_per_sample, int C, int groups,
-                           double* __restrict__ stats) {
-  const int sample = blockIdx.y;
-  const int r0 = blockIdx.x * kGnRowsPerCta;
-  const int r1 = min(rows_per_sample, r0 + kGnRowsPerCta);
-  const int cpg = C / groups, Q = C >> 2;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float* base = X + (size_t)sample * rows_per_sample * ldx;
-  __shared__ double sh_s[64], sh_q[64];
-  for (int g = threadIdx.x; g < groups; g += 256) { sh_s[g] = 0.0; sh_q[g] = 0.0; }
-  __syncthreads();
-  float s[kGnMaxQuadsPerLane], q[kGnMaxQuadsPerLane];
-#pragma unroll
-  for (int k = 0; k < kGnMaxQuadsPerLane; ++k) { s[k] = 0.f; q[k] = 0.f; }
-  for (int r = r0 + warp; r < r1; r += 8) {
-    const float4* row = reinterpret_cast<const float4*>(base + (size_t)r * ldx);
-#pragma unroll
-    for (int k = 0; k < kGnMaxQuadsPerLane; ++k) {
-      const int qi = lane + 32 * k;
-      if (qi < Q) {
-        const float4 v = row[qi];
-        s[k] += (v.x + v.y) + (v.z + v.w);
-        q[k] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, q[k]))));
-      }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < kGnMaxQuadsPerLane; ++k) {
-    const int qi = lane + 32 * k;
-    if (qi < Q) {
-      const int g = (qi * 4) / cpg;
-      atomicAdd(&sh_s[g], (double)s[k]);
-      atomicAdd(&sh_q[g], (double)q[k]);
-    }
-  }
-  __syncthreads();
-  for (int g = threadIdx.x; g < groups; g += 256) {
-    atomicAdd(&stats[((size_t)sample * groups + g) * 2 + 0], sh_s[g]);
-    atomicAdd(&stats[((size_t)sample * groups + g) * 2 + 1], sh_q[g]);
-  }
-}
-
-__global__ void __launch_bounds__(256)
 groupnorm_apply_vec_kernel(float* __restrict__ X, int ldx, int rows_per_sample, int C, int groups,
                            const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                            int relu, int write_back, const double* __restrict__ stats,
@@ -643,14 +600,14 @@ extern "C" int caspr_linear_gn_ball(const float* X, int ldx, const float* W, int
 extern "C" int caspr_groupnorm(float* X, int ldx, int samples, int rows_per_sample, int C, int groups,
                                const float* gamma, const float* beta, float eps, int relu,
                                int write_back, float* maxout, int ld_max, double* stats_ws,
-                               void* stream) {
+                               int stats_ready, void* stream) {
   CASPR_REQUIRE(X && gamma && beta && samples > 0 && rows_per_sample > 0 && C > 0);
   CASPR_REQUIRE(groups > 0 && groups <= 64 && C % groups == 0 && ldx >= C);
   CASPR_REQUIRE(write_back || maxout);
   CASPR_REQUIRE(!maxout || ld_max >= C);
   cudaStream_t s = (cudaStream_t)stream;
   const size_t tile_bytes = (size_t)rows_per_sample * C * sizeof(float);
-  if (rows_per_sample * C <= kGnWarpTile) {
+  if (!stats_ready && rows_per_sample * C <= kGnWarpTile) {
     const size_t smem = 8 * tile_bytes + 8 * 2 * groups * sizeof(float);
     if (smem > 48 * 1024) {
       if (cudaFuncSetAttribute(groupnorm_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -664,7 +621,7 @@ extern "C" int caspr_groupnorm(float* X, int ldx, int samples, int rows_per_samp
     CASPR_CHECK_LAUNCH();
     return CASPR_OK;
   }
-  if (rows_per_sample <= 64 && tile_bytes <= 96 * 1024) {
+  if (!stats_ready && rows_per_sample <= 64 && tile_bytes <= 96 * 1024) {
     if (tile_bytes > 48 * 1024) {
       if (cudaFuncSetAttribute(groupnorm_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                96 * 1024) != cudaSuccess)
@@ -676,14 +633,12 @@ extern "C" int caspr_groupnorm(float* X, int ldx, int samples, int rows_per_samp
     return CASPR_OK;
   }
   CASPR_REQUIRE(stats_ws != nullptr);
-  if (cudaMemsetAsync(stats_ws, 0, (size_t)samples * groups * 2 * sizeof(double), s) != cudaSuccess)
+  if (!stats_ready && cudaMemsetAsync(stats_ws, 0, (size_t)samples * groups * 2 * sizeof(double), s) != cudaSuccess)
     return CASPR_ELAUNCH;
   dim3 grid(ceil_div(rows_per_sample, kGnRowsPerCta), samples);
   const bool vec = (C / groups) % 4 == 0 && ldx % 4 == 0 && ((uintptr_t)X & 15) == 0 &&
                    ((uintptr_t)gamma & 15) == 0 && ((uintptr_t)beta & 15) == 0 && C <= 128 * kGnMaxQuadsPerLane;
-  if (vec) {
-    CASPR_COUNT(); groupnorm_stats_vec_kernel<<<grid, 256, 0, s>>>(X, ldx, rows_per_sample, C, groups, stats_ws);
-  } else {
+  if (!stats_ready) {
     CASPR_COUNT(); groupnorm_stats_kernel<<<grid, 256, 0, s>>>(X, ldx, rows_per_sample, C, groups, stats_ws);
   }
   CASPR_CHECK_LAUNCH();

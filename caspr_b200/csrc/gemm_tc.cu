@@ -24,13 +24,46 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   return v;
 }
 
+// GroupNorm folded into the operand split of the NEXT layer: x <- ReLU?((x - mean)*rstd*gamma + beta) with
+// (mean, rstd) per (sample, group) from `tab` (written by gn_table_kernel from the statistics the previous
+// GEMM's epilogue accumulated).  Saves the separate normalisation pass over the activation tensor.
+struct NormFold {
+  const float2* tab;     // [samples][C] (scale, shift): x <- x*scale + shift; nullptr = no folding
+  int rows_per_sample, C, relu;
+};
+
+__device__ __forceinline__ float fold_apply(const NormFold& nf, const float2* tab_row, float v, int c) {
+  const float2 ss = __ldg(tab_row + c);
+  v = fmaf(v, ss.x, ss.y);
+  return nf.relu ? fmaxf(v, 0.f) : v;
+}
+
+// (sum, sum of squares) in fp64 per (sample, group) -> per (sample, channel) scale = rstd*gamma and
+// shift = beta - mean*rstd*gamma in fp32
+__global__ void gn_table_kernel(const double* __restrict__ stats, int samples, int groups, int C, double count,
+                                float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                float2* __restrict__ tab) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= samples * C) return;
+  const int sample = i / C, c = i - sample * C;
+  const int g = c / (C / groups);
+  const double* st = stats + ((size_t)sample * groups + g) * 2;
+  const double mean = st[0] / count;
+  double var = st[1] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double rstd = 1.0 / sqrt(var + (double)eps);
+  const double sc = rstd * (double)gamma[c];
+  tab[i] = make_float2((float)sc, (float)((double)beta[c] - mean * sc));
+}
+
 // fp32 [rows][cols] (leading dimension ld) -> fp16 hi / lo planes [rows_pad][k_pad], zero padded, each
 // row scaled by its own power of two 2^(14-e) (max|row| < 2^e, so the largest element lands in
 // [2^13, 2^14)); inv_scale[row] = 2^(e-14) is undone exactly in the GEMM epilogue.  One warp per row:
 // the row is read twice, the second time from L1/L2.
 __global__ void __launch_bounds__(256)
 split_rows_kernel(const float* __restrict__ x, int ld, long long rows, int cols, long long rows_pad, int k_pad,
-                  int relu, __half2* __restrict__ hi, __half2* __restrict__ lo, float* __restrict__ inv_scale) {
+                  int relu, __half2* __restrict__ hi, __half2* __restrict__ lo, float* __restrict__ inv_scale,
+                  NormFold nf = NormFold()) {
   const int lane = threadIdx.x & 31;
   const int kp2 = k_pad / 2;
   const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -44,9 +77,11 @@ split_rows_kernel(const float* __restrict__ x, int ld, long long rows, int cols,
       continue;
     }
     const float* xr = x + r * ld;
+    const float2* tab_row = nf.tab ? nf.tab + (r / nf.rows_per_sample) * nf.C : nullptr;
     float m = 0.f;
     for (int c = lane; c < cols; c += 32) {
       float v = xr[c];
+      if (tab_row) v = fold_apply(nf, tab_row, v, c);
       if (relu) v = fmaxf(v, 0.f);
       m = fmaxf(m, fabsf(v));
     }
@@ -63,6 +98,10 @@ split_rows_kernel(const float* __restrict__ x, int ld, long long rows, int cols,
       const int c = 2 * c2;
       float a = c < cols ? xr[c] : 0.f;
       float b = c + 1 < cols ? xr[c + 1] : 0.f;
+      if (tab_row) {
+        if (c < cols) a = fold_apply(nf, tab_row, a, c);
+        if (c + 1 < cols) b = fold_apply(nf, tab_row, b, c + 1);
+      }
       if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
       a *= s;
       b *= s;
@@ -82,6 +121,10 @@ struct LinearEpilogue {
   int ldy;
   int rows, cout, act_out;
   int vec_ok;
+  // optional GroupNorm statistics of the OUTPUT (before any normalisation): per (sample, group) sum and sum
+  // of squares accumulated in fp64; requires rows_per_sample % 32 == 0 so a warp never straddles samples
+  double* stats;
+  int st_rows_per_sample, st_cpg, st_groups;
   // per-thread tile state
   long long row;
   int col0;
@@ -89,34 +132,83 @@ struct LinearEpilogue {
 
   __device__ __forceinline__ void setup(uint8_t*, const CUtensorMap*, const CUtensorMap*, int) {}
   __device__ __forceinline__ void tile_begin(int m_tile, int n_tile, int q, int lane) {
+    if (stats && st_live) flush_stats();               // statistics of the previous tile
     row = (long long)m_tile * kBM + q * 32 + lane;
     col0 = n_tile * kBN;
     inv = x_inv[row];       // planes are padded to whole tiles, so the index is always valid
+    if (stats) {
+      const long long warp_row = row - lane;
+      st_live = warp_row < rows;
+      st_row = stats + ((st_live ? warp_row : 0) / st_rows_per_sample) * st_groups * 2;
+      st_g = col0 / st_cpg;
+      st_next = (st_g + 1) * st_cpg;
+      st_s = 0.f; st_q = 0.f;
+    }
   }
   __device__ __forceinline__ void chunk(int chunk, uint32_t (&r)[32]) {
     const int c = col0 + chunk * 32;
-    if (row >= rows || c >= cout) return;
-    float* y = Y + row * ldy + c;
-    if (vec_ok && c + 32 <= cout) {
+    if (c >= cout) return;                              // warp-uniform
+    const bool row_ok = row < rows;
+    const bool full = vec_ok && c + 32 <= cout;
+    float v[32];
+    if (full) {
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) {
-        float4 b4 = bias ? *reinterpret_cast<const float4*>(bias + c + j4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 b4 = bias ? *reinterpret_cast<const float4*>(bias + c + j4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 w4 = *reinterpret_cast<const float4*>(w_inv + c + j4 * 4);
-        float4 o;
-        o.x = act_apply(fmaf(__uint_as_float(r[4 * j4 + 0]), inv * w4.x, b4.x), act_out);
-        o.y = act_apply(fmaf(__uint_as_float(r[4 * j4 + 1]), inv * w4.y, b4.y), act_out);
-        o.z = act_apply(fmaf(__uint_as_float(r[4 * j4 + 2]), inv * w4.z, b4.z), act_out);
-        o.w = act_apply(fmaf(__uint_as_float(r[4 * j4 + 3]), inv * w4.w, b4.w), act_out);
-        reinterpret_cast<float4*>(y)[j4] = o;
+        v[4 * j4 + 0] = fmaf(__uint_as_float(r[4 * j4 + 0]), inv * w4.x, b4.x);
+        v[4 * j4 + 1] = fmaf(__uint_as_float(r[4 * j4 + 1]), inv * w4.y, b4.y);
+        v[4 * j4 + 2] = fmaf(__uint_as_float(r[4 * j4 + 2]), inv * w4.z, b4.z);
+        v[4 * j4 + 3] = fmaf(__uint_as_float(r[4 * j4 + 3]), inv * w4.w, b4.w);
       }
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (c + j < cout)
-          y[j] = act_apply(fmaf(__uint_as_float(r[j]), inv * w_inv[c + j], bias ? bias[c + j] : 0.f), act_out);
+        v[j] = c + j < cout ? fmaf(__uint_as_float(r[j]), inv * w_inv[c + j], bias ? bias[c + j] : 0.f) : 0.f;
+    }
+    if (stats && st_live) {
+      // running (sum, sum of squares) of the current channel group; columns are the same in every lane, so the
+      // group boundaries are warp-uniform and a finished group is reduced over the warp's 32 rows once
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (c + j >= st_next) {
+          flush_stats();
+          st_s = 0.f; st_q = 0.f; ++st_g; st_next += st_cpg;
+        }
+        if (row_ok && c + j < cout) {
+          st_s += v[j];
+          st_q = fmaf(v[j], v[j], st_q);
+        }
+      }
+    }
+    if (!row_ok) return;
+    float* y = Y + row * ldy + c;
+    if (full) {
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4)
+        reinterpret_cast<float4*>(y)[j4] = make_float4(act_apply(v[4 * j4], act_out), act_apply(v[4 * j4 + 1], act_out),
+                                                       act_apply(v[4 * j4 + 2], act_out), act_apply(v[4 * j4 + 3], act_out));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (c + j < cout) y[j] = act_apply(v[j], act_out);
     }
   }
-  __device__ __forceinline__ void finish() {}
+  // per-thread state of the running group
+  double* st_row;
+  float st_s, st_q;
+  int st_g, st_next;
+  bool st_live;
+  __device__ __forceinline__ void flush_stats() {
+    const float s = warp_sum(st_s), q = warp_sum(st_q);
+    if ((threadIdx.x & 31) == 0 && st_g < st_groups) {
+      atomicAdd(st_row + 2 * st_g, (double)s);
+      atomicAdd(st_row + 2 * st_g + 1, (double)q);
+    }
+  }
+  __device__ __forceinline__ void finish() {
+    if (stats && st_live) flush_stats();
+  }
 };
 
 struct Layout {
@@ -168,6 +260,17 @@ extern "C" size_t caspr_linear_tc_workspace_bytes(int rows, int Cin, int Cout) {
   return make_layout(rows, Cin, Cout).total;
 }
 
+extern "C" int caspr_gn_table(const double* stats, int samples, int groups, int rows_per_sample, int C, float eps,
+                              const float* gamma, const float* beta, float* table, void* stream) {
+  CASPR_REQUIRE(stats && table && gamma && beta && samples > 0 && groups > 0 && rows_per_sample > 0 && C % groups == 0);
+  const int n = samples * C;
+  const double count = (double)(C / groups) * (double)rows_per_sample;
+  CASPR_COUNT(); gn_table_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(stats, samples, groups, C, count, eps,
+                                                                                   gamma, beta, (float2*)table);
+  CASPR_CHECK_LAUNCH();
+  return CASPR_OK;
+}
+
 extern "C" size_t caspr_linear_tc_weight_bytes(int Cin, int Cout) {
   if (Cin <= 0 || Cout <= 0) return 0;
   return make_weight_layout(Cin, Cout).total;
@@ -188,9 +291,16 @@ extern "C" int caspr_linear_tc_prepare_weights(const float* W, int ldw, int Cin,
 
 extern "C" int caspr_linear_tc(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y,
                                int ldy, int rows, int Cin, int Cout, int act_in, int act_out,
-                               const void* prepared_weights, void* workspace, size_t workspace_bytes,
+                               const void* prepared_weights, const caspr_gn_fold* in_norm,
+                               const caspr_gn_stats* out_stats, void* workspace, size_t workspace_bytes,
                                void* stream) {
   CASPR_REQUIRE(X && (W || prepared_weights) && Y && workspace && rows > 0 && Cin > 0 && Cout > 0);
+  if (in_norm)
+    CASPR_REQUIRE(in_norm->table && in_norm->rows_per_sample > 0);
+  if (out_stats)
+    CASPR_REQUIRE(out_stats->stats && out_stats->groups > 0 && Cout % out_stats->groups == 0 &&
+                  out_stats->rows_per_sample > 0 && out_stats->rows_per_sample % 32 == 0 &&
+                  rows % out_stats->rows_per_sample == 0);
   CASPR_REQUIRE(ldx >= Cin && (!W || ldw >= Cin) && ldy >= Cout);
   CASPR_REQUIRE(act_in == CASPR_ACT_NONE || act_in == CASPR_ACT_RELU);
   CASPR_REQUIRE(((uintptr_t)workspace & 1023) == 0 && ((uintptr_t)prepared_weights & 1023) == 0);
@@ -213,9 +323,18 @@ extern "C" int caspr_linear_tc(const float* X, int ldx, const float* W, int ldw,
   const __half* wlo = (const __half*)(wbase + wl.off_wlo);
 
   const int nb = 148 * 8;
+  NormFold nf = NormFold();
+  if (in_norm) {
+    nf.tab = (const float2*)in_norm->table; nf.rows_per_sample = in_norm->rows_per_sample; nf.C = Cin;
+    nf.relu = in_norm->relu;
+  }
   CASPR_COUNT(); split_rows_kernel<<<nb, 256, 0, s>>>(X, ldx, rows, Cin, l.rows_pad, l.k_pad, act_in == CASPR_ACT_RELU,
-                                       (__half2*)xhi, (__half2*)xlo, xinv);
+                                       (__half2*)xhi, (__half2*)xlo, xinv, nf);
   CASPR_CHECK_LAUNCH();
+  if (out_stats) {
+    const size_t n_stats = (size_t)(rows / out_stats->rows_per_sample) * out_stats->groups * 2;
+    if (cudaMemsetAsync(out_stats->stats, 0, n_stats * sizeof(double), s) != cudaSuccess) return CASPR_ELAUNCH;
+  }
 
   CUtensorMap tm_xhi, tm_xlo, tm_whi, tm_wlo;
   bool ok = true;
@@ -237,6 +356,10 @@ extern "C" int caspr_linear_tc(const float* X, int ldx, const float* W, int ldw,
   LinearEpilogue epi{};
   epi.bias = bias; epi.x_inv = xinv; epi.w_inv = winv; epi.Y = Y; epi.ldy = ldy; epi.rows = rows; epi.cout = Cout;
   epi.act_out = act_out;
+  if (out_stats) {
+    epi.stats = out_stats->stats; epi.st_rows_per_sample = out_stats->rows_per_sample;
+    epi.st_groups = out_stats->groups; epi.st_cpg = Cout / out_stats->groups;
+  }
   epi.vec_ok = (ldy % 4 == 0) && (((uintptr_t)Y & 15) == 0) && (!bias || ((uintptr_t)bias & 15) == 0);
   const int m_tiles = (int)(l.rows_pad / kBM), n_tiles = l.cout_pad / kBN;
   int grid = m_tiles * n_tiles;

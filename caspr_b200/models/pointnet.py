@@ -30,13 +30,12 @@ class PointNetfeat(nn.Module):
         `pointfeat_out` / `global_out` may be column slices of a wider concat buffer."""
         pf = ops.linear(rows, self.conv1.weight, self.conv1.bias, out=pointfeat_out)
         ops.groupnorm(pf, samples, rows_per_sample, NUM_GROUPS, self.bn1.weight, self.bn1.bias, relu=True)
-        h = ops.linear(pf, self.conv2.weight, self.conv2.bias)
-        ops.groupnorm(h, samples, rows_per_sample, NUM_GROUPS, self.bn2.weight, self.bn2.bias, relu=True)
-        h3 = ops.linear(h, self.conv3.weight, self.conv3.bias)
+        h3, st3 = ops.conv_gn_relu_conv(pf, self.conv2, self.bn2, self.conv3, samples, rows_per_sample, NUM_GROUPS,
+                                        stats_b=True)
         if global_out is None:
             global_out = torch.empty(samples, self.out_size, dtype=torch.float32, device=rows.device)
         ops.groupnorm(h3, samples, rows_per_sample, NUM_GROUPS, self.bn3.weight, self.bn3.bias, relu=False,
-                      write_back=False, maxout=global_out)
+                      write_back=False, maxout=global_out, stats=st3)
         return global_out, pf
 
     def forward(self, x):

@@ -136,6 +136,11 @@ class PointNet2FeaturePropagator(nn.Module):
         Bp, n, _ = xyz.shape
         dist, idx = ops.three_nn(xyz, xyz_prev)
         h = ops.three_interp_concat(features_prev, idx, dist, features)
+        if len(self.unit_pointnet) == 6:
+            conv_a, gn_a, _, conv_b, gn_b, _ = self.unit_pointnet
+            h, st = ops.conv_gn_relu_conv(h, conv_a, gn_a, conv_b, Bp, n, NUM_GROUPS, stats_b=True)
+            ops.groupnorm(h, Bp, n, NUM_GROUPS, gn_b.weight, gn_b.bias, relu=True, stats=st)
+            return h.view(Bp, n, -1)
         for i in range(0, len(self.unit_pointnet), 3):
             conv, gn = self.unit_pointnet[i], self.unit_pointnet[i + 1]
             h = ops.linear(h, conv.weight, conv.bias)
@@ -206,9 +211,7 @@ class PointNet2feat(nn.Module):
             ti -= 1
         h = feat_list[0].reshape(Bp * N, -1)
         conv0, gn, _, conv1 = self.final_layers
-        h = ops.linear(h, conv0.weight, conv0.bias)
-        ops.groupnorm(h, Bp, N, NUM_GROUPS, gn.weight, gn.bias, relu=True)
-        return ops.linear(h, conv1.weight, conv1.bias, out=out)
+        return ops.conv_gn_relu_conv(h, conv0, gn, conv1, Bp, N, NUM_GROUPS, out=out)
 
     def forward(self, points):
         """Reference layout: points (B',N,3+C) -> (B',N,num_classes)."""

@@ -109,12 +109,11 @@ class TPointNet2(nn.Module):
             trace.setdefault('ball_idx', [])
         self.local_extract.forward_rows(local_in.view(B * T, N, -1), out=feat[:, :L], trace=trace)
         # head (tpointnet2.py:99-113)
-        h = ops.linear(feat, self.conv1.weight, self.conv1.bias)
-        ops.groupnorm(h, B, T * N, 16, self.bn1.weight, self.bn1.bias, relu=True)
-        h2 = ops.linear(h, self.conv2.weight, self.conv2.bias, out=feat if self.latent_feat_size == feat.shape[1] else None)
+        h2, st2 = ops.conv_gn_relu_conv(feat, self.conv1, self.bn1, self.conv2, B, T * N, 16,
+                                        out=feat if self.latent_feat_size == feat.shape[1] else None, stats_b=True)
         z0 = torch.empty(B, self.latent_feat_size, dtype=torch.float32, device=x.device)
         ops.groupnorm(h2, B, T * N, 16, self.bn2.weight, self.bn2.bias, relu=False, write_back=self.regress_tnocs,
-                      maxout=z0)
+                      maxout=z0, stats=st2)
         tnocs = None
         if self.regress_tnocs:
             t = ops.linear(h2, self.conv3.weight, self.conv3.bias, act_in=ops.ACT_RELU, act_out=ops.ACT_SIGMOID)

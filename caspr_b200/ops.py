@@ -163,11 +163,57 @@ def _prepared_weights(weight, w2d):
     return planes_ptr
 
 
-def linear(x, weight, bias=None, out=None, act_in=ACT_NONE, act_out=ACT_NONE, engine='auto'):
+class PendingNorm(object):
+    """GroupNorm (+ReLU) that has NOT been applied to a tensor yet: the statistics were accumulated by the GEMM
+    that produced it; the next tensor-core linear folds the normalisation into its operand split
+    (``linear(..., in_norm=...)``) or ``groupnorm(..., stats=...)`` materialises it."""
+
+    def __init__(self, stats, samples, rows_per_sample, groups, channels, gamma, beta, relu, eps=1e-5):
+        self.stats, self.samples, self.rows_per_sample, self.groups = stats, samples, rows_per_sample, groups
+        self.channels, self.gamma, self.beta, self.relu, self.eps = channels, gamma, beta, relu, eps
+        self._table = None
+
+    def table(self):
+        if self._table is None:
+            self._table = torch.empty(self.samples * self.channels * 2, dtype=torch.float32,
+                                      device=self.stats.device)
+            _count('gn_table')
+            check(lib.caspr_gn_table(_p(self.stats), self.samples, self.groups, self.rows_per_sample, self.channels,
+                                     float(self.eps), _p(self.gamma), _p(self.beta), _p(self._table), _stream()),
+                  'caspr_gn_table')
+        return self._table
+
+
+def tc_eligible(rows, cin, cout):
+    return LINEAR_ENGINE != 'simt' and rows >= TC_MIN_ROWS and cin >= TC_MIN_CIN and cout >= TC_MIN_COUT
+
+
+def conv_gn_relu_conv(x, conv_a, gn_a, conv_b, samples, rows_per_sample, groups, out=None, stats_b=False):
+    """Conv1d -> GroupNorm -> ReLU -> Conv1d on rows.  On the tensor-core path the first GEMM's epilogue
+    accumulates the GroupNorm statistics and the second GEMM normalises while splitting its operand, so the
+    normalised intermediate never exists in memory.  Returns y (and y's statistics if stats_b)."""
+    rows, cin = x.shape
+    ca, cb = conv_a.weight.shape[0], conv_b.weight.shape[0]
+    fold = tc_eligible(rows, cin, ca) and tc_eligible(rows, ca, cb) and rows_per_sample % 32 == 0
+    if fold:
+        h, st = linear(x, conv_a.weight, conv_a.bias, engine='tc', out_stats=(samples, rows_per_sample, groups))
+        pn = PendingNorm(st, samples, rows_per_sample, groups, ca, gn_a.weight, gn_a.bias, relu=True, eps=gn_a.eps)
+        return linear(h, conv_b.weight, conv_b.bias, out=out, engine='tc', in_norm=pn,
+                      out_stats=(samples, rows_per_sample, groups) if stats_b else None)
+    h = linear(x, conv_a.weight, conv_a.bias)
+    groupnorm(h, samples, rows_per_sample, groups, gn_a.weight, gn_a.bias, eps=gn_a.eps, relu=True)
+    y = linear(h, conv_b.weight, conv_b.bias, out=out)
+    return (y, None) if stats_b else y
+
+
+def linear(x, weight, bias=None, out=None, act_in=ACT_NONE, act_out=ACT_NONE, engine='auto', in_norm=None,
+           out_stats=None):
     """1x1 Conv1d / Linear on rows: y = act_out(act_in(x) @ W^T + b).
 
     x (rows, Cin) view; weight (Cout, Cin) or Conv1d-shaped (Cout, Cin, 1); out optional (rows, Cout) view.
-    engine: 'auto' (tensor cores for large layers), 'tc' or 'simt'."""
+    engine: 'auto' (tensor cores for large layers), 'tc' or 'simt'.
+    Tensor-core engine only: in_norm = PendingNorm of x (normalise while splitting the operand);
+    out_stats = (samples, rows_per_sample, groups): also return the fp64 GroupNorm statistics of y."""
     x, ldx = _rows2d(x, 'x')
     w = weight.reshape(weight.shape[0], weight.shape[1])
     _f32(w, 'weight')
@@ -183,7 +229,17 @@ def linear(x, weight, bias=None, out=None, act_in=ACT_NONE, act_out=ACT_NONE, en
         engine = LINEAR_ENGINE if (LINEAR_ENGINE == 'simt' or cin >= 16) else 'simt'
     if engine == 'auto':
         engine = 'tc' if (rows >= TC_MIN_ROWS and cin >= TC_MIN_CIN and cout >= TC_MIN_COUT) else 'simt'
+    if engine != 'tc' and (in_norm is not None or out_stats is not None):
+        raise ValueError('GroupNorm folding is implemented by the tensor-core linear only')
     if engine == 'tc':
+        fold_s = stats_s = None
+        stats_t = None
+        if in_norm is not None:
+            fold_s = _lib.GnFold(in_norm.table().data_ptr(), in_norm.rows_per_sample, int(in_norm.relu))
+        if out_stats is not None:
+            samples, rps, groups = out_stats
+            stats_t = torch.empty(samples * groups * 2, dtype=torch.float64, device=x.device)
+            stats_s = _lib.GnStats(stats_t.data_ptr(), rps, groups)
         ws_bytes = lib.caspr_linear_tc_workspace_bytes(rows, cin, cout)
         ws, ws_ptr = _aligned_bytes(ws_bytes, x.device)
         # weights are split once per (storage, in-place version); CUDA graphs that captured a call are keyed
@@ -191,9 +247,11 @@ def linear(x, weight, bias=None, out=None, act_in=ACT_NONE, act_out=ACT_NONE, en
         prepared = _prepared_weights(weight, w)
         _count('linear_tc')
         check(lib.caspr_linear_tc(_p(x), ldx, _p(w), cin, _p(bias), _p(out), ldy, rows, cin, cout, act_in, act_out,
-                                  ctypes.c_void_p(prepared) if prepared else None, ctypes.c_void_p(ws_ptr), ws_bytes,
-                                  _stream()), 'caspr_linear_tc')
-        return out
+                                  ctypes.c_void_p(prepared) if prepared else None,
+                                  ctypes.byref(fold_s) if fold_s is not None else None,
+                                  ctypes.byref(stats_s) if stats_s is not None else None,
+                                  ctypes.c_void_p(ws_ptr), ws_bytes, _stream()), 'caspr_linear_tc')
+        return (out, stats_t) if out_stats is not None else out
     _count('linear')
     check(lib.caspr_linear(_p(x), ldx, _p(w), cin, _p(bias), _p(out), ldy, rows, cin, cout, act_in, act_out,
                            _stream()), 'caspr_linear')
@@ -222,11 +280,12 @@ def linear_gn_ball(x, weight, bias, gamma, beta, ns, relu, want_rows=True, maxou
 
 
 def groupnorm(x, samples, rows_per_sample, groups, gamma, beta, eps=1e-5, relu=False, write_back=True,
-              maxout=None):
+              maxout=None, stats=None):
     """In-place GroupNorm(groups, C) over `samples` blocks of consecutive rows, fused ReLU / max-pool.
 
     x (samples*rows_per_sample, C) view.  maxout: optional (samples, C) view receiving the max over
-    the rows of each sample of the normalised (and ReLU'd) values."""
+    the rows of each sample of the normalised (and ReLU'd) values.  stats: fp64 (sum, sum of squares)
+    already accumulated by the producing GEMM (skips the statistics pass)."""
     x, ldx = _rows2d(x, 'x')
     C = x.shape[1]
     assert x.shape[0] == samples * rows_per_sample
@@ -234,10 +293,12 @@ def groupnorm(x, samples, rows_per_sample, groups, gamma, beta, eps=1e-5, relu=F
     if maxout is not None:
         maxout, ld_max = _rows2d(maxout, 'maxout')
         assert maxout.shape == (samples, C)
-    stats = torch.empty(samples * groups * 2, dtype=torch.float64, device=x.device)
+    ready = stats is not None
+    if stats is None:
+        stats = torch.empty(samples * groups * 2, dtype=torch.float64, device=x.device)
     _count('groupnorm')
     check(lib.caspr_groupnorm(_p(x), ldx, samples, rows_per_sample, C, groups, _p(gamma), _p(beta), float(eps),
-                              int(relu), int(write_back), _p(maxout), ld_max, _p(stats), _stream()),
+                              int(relu), int(write_back), _p(maxout), ld_max, _p(stats), int(ready), _stream()),
           'caspr_groupnorm')
     return x
 

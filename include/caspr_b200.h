@@ -116,6 +116,26 @@ int caspr_linear_gn_ball(const float* X, int ldx, const float* W, int ldw, const
  * two taken from max|X| and max|W| (undone exactly in the epilogue).  Meant for the large layers
  * (feature propagation, final layers, the 1600-wide head); any Cin / Cout / rows are accepted.
  * workspace: caspr_linear_tc_workspace_bytes(rows, Cin, Cout) bytes, 1024-byte aligned. */
+/* GroupNorm folded around the tensor-core linear (saves the separate statistics and normalisation passes
+ * of a Conv1d -> GroupNorm -> ReLU -> Conv1d chain, pointnet2.py:471-481, tpointnet2.py:99-100):
+ *   out_stats : the epilogue accumulates per (sample, group) the sum and the sum of squares of the OUTPUT
+ *               rows (fp64 [samples][groups][2], zeroed by the call); rows_per_sample % 32 == 0.
+ *   caspr_gn_table turns them into per (sample, channel) fp32 pairs (scale, shift) = (rstd*gamma,
+ *               beta - mean*rstd*gamma), [samples][C][2].
+ *   in_norm   : the operand split of the next layer applies ReLU?(x*scale + shift) on the fly.
+ * caspr_groupnorm(..., stats_ready = 1) consumes the same statistics when the normalised tensor itself
+ * (or its max-pool) is needed. */
+typedef struct {
+  const float* table;        /* [samples][C] (scale, shift) from caspr_gn_table */
+  int rows_per_sample, relu;
+} caspr_gn_fold;
+typedef struct {
+  double* stats;             /* [samples][groups][2] */
+  int rows_per_sample, groups;
+} caspr_gn_stats;
+int caspr_gn_table(const double* stats, int samples, int groups, int rows_per_sample, int C, float eps,
+                   const float* gamma, const float* beta, float* table, void* stream);
+
 size_t caspr_linear_tc_workspace_bytes(int rows, int Cin, int Cout);
 /* Optional: split the weights once (caspr_linear_tc_weight_bytes bytes, 1024-byte aligned) and pass the
  * block as `prepared_weights` for as long as W does not change; with prepared_weights == NULL the split
@@ -125,16 +145,19 @@ int caspr_linear_tc_prepare_weights(const float* W, int ldw, int Cin, int Cout, 
                                     size_t prepared_bytes, void* stream);
 int caspr_linear_tc(const float* X, int ldx, const float* W, int ldw, const float* bias,
                     float* Y, int ldy, int rows, int Cin, int Cout, int act_in, int act_out,
-                    const void* prepared_weights, void* workspace, size_t workspace_bytes, void* stream);
+                    const void* prepared_weights, const caspr_gn_fold* in_norm, const caspr_gn_stats* out_stats,
+                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* GroupNorm over samples of `rows_per_sample` consecutive rows (torch.nn.GroupNorm(groups, C)
  * on (samples, C, rows_per_sample)), eps as given; optional ReLU; optional max over the rows
  * of each sample AFTER normalisation (and after ReLU if set) into maxout (samples, C) with
  * row stride ld_max.  If write_back == 0 X is left untouched (only maxout is produced).
- * stats_ws: >= samples*groups*2 doubles (used when a sample spans several CTAs). */
+ * stats_ws: >= samples*groups*2 doubles (used when a sample spans several CTAs); with stats_ready != 0 it
+ * already holds the (sum, sum of squares) pairs (caspr_linear_tc out_stats) and the statistics pass is skipped. */
 int caspr_groupnorm(float* X, int ldx, int samples, int rows_per_sample, int C, int groups,
                     const float* gamma, const float* beta, float eps, int relu,
-                    int write_back, float* maxout, int ld_max, double* stats_ws, void* stream);
+                    int write_back, float* maxout, int ld_max, double* stats_ws, int stats_ready,
+                    void* stream);
 
 /* tpointnet2.py:79-90: x (R,4) rows [x,y,z,t] -> out (R,9) rows [x,y,z,x2,y2,z2,xz,xy,yz]. */
 int caspr_augment_xyz(const float* x4, int rows, float* out9, void* stream);

@@ -154,6 +154,37 @@ def test_linear_tensor_core_strided_and_relu_in(ops):
     assert float(out[:, :30].abs().sum()) == 0 and float(out[:, 130:].abs().sum()) == 0
 
 
+def test_conv_gn_relu_conv_fold_matches_unfused(ops):
+    """GroupNorm folded around the tensor-core GEMMs (statistics in the epilogue, normalisation in the next
+    operand split) against fp64 torch and against the unfused kernel sequence."""
+    g = torch.Generator().manual_seed(4)
+    samples, rps, cin, ca, cb = 3, 1024, 96, 128, 80
+    x = torch.randn(samples * rps, cin, generator=g)
+    conv_a = torch.nn.Conv1d(cin, ca, 1)
+    conv_b = torch.nn.Conv1d(ca, cb, 1)
+    gn_a = torch.nn.GroupNorm(16, ca)
+    with torch.no_grad():
+        gn_a.weight.uniform_(0.5, 1.5)
+        gn_a.bias.normal_(0, 0.1)
+    ref_in = x.view(samples, rps, cin).transpose(1, 2).double()
+    ref = conv_b.double()(torch.relu(gn_a.double()(conv_a.double()(ref_in))))           # (samples, cb, rps)
+    ref_rows = ref.transpose(1, 2).reshape(samples * rps, cb)
+    ref_stats = torch.stack([ref.view(samples, 16, -1).sum(-1), (ref.view(samples, 16, -1) ** 2).sum(-1)], -1)
+    for m in (conv_a, conv_b, gn_a):
+        m.float().to(DEV)
+    y, st = ops.conv_gn_relu_conv(x.to(DEV), conv_a, gn_a, conv_b, samples, rps, 16, stats_b=True)
+    assert st is not None                                                            # the folded path ran
+    assert _rel(y, ref_rows) < 1e-5
+    assert _rel(st.view(samples, 16, 2), ref_stats) < 1e-5
+    old = ops.LINEAR_ENGINE
+    ops.LINEAR_ENGINE = 'simt'
+    try:
+        y2 = ops.conv_gn_relu_conv(x.to(DEV), conv_a, gn_a, conv_b, samples, rps, 16)
+    finally:
+        ops.LINEAR_ENGINE = old
+    assert _rel(y, y2) < 1e-5
+
+
 def test_linear_strided_views(ops):
     g = torch.Generator().manual_seed(5)
     buf = torch.randn(200, 96, generator=g).to(DEV)
