@@ -305,8 +305,17 @@ def run_ours(args, rank, world, local_rank):
     if cnt > 0:
         avg_ms = tot_ms / cnt
         achieved = flop_per_launch / (avg_ms * 1e-3) / 1e12
+        # DRAM bytes per launch from the committed ncu --set full capture of the same kernels on this workload
+        # (profiles/r1_ncu_cnf_gemm_fp16x3_tcgen05.txt: layer 1 reads 672.5 MB + writes 619.1 MB, layer 2 reads
+        # 677.8 MB + writes 7.9 MB; profiles/r1_ncu_cnf_mid_layer_simt.txt: 2686 MB + 651 MB); algorithmic bytes
+        # are 671 MB per plane pass, i.e. 1342 MB (layer 1) and 671 MB (layer 2)
+        traffic = None
+        if B * Tq * P == 163840:
+            traffic = (672.53e6 + 619.10e6 + 677.78e6 + 7.89e6) / 2 if 'tcgen05' in kname else 2686.1e6 + 650.7e6
         roofline = {'bound': 'tensor', 'kernel': kname, 'achieved': achieved, 'peak': peaks['tf_sustained'],
-                    'unit': 'TFLOP/s', 'frac': achieved / peaks['tf_sustained'], 'traffic': None,
+                    'unit': 'TFLOP/s', 'frac': achieved / peaks['tf_sustained'], 'traffic': traffic,
+                    'traffic_unit': 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, average of '
+                                    'the two H x H layers)',
                     'peak_source': peaks['source'] + ' bf16 dense sustained', 'launches': cnt,
                     'avg_launch_ms': avg_ms, 'share_of_step': tot_ms / (ms / args.steps) / args.steps,
                     'flop_per_launch': flop_per_launch,

@@ -523,33 +523,50 @@ cnf_passthrough_kernel(const float4* __restrict__ y0, int n, MbnDev post, int re
 }
 
 // Hyper-network hoist: out[f][j] = W[j][1:1+C] . ctx[f] (+ bias[j]) for a handful of frames.  A skinny GEMM
-// (frames x C x D with frames ~ 80): one warp per output channel keeps its weight row in registers and
-// streams the contexts from L2, instead of a tiled GEMM that would run on four CTAs.
+// (frames x C x D with frames ~ 80).  Each CTA owns 16 output channels (two per warp, weight rows kept in
+// registers) for one tile of 8 frames staged in shared memory (grid = channel blocks x frame tiles).
 constexpr int kHoistMaxC = 2048;
+constexpr int kHoistFrames = 8;
+constexpr int kHoistChPerCta = 16;
 __global__ void __launch_bounds__(256)
 cnf_hyper_hoist_kernel(const float* __restrict__ ctx, int C, const float* __restrict__ W, int ldw,
                        const float* __restrict__ bias, int frames, int D, float* __restrict__ out, int ld_out) {
-  const int lane = threadIdx.x & 31;
-  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (j >= D) return;
-  const float* wrow = W + (size_t)j * ldw + 1;                 // column 0 multiplies t
-  float w[kHoistMaxC / 32];
+  extern __shared__ float s_ctx[];                               // kHoistFrames x C
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j0 = blockIdx.x * kHoistChPerCta + warp * 2;
+  float w0[kHoistMaxC / 32], w1[kHoistMaxC / 32];
 #pragma unroll
   for (int i = 0; i < kHoistMaxC / 32; ++i) {
     const int k = lane + 32 * i;
-    w[i] = k < C ? wrow[k] : 0.f;
+    w0[i] = (k < C && j0 < D) ? W[(size_t)j0 * ldw + 1 + k] : 0.f;          // column 0 multiplies t
+    w1[i] = (k < C && j0 + 1 < D) ? W[(size_t)(j0 + 1) * ldw + 1 + k] : 0.f;
   }
-  const float b = bias ? bias[j] : 0.f;
-  for (int f = 0; f < frames; ++f) {
-    const float* c = ctx + (size_t)f * C;
-    float acc = 0.f;
+  const float b0 = (bias && j0 < D) ? bias[j0] : 0.f;
+  const float b1 = (bias && j0 + 1 < D) ? bias[j0 + 1] : 0.f;
+  {
+    const int f0 = blockIdx.y * kHoistFrames;                    // one tile of frames per CTA
+    const int nf = min(kHoistFrames, frames - f0);
+    for (int i = threadIdx.x; i < nf * C; i += 256) s_ctx[i] = ctx[(size_t)f0 * C + i];
+    __syncthreads();
+    for (int f = 0; f < nf; ++f) {
+      const float* c = s_ctx + f * C;
+      float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-    for (int i = 0; i < kHoistMaxC / 32; ++i) {
-      const int k = lane + 32 * i;
-      if (k < C) acc = fmaf(w[i], c[k], acc);
+      for (int i = 0; i < kHoistMaxC / 32; ++i) {
+        const int k = lane + 32 * i;
+        if (k < C) {
+          const float cv = c[k];
+          a0 = fmaf(w0[i], cv, a0);
+          a1 = fmaf(w1[i], cv, a1);
+        }
+      }
+      a0 = warp_sum(a0);
+      a1 = warp_sum(a1);
+      if (lane == 0) {
+        if (j0 < D) out[(size_t)(f0 + f) * ld_out + j0] = a0 + b0;
+        if (j0 + 1 < D) out[(size_t)(f0 + f) * ld_out + j0 + 1] = a1 + b1;
+      }
     }
-    acc = warp_sum(acc);
-    if (lane == 0) out[(size_t)f * ld_out + j] = acc + b;
   }
 }
 
@@ -640,10 +657,19 @@ int prepare_hyper(const CnfWorkspace& w, const caspr_cnf_weights* cw, const floa
   for (int l = 0; l < 4; ++l) {
     const int D = l < 3 ? H : 3;
     if (C <= kHoistMaxC) {
-      CASPR_COUNT(); cnf_hyper_hoist_kernel<<<ceil_div(D, 8), 256, 0, s>>>(ctx, C, cw->Wgate[l], C + 1, cw->bgate[l],
-                                                                          frames, D, w.Gc + off, ctot);
-      CASPR_COUNT(); cnf_hyper_hoist_kernel<<<ceil_div(D, 8), 256, 0, s>>>(ctx, C, cw->Wbias[l], C + 1, nullptr,
-                                                                          frames, D, w.Bc + off, ctot);
+      const size_t smem = (size_t)kHoistFrames * C * sizeof(float);
+      static bool attr_set = false;
+      if (!attr_set) {
+        if (cudaFuncSetAttribute(cnf_hyper_hoist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kHoistFrames * kHoistMaxC * (int)sizeof(float)) != cudaSuccess)
+          return CASPR_ELAUNCH;
+        attr_set = true;
+      }
+      const dim3 grid(ceil_div(D, kHoistChPerCta), ceil_div(frames, kHoistFrames));
+      CASPR_COUNT(); cnf_hyper_hoist_kernel<<<grid, 256, smem, s>>>(ctx, C, cw->Wgate[l], C + 1, cw->bgate[l], frames, D,
+                                                                   w.Gc + off, ctot);
+      CASPR_COUNT(); cnf_hyper_hoist_kernel<<<grid, 256, smem, s>>>(ctx, C, cw->Wbias[l], C + 1, nullptr, frames, D,
+                                                                   w.Bc + off, ctot);
     } else {
       int rc = caspr_linear(ctx, C, cw->Wgate[l] + 1, C + 1, cw->bgate[l], w.Gc + off, ctot, frames, C, D,
                             CASPR_ACT_NONE, CASPR_ACT_NONE, s);

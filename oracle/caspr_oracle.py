@@ -84,7 +84,8 @@ class CasprOracle(object):
             self.trace['ball_idx_%d_%d' % (level, s)] = bq
             gxyz = pn2.group_gather_by_index(xyz.transpose(1, 2).contiguous(), bq)
             gxyz = gxyz - new_xyz.transpose(1, 2).unsqueeze(-1)
-            g = torch.cat([gxyz, pn2.group_gather_by_index(features, bq)], dim=1)   # (B,3+C,M,ns)
+            g = gxyz if features is None else \
+                torch.cat([gxyz, pn2.group_gather_by_index(features, bq)], dim=1)  # (B,3+C,M,ns)
             g = g.permute(0, 2, 1, 3).reshape(B * M, g.shape[1], ns)                # :397
             prefix = 'encoder.local_extract.set_abstractions.%d.pointnet_modules.%d.' % (level, s)
             f = self._sa_pointnet(g, prefix)                                        # :401
@@ -97,7 +98,8 @@ class CasprOracle(object):
         inv = 1.0 / (dist + 1e-8)                                                   # :516
         w = inv / torch.sum(inv, dim=2, keepdim=True)                               # :517-518
         new = pn2.three_interpolate(features_prev, idx, w)                          # :519
-        new = torch.cat([new, features], dim=1)                                     # :523
+        if features is not None:                                                    # :521-523
+            new = torch.cat([new, features], dim=1)
         p = 'encoder.local_extract.feature_propagators.%d.unit_pointnet.' % i
         new = F.relu(self._gn(self._conv(new, p + '0'), p + '1'))
         new = F.relu(self._gn(self._conv(new, p + '3'), p + '4'))
