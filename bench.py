@@ -292,8 +292,11 @@ def run_ours(args, rank, world, local_rank):
     # dominant kernel: the H x H layers of the CNF dynamics over [activation ; tangent] rows
     H = 512
     n_pts = B * Tq * P
-    # ALGORITHMIC flops of one launch: one H x H ConcatSquash layer over {activation, tangent} rows of every point
-    flop_per_launch = 2.0 * 2 * n_pts * H * H
+    # ALGORITHMIC flops: one H x H ConcatSquash layer over {activation, tangent} rows of every point, two such
+    # layers per dynamics evaluation.  The tensor-core engine pipelines the point set in two halves on two
+    # streams, so a launch covers n_pts / chunks points; flops per launch follow from the launch count.
+    layer_flop = 2.0 * 2 * n_pts * H * H
+    chunks = 2 if (os.environ.get('CASPR_CNF_PIPELINE_HALVES') == '1' and (n_pts + 63) // 64 >= 296) else 1
     if prof['cnf_tc_layer_kernel'][1] > 0:
         kname = 'gemm_fp16x3_kernel<CnfEpilogue> (tcgen05, 3 fp16 MMAs per algorithmic MAC)'
         prof[kname] = prof['cnf_tc_layer_kernel']
@@ -304,6 +307,7 @@ def run_ours(args, rank, world, local_rank):
     roofline = None
     if cnt > 0:
         avg_ms = tot_ms / cnt
+        flop_per_launch = layer_flop / chunks
         achieved = flop_per_launch / (avg_ms * 1e-3) / 1e12
         # DRAM bytes per launch from the committed ncu --set full capture of the same kernels on this workload
         # (profiles/r1_ncu_cnf_gemm_fp16x3_tcgen05.txt: layer 1 reads 672.5 MB + writes 619.1 MB, layer 2 reads
@@ -312,6 +316,7 @@ def run_ours(args, rank, world, local_rank):
         traffic = None
         if B * Tq * P == 163840:
             traffic = (672.53e6 + 619.10e6 + 677.78e6 + 7.89e6) / 2 if 'tcgen05' in kname else 2686.1e6 + 650.7e6
+            traffic *= flop_per_launch / layer_flop            # the capture covered all points in one launch
         roofline = {'bound': 'tensor', 'kernel': kname, 'achieved': achieved, 'peak': peaks['tf_sustained'],
                     'unit': 'TFLOP/s', 'frac': achieved / peaks['tf_sustained'], 'traffic': traffic,
                     'traffic_unit': 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, average of '

@@ -18,6 +18,7 @@
 // mathematically equal to the reference's VJP (e^T J).e (odefunc.py:13-26).
 //
 // This file holds the exact-fp32 SIMT engine (CASPR_CNF_SIMT_FP32).
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 #include "dopri5.cuh"
@@ -90,10 +91,15 @@ cnf_init_state_kernel(const float* __restrict__ x_in, const float* __restrict__ 
 __global__ void __launch_bounds__(256)
 cnf_hyper_stage_kernel(const float* __restrict__ Gc, const float* __restrict__ Bc,
                        const float* __restrict__ wg_t, const float* __restrict__ wb_t,
-                       const float* __restrict__ lbias, int frames, int ctot, int ld, int stage,
+                       const float* __restrict__ lbias, int frames, int ctot, int ld, int stage_first,
                        int reverse, const CnfState* __restrict__ st, const float* __restrict__ col_scale,
-                       float* __restrict__ gate, float* __restrict__ biasf) {
+                       float* __restrict__ gate_all, float* __restrict__ biasf_all) {
   if (st->done) return;
+  // blockIdx.y selects the RK stage; every stage has its own slot of (frames x ld) gates / biases so that the
+  // stages of a step can be evaluated by independent streams
+  const int stage = stage_first + blockIdx.y;
+  float* gate = gate_all + (size_t)stage * frames * ld;
+  float* biasf = biasf_all + (size_t)stage * frames * ld;
   // stage time exactly as torchdiffeq forms it: ti = t0.to(fp32) + alpha_i * dt.to(fp32); the
   // dynamics see -ti when integrating backwards (odeint001.odeint negates time).
   float ti = (float)st->t;
@@ -606,8 +612,8 @@ CnfWorkspace carve(void* base, int frames, int pts, int H) {
   w.st = (CnfState*)take(sizeof(CnfState));
   w.Gc = (float*)take(frames * ctot * 4);
   w.Bc = (float*)take(frames * ctot * 4);
-  w.gate = (float*)take(frames * ctot * 4);
-  w.biasf = (float*)take(frames * ctot * 4);
+  w.gate = (float*)take(7 * frames * ctot * 4);        // one slot per RK stage (0 = f at the step start)
+  w.biasf = (float*)take(7 * frames * ctot * 4);
   w.wg_t = (float*)take(ctot * 4);
   w.wb_t = (float*)take(ctot * 4);
   w.lbias = (float*)take(ctot * 4);
@@ -687,47 +693,110 @@ int prepare_hyper(const CnfWorkspace& w, const caspr_cnf_weights* cw, const floa
   return CASPR_OK;
 }
 
-// One dynamics evaluation into kbuf[stage] (stage 0 = f at the step start / f0).
-int enqueue_feval(const CnfWorkspace& w, const caspr_cnf_weights* cw, const float* e, int frames,
-                  int pts, int stage, int reverse, int engine, const cnf_tc::Plan* plan, int num_sms,
-                  cudaStream_t s) {
+// Side stream used to pipeline the two halves of the point set (tensor-core engine): while one half runs its
+// MMA-bound GEMMs, the other half's HBM-bound layer-0 kernel shares the SMs.  Created once per process.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool ok = false;
+};
+SideStream& side_stream() {
+  static SideStream ss;
+  if (!ss.ok) {
+    ss.ok = cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) == cudaSuccess;
+  }
+  return ss;
+}
+
+// tensor-core engine: layers 0..3 of one dynamics evaluation for the points [pt0, pt1) into kbuf[stage]
+int enqueue_feval_tc_range(const CnfWorkspace& w, const caspr_cnf_weights* cw, const float* e, int frames, int pts,
+                           int stage, int reverse, const cnf_tc::Plan* plan, int num_sms, int pt0, int pt1,
+                           cudaStream_t s) {
+  const int H = cw->hidden;
+  const int n = frames * pts;
+  const int ctot = hyper_ld(H);
+  const float* gate = w.gate + (size_t)stage * frames * ctot;
+  const float* biasf = w.biasf + (size_t)stage * frames * ctot;
+  const int m0 = pt0 / 64, m1 = (pt1 + 63) / 64;
+  int rc = cnf_tc::enqueue_layer0(*plan, w.y0, w.kbuf, (size_t)n, e, cw->W[0], pt0, pt1, pts, stage, gate, biasf,
+                                  ctot, w.st, w.range_flag, s);
+  if (rc) return rc;
+  rc = cnf_tc::enqueue_mid(*plan, 0, m0, m1 - m0, gate + H, biasf + H, ctot, pt1, pts, w.st, nullptr, nullptr,
+                           w.range_flag, num_sms, s);
+  if (rc) return rc;
+  rc = cnf_tc::enqueue_mid(*plan, 1, m0, m1 - m0, gate + 2 * H, biasf + 2 * H, ctot, pt1, pts, w.st, cw->W[3], w.acc6,
+                           w.range_flag, num_sms, s);
+  if (rc) return rc;
+  return cnf_tc::enqueue_last_finish(w.acc6, e, pt0, pt1, pts, gate + 3 * H, biasf + 3 * H, ctot, reverse, w.st,
+                                     w.kbuf + (size_t)stage * n, s);
+}
+
+// Dynamics evaluations for the RK stages [stage_first, stage_last] into kbuf[stage] (stage 0 = f at the step
+// start / f0).  Stage inputs depend only on the same point's earlier stages, so on the tensor-core engine the two
+// halves of the point set run all stages independently on two streams and meet again before the error norm.
+int enqueue_stages(const CnfWorkspace& w, const caspr_cnf_weights* cw, const float* e, int frames, int pts,
+                   int stage_first, int stage_last, int reverse, int engine, const cnf_tc::Plan* plan, int num_sms,
+                   cudaStream_t s) {
   const int H = cw->hidden;
   const int n = frames * pts;
   const int ctot = hyper_ld(H);
   const long long tot = (long long)frames * ctot;
   const bool use_tc = engine == CASPR_CNF_TC_FP16X3;
-  CASPR_COUNT(); cnf_hyper_stage_kernel<<<(int)((tot + 255) / 256), 256, 0, s>>>(
-      w.Gc, w.Bc, w.wg_t, w.wb_t, w.lbias, frames, 3 * H + 3, ctot, stage, reverse, w.st,
+  const dim3 hgrid((unsigned)((tot + 255) / 256), (unsigned)(stage_last - stage_first + 1));
+  CASPR_COUNT(); cnf_hyper_stage_kernel<<<hgrid, 256, 0, s>>>(
+      w.Gc, w.Bc, w.wg_t, w.wb_t, w.lbias, frames, 3 * H + 3, ctot, stage_first, reverse, w.st,
       use_tc ? w.col_scale : nullptr, w.gate, w.biasf);
+  CASPR_CHECK_LAUNCH();
   if (use_tc) {
-    int rc = cnf_tc::enqueue_layer0(*plan, w.y0, w.kbuf, (size_t)n, e, cw->W[0], n, pts, stage, w.gate, w.biasf,
-                                    ctot, w.st, w.range_flag, s);
-    if (rc) return rc;
-    rc = cnf_tc::enqueue_mid(*plan, 0, w.gate + H, w.biasf + H, ctot, n, pts, w.st, nullptr, nullptr,
-                             w.range_flag, num_sms, s);
-    if (rc) return rc;
-    rc = cnf_tc::enqueue_mid(*plan, 1, w.gate + 2 * H, w.biasf + 2 * H, ctot, n, pts, w.st, cw->W[3], w.acc6,
-                             w.range_flag, num_sms, s);
-    if (rc) return rc;
-    return cnf_tc::enqueue_last_finish(w.acc6, e, n, pts, w.gate + 3 * H, w.biasf + 3 * H, ctot, reverse, w.st,
-                                       w.kbuf + (size_t)stage * n, s);
-  } else {
+    const int n_tiles = (n + 63) / 64;
+    // Optional (CASPR_CNF_PIPELINE_HALVES=1): measured on B200 at 163 840 points the decode span drops from 41.1 to
+    // 38.8 ms, but kernels of the two streams then queue behind each other, which makes the per-kernel CUDA-event
+    // durations (bench.py's roofline) meaningless; off by default.
+    const char* env = getenv("CASPR_CNF_PIPELINE_HALVES");
+    const bool want_split = env && env[0] == '1';
+    SideStream dummy;
+    SideStream& ss = want_split ? side_stream() : dummy;
+    const bool split = want_split && ss.ok && n_tiles >= 2 * num_sms;       // each half keeps every SM busy
+    const int pt_split = split ? (n_tiles / 2) * 64 : n;
+    if (split) {
+      if (cudaEventRecord(ss.fork, s) != cudaSuccess || cudaStreamWaitEvent(ss.stream, ss.fork, 0) != cudaSuccess)
+        return CASPR_ELAUNCH;
+    }
+    for (int stage = stage_first; stage <= stage_last; ++stage) {
+      int rc = enqueue_feval_tc_range(w, cw, e, frames, pts, stage, reverse, plan, num_sms, 0, pt_split, s);
+      if (rc) return rc;
+      if (split) {
+        rc = enqueue_feval_tc_range(w, cw, e, frames, pts, stage, reverse, plan, num_sms, pt_split, n, ss.stream);
+        if (rc) return rc;
+      }
+    }
+    if (split) {
+      if (cudaEventRecord(ss.join, ss.stream) != cudaSuccess || cudaStreamWaitEvent(s, ss.join, 0) != cudaSuccess)
+        return CASPR_ELAUNCH;
+    }
+    return CASPR_OK;
+  }
+  for (int stage = stage_first; stage <= stage_last; ++stage) {
+    const float* gate = w.gate + (size_t)stage * frames * ctot;
+    const float* biasf = w.biasf + (size_t)stage * frames * ctot;
     CASPR_COUNT(); cnf_layer0_kernel<<<blocks_for(n, 8, 148 * 16), 256, 0, s>>>(
-        w.y0, w.kbuf, (size_t)n, e, cw->W[0], H, n, pts, stage, w.gate, w.biasf, ctot, w.st, w.Ha, w.Va);
+        w.y0, w.kbuf, (size_t)n, e, cw->W[0], H, n, pts, stage, gate, biasf, ctot, w.st, w.Ha, w.Va);
     dim3 grid(ceil_div(n, kMidBM), H / kMidBN);
     caspr_prof_begin(CASPR_PROF_CNF_MID_SIMT, s);
-    CASPR_COUNT(); cnf_mid_layer_kernel<<<grid, 256, 0, s>>>(w.Ha, w.Va, cw->W[1], H, n, pts, w.gate + H, w.biasf + H,
+    CASPR_COUNT(); cnf_mid_layer_kernel<<<grid, 256, 0, s>>>(w.Ha, w.Va, cw->W[1], H, n, pts, gate + H, biasf + H,
                                               ctot, w.st, w.Hb, w.Vb);
     caspr_prof_end(CASPR_PROF_CNF_MID_SIMT, s);
     caspr_prof_begin(CASPR_PROF_CNF_MID_SIMT, s);
-    CASPR_COUNT(); cnf_mid_layer_kernel<<<grid, 256, 0, s>>>(w.Hb, w.Vb, cw->W[2], H, n, pts, w.gate + 2 * H,
-                                              w.biasf + 2 * H, ctot, w.st, w.Ha, w.Va);
+    CASPR_COUNT(); cnf_mid_layer_kernel<<<grid, 256, 0, s>>>(w.Hb, w.Vb, cw->W[2], H, n, pts, gate + 2 * H,
+                                              biasf + 2 * H, ctot, w.st, w.Ha, w.Va);
     caspr_prof_end(CASPR_PROF_CNF_MID_SIMT, s);
+    CASPR_COUNT(); cnf_last_layer_kernel<<<blocks_for(n, 8, 148 * 16), 256, 0, s>>>(
+        w.Ha, w.Va, cw->W[3], H, n, pts, e, gate + 3 * H, biasf + 3 * H, ctot, reverse, w.st,
+        w.kbuf + (size_t)stage * n);
+    CASPR_CHECK_LAUNCH();
   }
-  CASPR_COUNT(); cnf_last_layer_kernel<<<blocks_for(n, 8, 148 * 16), 256, 0, s>>>(
-      w.Ha, w.Va, cw->W[3], H, n, pts, e, w.gate + 3 * H, w.biasf + 3 * H, ctot, reverse, w.st,
-      w.kbuf + (size_t)stage * n);
-  CASPR_CHECK_LAUNCH();
   return CASPR_OK;
 }
 
@@ -820,7 +889,7 @@ extern "C" int caspr_cnf_flow(const float* x_in, const float* logp_in, const flo
       return CASPR_ELAUNCH;
     if (cudaStreamSynchronize(s) != cudaSuccess) return CASPR_ELAUNCH;   // h0 is a stack object
   }
-  rc = enqueue_feval(w, cw, e, frames, pts, 0, reverse, engine, &plan, num_sms, s);
+  rc = enqueue_stages(w, cw, e, frames, pts, 0, 0, reverse, engine, &plan, num_sms, s);
   if (rc) return rc;
   CASPR_COUNT(); cnf_init_norm_kernel<<<eb, 256, 0, s>>>(w.y0, w.kbuf, n, rtol, atol, w.st);
   CASPR_COUNT(); cnf_init_controller_kernel<<<1, 1, 0, s>>>(w.st, n, t_start, t_stop);
@@ -836,10 +905,8 @@ extern "C" int caspr_cnf_flow(const float* x_in, const float* logp_in, const flo
   CnfState hst;
   for (;;) {
     for (int b = 0; b < kBatch; ++b, ++step_id) {
-      for (int stage = 1; stage <= 6; ++stage) {
-        rc = enqueue_feval(w, cw, e, frames, pts, stage, reverse, engine, &plan, num_sms, s);
-        if (rc) return rc;
-      }
+      rc = enqueue_stages(w, cw, e, frames, pts, 1, 6, reverse, engine, &plan, num_sms, s);
+      if (rc) return rc;
       CASPR_COUNT(); cnf_error_kernel<<<eb, 256, 0, s>>>(w.y0, w.kbuf, (size_t)n, n, rtol, atol, w.st, w.y1);
       CASPR_COUNT(); cnf_controller_kernel<<<1, 1, 0, s>>>(w.st, n, step_id);
       CASPR_COUNT(); cnf_finalize_kernel<<<eb, 256, 0, s>>>(w.y0, w.kbuf, (size_t)n, w.y1, n, step_id, w.st, post, reverse,
@@ -896,7 +963,7 @@ extern "C" int caspr_cnf_feval(const float* y, const float* e, const float* ctx,
   MbnDev none = load_mbn(nullptr, nullptr);
   CASPR_COUNT(); cnf_init_state_kernel<<<ceil_div(n, 256), 256, 0, s>>>(y, nullptr, n, none, 0, w.y0);
   CASPR_CHECK_LAUNCH();
-  rc = enqueue_feval(w, cw, e, frames, pts, 0, 0, engine, &plan, num_sms, s);
+  rc = enqueue_stages(w, cw, e, frames, pts, 0, 0, 0, engine, &plan, num_sms, s);
   if (rc) return rc;
   // unpack k0 -> dy (n,3), neg_div (n)
   if (cudaMemcpy2DAsync(dy, 12, w.kbuf, 16, 12, n, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return CASPR_ELAUNCH;

@@ -272,25 +272,20 @@ __global__ void fill_col_scale_kernel(const float* __restrict__ scales, int H, i
 // outputs are written as scaled fp16 hi/lo planes in the tile/quadrant row order described above.
 __global__ void __launch_bounds__(256)
 cnf_tc_layer0_kernel(const float4* __restrict__ y0, const float4* __restrict__ kbuf, size_t kstride,
-                     const float* __restrict__ e, const float* __restrict__ W0, int n, int P, int stage,
+                     const float* __restrict__ e, const float* __restrict__ W0, int pt0, int n, int P, int stage,
                      const float* __restrict__ gate, const float* __restrict__ biasf, int ld_hyper,
                      const CnfState* __restrict__ st, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
                      int* __restrict__ range_flag) {
   if (st->done) return;
   constexpr int H = 512;
-  // W0 transposed to [3][H] with one pad word per 8 channels: lane L reads channels 8L..8L+7 (and
-  // 256+8L..), the padding spreads the 32 lanes over all banks
-  __shared__ float sW[3][H + H / 8];
-  for (int i = threadIdx.x; i < H * 3; i += blockDim.x) {
-    const int j = i / 3, c = i - 3 * j;
-    sW[c][j + (j >> 3)] = W0[i];
-  }
-  __syncthreads();
+  // no shared memory: the kernel must be able to co-reside with the persistent GEMM CTAs (which own almost all
+  // of it) when the two halves of the point set are pipelined on two streams; the 6 KB of layer-0 weights are
+  // read through L1, 24 contiguous floats (8 channels x 3) per lane and channel set
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const float dt = (float)st->dt;
   float range_max = 0.f;
-  for (int pt = blockIdx.x * wpb + (threadIdx.x >> 5); pt < n; pt += gridDim.x * wpb) {
+  for (int pt = pt0 + blockIdx.x * wpb + (threadIdx.x >> 5); pt < n; pt += gridDim.x * wpb) {      // points [pt0, n)
     float4 y = y0[pt];
     float ys[3] = {y.x, y.y, y.z};
     if (stage > 0) {
@@ -327,6 +322,12 @@ cnf_tc_layer0_kernel(const float4* __restrict__ y0, const float4* __restrict__ k
         g[4 * j4] = a.x; g[4 * j4 + 1] = a.y; g[4 * j4 + 2] = a.z; g[4 * j4 + 3] = a.w;
         bf[4 * j4] = b.x; bf[4 * j4 + 1] = b.y; bf[4 * j4 + 2] = b.z; bf[4 * j4 + 3] = b.w;
       }
+      float wl[24];
+#pragma unroll
+      for (int j4 = 0; j4 < 6; ++j4) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(W0 + 3 * j0) + j4);
+        wl[4 * j4] = w4.x; wl[4 * j4 + 1] = w4.y; wl[4 * j4 + 2] = w4.z; wl[4 * j4 + 3] = w4.w;
+      }
       uint32_t hh[4], hl[4], vh[4], vl[4];
 #pragma unroll
       for (int j2 = 0; j2 < 4; ++j2) {
@@ -334,8 +335,7 @@ cnf_tc_layer0_kernel(const float4* __restrict__ y0, const float4* __restrict__ k
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int jj = j2 * 2 + u;
-          const int ji = j0 + (j0 >> 3) + jj;            // padded index of channel j0 + jj
-          const float w0 = sW[0][ji], w1 = sW[1][ji], w2 = sW[2][ji];
+          const float w0 = wl[3 * jj], w1 = wl[3 * jj + 1], w2 = wl[3 * jj + 2];
           const float a = fmaf(w2, ys[2], fmaf(w1, ys[1], w0 * ys[0]));
           const float ta = fmaf(w2, e2, fmaf(w1, e1, w0 * e0));
           const float pre = fmaf(a, g[jj], bf[jj]);
@@ -363,11 +363,11 @@ cnf_tc_layer0_kernel(const float4* __restrict__ y0, const float4* __restrict__ k
 // Output layer, second half: k = sign * (W3.h * gate + biasf, -(e . (gate * W3.v))) from the per-point sums
 // the last tensor-core layer accumulated; the sums are cleared for the next evaluation.
 __global__ void __launch_bounds__(256)
-cnf_tc_last_finish_kernel(float* __restrict__ acc6, const float* __restrict__ e, int n, int P,
+cnf_tc_last_finish_kernel(float* __restrict__ acc6, const float* __restrict__ e, int pt0, int n, int P,
                           const float* __restrict__ gate, const float* __restrict__ biasf, int ld_hyper, int reverse,
                           const CnfState* __restrict__ st, float4* __restrict__ kout) {
   if (st->done) return;
-  const int pt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pt = pt0 + blockIdx.x * blockDim.x + threadIdx.x;          // points [pt0, n)
   if (pt >= n) return;
   float4* a4 = reinterpret_cast<float4*>(acc6 + (size_t)pt * 8);
   const float4 lo = a4[0], hi = a4[1];
@@ -440,19 +440,20 @@ int make_plan(Plan& plan, const Weights& w, __half* a_hi, __half* a_lo, __half* 
 }
 
 int enqueue_layer0(const Plan& plan, const float4* y0, const float4* kbuf, size_t kstride, const float* e,
-                   const float* W0, int n, int P, int stage, const float* gate, const float* biasf, int ld_hyper,
-                   const CnfState* st, int* range_flag, cudaStream_t s) {
-  int blocks = (n + 7) / 8;
+                   const float* W0, int pt0, int n, int P, int stage, const float* gate, const float* biasf,
+                   int ld_hyper, const CnfState* st, int* range_flag, cudaStream_t s) {
+  int blocks = (n - pt0 + 7) / 8;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  CASPR_COUNT(); cnf_tc_layer0_kernel<<<blocks, 256, 0, s>>>(y0, kbuf, kstride, e, W0, n, P, stage, gate, biasf,
+  CASPR_COUNT(); cnf_tc_layer0_kernel<<<blocks, 256, 0, s>>>(y0, kbuf, kstride, e, W0, pt0, n, P, stage, gate, biasf,
                                                              ld_hyper, st, plan.a_hi, plan.a_lo, range_flag);
   CASPR_CHECK_LAUNCH();
   return CASPR_OK;
 }
 
-int enqueue_mid(const Plan& plan, int layer, const float* gate, const float* biasf, int ld_hyper, int n, int P,
-                const CnfState* st, const float* W3, float* acc6, int* range_flag, int num_sms, cudaStream_t s) {
-  int grid = plan.n_tiles * 2;
+int enqueue_mid(const Plan& plan, int layer, int m_tile0, int m_tiles, const float* gate, const float* biasf,
+                int ld_hyper, int n, int P, const CnfState* st, const float* W3, float* acc6, int* range_flag,
+                int num_sms, cudaStream_t s) {
+  int grid = m_tiles * 2;
   if (grid > num_sms) grid = num_sms;
   const int* skip = &st->done;
   caspr_prof_begin(CASPR_PROF_CNF_FUSED_TC, s);
@@ -463,24 +464,24 @@ int enqueue_mid(const Plan& plan, int layer, const float* gate, const float* bia
     epi.out_hi = plan.b_hi; epi.out_lo = plan.b_lo; epi.range_flag = range_flag;
     tcg::gemm_fp16x3_kernel<CnfEpilogue<false>><<<grid, tcg::kThreads, tcg::kSmemBytes, s>>>(
         plan.tm_act[0][0], plan.tm_act[0][1], plan.tm_w[0][0], plan.tm_w[0][1], plan.tm_act[1][0], plan.tm_act[1][1],
-        plan.n_tiles, 2, 512 / tcg::kBK, skip, epi);
+        m_tile0, m_tiles, 2, 512 / tcg::kBK, skip, epi);
   } else {
     CnfEpilogue<true> epi{};
     epi.gate = gate; epi.biasf = biasf; epi.ld_hyper = ld_hyper; epi.n = n; epi.P = P;
     epi.W3 = W3; epi.acc6 = acc6; epi.range_flag = range_flag; epi.pending = false;
     tcg::gemm_fp16x3_kernel<CnfEpilogue<true>><<<grid, tcg::kThreads, tcg::kSmemBytes, s>>>(
         plan.tm_act[1][0], plan.tm_act[1][1], plan.tm_w[1][0], plan.tm_w[1][1], plan.tm_act[1][0], plan.tm_act[1][1],
-        plan.n_tiles, 2, 512 / tcg::kBK, skip, epi);
+        m_tile0, m_tiles, 2, 512 / tcg::kBK, skip, epi);
   }
   caspr_prof_end(CASPR_PROF_CNF_FUSED_TC, s);
   CASPR_CHECK_LAUNCH();
   return CASPR_OK;
 }
 
-int enqueue_last_finish(float* acc6, const float* e, int n, int P, const float* gate, const float* biasf,
+int enqueue_last_finish(float* acc6, const float* e, int pt0, int n, int P, const float* gate, const float* biasf,
                         int ld_hyper, int reverse, const CnfState* st, float4* kout, cudaStream_t s) {
-  CASPR_COUNT(); cnf_tc_last_finish_kernel<<<ceil_div(n, 256), 256, 0, s>>>(acc6, e, n, P, gate, biasf, ld_hyper,
-                                                                            reverse, st, kout);
+  CASPR_COUNT(); cnf_tc_last_finish_kernel<<<ceil_div(n - pt0, 256), 256, 0, s>>>(acc6, e, pt0, n, P, gate, biasf,
+                                                                                  ld_hyper, reverse, st, kout);
   CASPR_CHECK_LAUNCH();
   return CASPR_OK;
 }

@@ -28,13 +28,16 @@ size_t weights_workspace_bytes();
 int prepare_weights(const float* W1, const float* W2, const Weights& out, cudaStream_t s);
 int fill_col_scale(const Weights& w, int ctot, float* col_scale, cudaStream_t s);
 int make_plan(Plan& plan, const Weights& w, __half* a_hi, __half* a_lo, __half* b_hi, __half* b_lo, int n);
+// The three stages below work on the point range [pt0, n_end) (tile aligned: pt0 % 64 == 0) resp. the row tiles
+// [m_tile0, m_tile0 + m_tiles), so that two halves of the point set can be pipelined on two streams.
 int enqueue_layer0(const Plan& plan, const float4* y0, const float4* kbuf, size_t kstride, const float* e,
-                   const float* W0, int n, int P, int stage, const float* gate, const float* biasf, int ld_hyper,
-                   const CnfState* st, int* range_flag, cudaStream_t s);
+                   const float* W0, int pt0, int n_end, int P, int stage, const float* gate, const float* biasf,
+                   int ld_hyper, const CnfState* st, int* range_flag, cudaStream_t s);
 // layer 0: planes A -> planes B;  layer 1: planes B -> fused output layer (W3 (3,512)) accumulated into acc6 [n][8]
-int enqueue_mid(const Plan& plan, int layer, const float* gate, const float* biasf, int ld_hyper, int n, int P,
-                const CnfState* st, const float* W3, float* acc6, int* range_flag, int num_sms, cudaStream_t s);
-int enqueue_last_finish(float* acc6, const float* e, int n, int P, const float* gate, const float* biasf,
+int enqueue_mid(const Plan& plan, int layer, int m_tile0, int m_tiles, const float* gate, const float* biasf,
+                int ld_hyper, int n, int P, const CnfState* st, const float* W3, float* acc6, int* range_flag,
+                int num_sms, cudaStream_t s);
+int enqueue_last_finish(float* acc6, const float* e, int pt0, int n_end, int P, const float* gate, const float* biasf,
                         int ld_hyper, int reverse, const CnfState* st, float4* kout, cudaStream_t s);
 
 }  // namespace cnf_tc

@@ -366,7 +366,7 @@ extern "C" int caspr_linear_tc(const float* X, int ldx, const float* W, int ldw,
   if (grid > num_sms) grid = num_sms;
   caspr_prof_begin(CASPR_PROF_LINEAR, s);
   CASPR_COUNT(); tcg::gemm_fp16x3_kernel<LinearEpilogue><<<grid, tcg::kThreads, tcg::kSmemBytes, s>>>(
-      tm_xhi, tm_xlo, tm_whi, tm_wlo, tm_xhi, tm_xlo, m_tiles, n_tiles, l.k_pad / kBK, nullptr, epi);
+      tm_xhi, tm_xlo, tm_whi, tm_wlo, tm_xhi, tm_xlo, 0, m_tiles, n_tiles, l.k_pad / kBK, nullptr, epi);
   caspr_prof_end(CASPR_PROF_LINEAR, s);
   CASPR_CHECK_LAUNCH();
   return CASPR_OK;

@@ -3,6 +3,8 @@
 // encoder's dense layers (gemm_tc.cu).
 //
 //   D[128 x 256 tile] = sum_k  A[128 x K] . W[256 x K]^T       (both operands K-major fp16 planes)
+// for the row tiles m_tile0 .. m_tile0 + m_tiles - 1 (a launch may cover a sub-range of the rows so that
+// independent row ranges can be pipelined on different streams).
 //
 // One CTA per SM, 192 threads:
 //   warp 0    TMA producer : per 64-wide k-chunk the A_hi, A_lo (128x64) and W_hi, W_lo (256x64)
@@ -39,7 +41,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_fp16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                    const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
-                   int m_tiles, int n_tiles, int k_chunks, const int* __restrict__ skip_flag, Epilogue epi) {
+                   int m_tile0, int m_tiles, int n_tiles, int k_chunks, const int* __restrict__ skip_flag,
+                   Epilogue epi) {
   if (skip_flag && *skip_flag) return;       // device-side "solve finished" flag (CNF solver)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -80,7 +83,8 @@ gemm_fp16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
+        const int m_local = tile / n_tiles, n_tile = tile - m_local * n_tiles;
+        const int m_tile = m_tile0 + m_local;
         for (int kc = 0; kc < k_chunks; ++kc) {
           tc::mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sb = smem + stage * kStageBytes;
@@ -131,7 +135,8 @@ gemm_fp16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     epi.setup(staging, &tm_o_hi, &tm_o_lo, (int)threadIdx.x - 64);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
+      const int m_local = tile / n_tiles, n_tile = tile - m_local * n_tiles;
+      const int m_tile = m_tile0 + m_local;
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       epi.tile_begin(m_tile, n_tile, q, lane);

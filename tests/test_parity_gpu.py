@@ -504,6 +504,24 @@ def test_flow_round_trip(case, engine):
     assert torch.isfinite(dlogp).all()
 
 
+def test_pipelined_halves_match_single_stream(case, ops):
+    """CASPR_CNF_PIPELINE_HALVES=1 runs the two halves of the point set on two streams; per-point arithmetic is
+    unchanged, so the result is bit-identical to the single-stream schedule."""
+    _, _, model, _, _, _ = case
+    g = torch.Generator().manual_seed(12)
+    F, P = 10, 2048                                   # 320 tiles >= 2 x 148: the split is taken
+    ctx = (0.5 * torch.randn(F, 1600, generator=g)).to(DEV)
+    y = torch.randn(F, P, 3, generator=g).to(DEV)
+    e = torch.randn(F, P, 3, generator=g).to(DEV)
+    x1 = model.point_cnf(y, ctx, reverse=True, e=e)
+    os.environ['CASPR_CNF_PIPELINE_HALVES'] = '1'
+    try:
+        x2 = model.point_cnf(y, ctx, reverse=True, e=e)
+    finally:
+        os.environ.pop('CASPR_CNF_PIPELINE_HALVES', None)
+    assert torch.equal(x1, x2)
+
+
 def test_solver_failure_is_reported(case, ops, engine):
     """Non-finite inputs surface as the solver's status (torchdiffeq asserts), not as silent garbage."""
     from caspr_b200._lib import CasprError
