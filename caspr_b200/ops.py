@@ -423,6 +423,36 @@ def cnf_feval(y, e, ctx, pack, t, engine=CNF_SIMT_FP32):
     return dy, nd
 
 
+def cnf_param_count(pack):
+    return int(lib.caspr_cnf_param_count(pack.struct.hidden, pack.struct.ctx_dim))
+
+
+def cnf_adjoint(x1, logp1, gx1, glogp1, e, ctx, pack, end_time, rtol=1e-5, atol=1e-5):
+    """Adjoint backward of the CNF block (forward direction).  x1 (F,P,3), logp1 (F,P): block outputs at t1;
+    gx1, glogp1: their gradients.  Returns gx0 (F,P,3), glogp0 (F,P), gctx (F,ctx), gparams (flat, ODEfunc
+    parameters() order), gtimes (2,), info list, status."""
+    x1, gx1, e, ctx = [_f32(t, n).contiguous() for t, n in ((x1, 'x1'), (gx1, 'gx1'), (e, 'e'), (ctx, 'ctx'))]
+    logp1, glogp1 = _f32(logp1, 'logp1').contiguous(), _f32(glogp1, 'glogp1').contiguous()
+    F, P, _ = x1.shape
+    dev = x1.device
+    H, C = pack.struct.hidden, pack.struct.ctx_dim
+    gx0 = torch.empty_like(x1)
+    glogp0 = torch.empty(F, P, dtype=torch.float32, device=dev)
+    gctx = torch.empty(F, C, dtype=torch.float32, device=dev)
+    gparams = torch.empty(cnf_param_count(pack), dtype=torch.float32, device=dev)
+    gtimes = torch.zeros(2, dtype=torch.float32, device=dev)
+    info = torch.zeros(8, dtype=torch.int32, device=dev)
+    h_info = (ctypes.c_int32 * 8)()
+    ws_bytes = lib.caspr_cnf_adjoint_workspace_bytes(F, P, H, C)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _count('cnf_adjoint')
+    rc = lib.caspr_cnf_adjoint(_p(x1), _p(logp1), _p(gx1), _p(glogp1), _p(e), _p(ctx), F, P,
+                               ctypes.byref(pack.struct), float(end_time), float(rtol), float(atol),
+                               _p(gx0), _p(glogp0), _p(gctx), _p(gparams), _p(gtimes), _p(info), h_info,
+                               _p(ws), ws_bytes, _stream())
+    return gx0, glogp0, gctx, gparams, gtimes, list(h_info), rc
+
+
 def chamfer(a, b):
     """Squared-NN distances both ways: a (B,P,3), b (B,Q,3) -> d_ab (B,P), d_ba (B,Q)."""
     a, b = _f32(a, 'a').contiguous(), _f32(b, 'b').contiguous()

@@ -238,6 +238,27 @@ int caspr_cnf_feval(const float* y, const float* e, const float* ctx, int frames
                     const caspr_cnf_weights* w, float t, int engine,
                     float* dy, float* neg_div, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------ CNF training (adjoint backward)
+ * Replaces torchdiffeq 0.0.1's OdeintAdjointMethod.backward for the CNF block (call site cnf.py:102-111) and the
+ * autograd VJP through ODEfunc / divergence_approx / ODEnet (odefunc.py:13-31,98-105,119-142): integrates the
+ * augmented state (x, logp, ctx, adj_x, adj_logp, adj_ctx, adj_t, adj_params) from t1 = end_time back to 0 with
+ * dopri5; step control sees (x, logp, ctx) only (three-entry tolerance lists, cnf.py:80-81), the initial-step
+ * heuristic sees all eight tensors.
+ *   x1 (frames,pts,3), logp1 (frames,pts): the block's outputs at t1;  gx1, glogp1: dL/d(x1), dL/d(logp1);
+ *   e, ctx, w, rtol, atol: as in the forward caspr_cnf_flow call (MovingBatchNorm layers are NOT part of this call);
+ *   gx0 (frames,pts,3), glogp0 (frames,pts), gctx (frames,ctx_dim): dL/d(x0), dL/d(logp0), dL/d(ctx);
+ *   gparams: caspr_cnf_param_count(hidden, ctx_dim) floats in ODEfunc.parameters() order — per layer
+ *            _layer.weight, _layer.bias, _hyper_bias.weight, _hyper_gate.weight, _hyper_gate.bias;
+ *   gtimes (2 floats, device): dL/dt0, dL/dt1 (dL/d sqrt_end_time = 2 sqrt_end_time gtimes[1], cnf.py:89-91).
+ * Synchronises `stream` once per attempted step (polls the device-side controller). */
+size_t caspr_cnf_param_count(int hidden, int ctx_dim);
+size_t caspr_cnf_adjoint_workspace_bytes(int frames, int pts, int hidden, int ctx_dim);
+int caspr_cnf_adjoint(const float* x1, const float* logp1, const float* gx1, const float* glogp1,
+                      const float* e, const float* ctx, int frames, int pts,
+                      const caspr_cnf_weights* w, float end_time, float rtol, float atol,
+                      float* gx0, float* glogp0, float* gctx, float* gparams, float* gtimes,
+                      int32_t* info, int32_t* h_info, void* workspace, size_t workspace_bytes, void* stream);
+
 /* -------------------------------------------------------------------- metric
  * Symmetric squared-NN Chamfer distance (reference utils/evaluations.py:40-43 via
  * tk3dv ChamferDistance): a (B,P,3), b (B,Q,3) -> d_ab (B,P) min sq dist a->b, d_ba (B,Q). */
