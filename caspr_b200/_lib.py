@@ -82,6 +82,11 @@ SIGNATURES = {
     'caspr_cnf_adjoint_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
     'caspr_cnf_adjoint': (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, POINTER(CnfWeights), c_float, c_float,
                                   c_float, _P, _P, _P, _P, _P, _P, POINTER(c_int32), _P, c_size_t, _P]),
+    'caspr_latent_ode_param_count': (c_size_t, [c_int, c_int]),
+    'caspr_latent_ode_adjoint_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'caspr_latent_ode_adjoint': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P,
+                                         POINTER(c_double), c_int, c_float, c_float, _P, _P, _P,
+                                         POINTER(c_int32), _P, c_size_t, _P]),
     'caspr_chamfer': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P]),
 }
 

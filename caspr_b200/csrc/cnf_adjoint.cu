@@ -16,6 +16,7 @@
 //              then the hyper-network gradients (weights, context, time).
 // Everything is exact fp32 SIMT in this version.
 #include "cnf_kernels.cuh"
+#include "rk_flat.cuh"
 
 namespace {
 
@@ -476,36 +477,6 @@ adj_hyper_wgrad_kernel(const float* __restrict__ Ghat, const float* __restrict__
   }
 }
 
-// ------------------------------------------------------------------ flat-state dopri5 pieces
-// Accepted step: y0 <- y0 + sum_j dt*c_sol[j] k_j and FSAL shift k_0 <- k_6; on the step that passes t_end the
-// dense-output value at t_end goes to `out` instead (torchdiffeq _interp_fit / _interp_evaluate).
-__global__ void __launch_bounds__(256)
-adj_flat_finalize_kernel(float* __restrict__ y0, float* __restrict__ k, size_t kstride, size_t nelem, int step_id,
-                         const CnfState* __restrict__ st, float* __restrict__ out) {
-  if (st->fin_step != step_id || !st->accept) return;
-  const int finished = st->done && st->status == CASPR_OK;
-  const float dt = st->dt_prev;
-  float xq = 0.f;
-  if (finished) {
-    const float t0f = (float)st->t_prev, t1f = (float)st->t, tf = (float)st->t_end;
-    xq = __fdiv_rn(__fsub_rn(tf, t0f), __fsub_rn(t1f, t0f));
-  }
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nelem; i += (size_t)gridDim.x * blockDim.x) {
-    float kc[7];
-#pragma unroll
-    for (int j = 0; j < 7; ++j) kc[j] = k[(size_t)j * kstride + i];
-    const float y = y0[i];
-    const float y1 = dopri5::stage_combine(y, dt, kc, 5);
-    if (finished) {
-      const float ymid = __fadd_rn(y, dopri5::weighted7(dt, dopri5::kCMid, kc));
-      out[i] = dopri5::interp_eval(y, y1, ymid, kc[0], kc[6], dt, xq);
-    } else {
-      y0[i] = y1;
-      k[i] = kc[6];
-    }
-  }
-}
-
 // sum over a flat range of (k0 / (atol + |y0| rtol))^2 -> dst (double), for the initial-step heuristic
 __global__ void __launch_bounds__(256)
 adj_sumsq_kernel(const float* __restrict__ y0, const float* __restrict__ k0, size_t nelem, float rtol, float atol,
@@ -858,9 +829,9 @@ extern "C" int caspr_cnf_adjoint(const float* x1, const float* logp1, const floa
     CASPR_COUNT(); cnf_controller_kernel<<<1, 1, 0, s>>>(b.st, n, step_id);
     CASPR_COUNT(); cnf_finalize_kernel<<<eb, 256, 0, s>>>(b.y0, b.kbuf, (size_t)n, b.y1, n, step_id, b.st, post, 1, 1,
                                                          w.scratch_x, w.scratch_x + (size_t)3 * n);
-    CASPR_COUNT(); adj_flat_finalize_kernel<<<fb4, 256, 0, s>>>((float*)w.adj0, (float*)w.kadj, (size_t)n * 4,
+    CASPR_COUNT(); flat_finalize_kernel<<<fb4, 256, 0, s>>>((float*)w.adj0, (float*)w.kadj, (size_t)n * 4,
                                                                (size_t)n * 4, step_id, b.st, (float*)w.adj_out);
-    CASPR_COUNT(); adj_flat_finalize_kernel<<<fbu, 256, 0, s>>>(w.U0, w.kU, w.nu, w.nu, step_id, b.st, w.Uout);
+    CASPR_COUNT(); flat_finalize_kernel<<<fbu, 256, 0, s>>>(w.U0, w.kU, w.nu, w.nu, step_id, b.st, w.Uout);
     CASPR_CHECK_LAUNCH();
     ++step_id;
     if (cudaMemcpyAsync(&hst, b.st, sizeof(CnfState), cudaMemcpyDeviceToHost, s) != cudaSuccess) return CASPR_ELAUNCH;

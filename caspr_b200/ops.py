@@ -359,6 +359,29 @@ def latent_ode_solve(z0, weights, biases, times, rtol, atol):
     return out, list(h_info), rc
 
 
+def latent_ode_adjoint(zs, gzs, weights, biases, times, rtol, atol):
+    """Adjoint backward of latent_ode_solve: zs, gzs (nT,B,D) -> gz0 (B,D), gparams (flat: W0,b0,...,W3,b3)."""
+    zs, gzs = _f32(zs, 'zs').contiguous(), _f32(gzs, 'gzs').contiguous()
+    nT, B, D = zs.shape
+    H = weights[0].shape[0]
+    tl = [float(t) for t in times]
+    assert len(tl) == nT
+    h_times = (ctypes.c_double * nT)(*tl)
+    gz0 = torch.empty(B, D, dtype=torch.float32, device=zs.device)
+    gparams = torch.empty(int(lib.caspr_latent_ode_param_count(D, H)), dtype=torch.float32, device=zs.device)
+    info = torch.zeros(8, dtype=torch.int32, device=zs.device)
+    h_info = (ctypes.c_int32 * 8)()
+    ws_bytes = lib.caspr_latent_ode_adjoint_workspace_bytes(B, D, H)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=zs.device)
+    w = [x.detach().contiguous() for x in weights]
+    b = [x.detach().contiguous() for x in biases]
+    _count('latent_ode_adjoint')
+    rc = lib.caspr_latent_ode_adjoint(_p(zs), _p(gzs), B, D, H, _p(w[0]), _p(b[0]), _p(w[1]), _p(b[1]), _p(w[2]),
+                                      _p(b[2]), _p(w[3]), _p(b[3]), h_times, nT, float(rtol), float(atol),
+                                      _p(gz0), _p(gparams), _p(info), h_info, _p(ws), ws_bytes, _stream())
+    return gz0, gparams, list(h_info), rc
+
+
 # -------------------------------------------------------------------------------------- CNF
 class CnfWeightPack(object):
     """Keeps the tensors referenced by a caspr_cnf_weights struct alive."""

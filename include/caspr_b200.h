@@ -259,6 +259,22 @@ int caspr_cnf_adjoint(const float* x1, const float* logp1, const float* gx1, con
                       float* gx0, float* glogp0, float* gctx, float* gparams, float* gtimes,
                       int32_t* info, int32_t* h_info, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ----------------------------------------------------- latent ODE training (adjoint backward)
+ * Replaces OdeintAdjointMethod.backward for latent_ode_model.py:98 and the VJP through DynamicsNet
+ * (latent_ode_model.py:129-147).  zs (nT,B,D): the forward solution (caspr_latent_ode_solve's `out`);
+ * gzs (nT,B,D): dL/d(zs); h_times as in the forward call.  Returns gz0 (B,D) = dL/d(z0) and gparams:
+ * caspr_latent_ode_param_count(D,H) floats in DynamicsNet.parameters() order (W0,b0,W1,b1,W2,b2,W3,b3).
+ * Scalar tolerances: every augmented tensor (z, adj_z, adj_params) is under step control, one dopri5 solve per
+ * output interval, last to first.  Synchronises `stream` once per attempted step. */
+size_t caspr_latent_ode_param_count(int D, int H);
+size_t caspr_latent_ode_adjoint_workspace_bytes(int B, int D, int H);
+int caspr_latent_ode_adjoint(const float* zs, const float* gzs, int B, int D, int H,
+                             const float* W0, const float* b0, const float* W1, const float* b1,
+                             const float* W2, const float* b2, const float* W3, const float* b3,
+                             const double* h_times, int nT, float rtol, float atol,
+                             float* gz0, float* gparams, int32_t* info, int32_t* h_info,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* -------------------------------------------------------------------- metric
  * Symmetric squared-NN Chamfer distance (reference utils/evaluations.py:40-43 via
  * tk3dv ChamferDistance): a (B,P,3), b (B,Q,3) -> d_ab (B,P) min sq dist a->b, d_ba (B,Q). */
