@@ -6,7 +6,7 @@ every model call fails loudly.  Build it with ``python -m caspr_b200.build`` (or
 """
 import ctypes
 import os
-from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_size_t,
+from ctypes import (c_longlong, POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_size_t,
                     c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -87,6 +87,21 @@ SIGNATURES = {
     'caspr_latent_ode_adjoint': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P,
                                          POINTER(c_double), c_int, c_float, c_float, _P, _P, _P,
                                          POINTER(c_int32), _P, c_size_t, _P]),
+    'caspr_gn_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'caspr_gn_moments': (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, c_size_t, _P]),
+    'caspr_gn_apply': (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, _P]),
+    'caspr_rowmax_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'caspr_rowmax': (c_int, [_P, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_size_t, _P]),
+    'caspr_gn_backward': (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P,
+                                  c_int, _P, c_int, _P, _P, _P, c_size_t, _P]),
+    'caspr_linear_wgrad_workspace_bytes': (c_size_t, [c_longlong, c_int, c_int]),
+    'caspr_linear_wgrad': (c_int, [_P, c_int, _P, c_int, c_longlong, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    'caspr_colsum_workspace_bytes': (c_size_t, [c_longlong, c_int]),
+    'caspr_colsum': (c_int, [_P, c_int, c_longlong, c_int, _P, c_int, _P, c_size_t, _P]),
+    'caspr_group_points_bwd': (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P]),
+    'caspr_three_interp_bwd': (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, _P]),
+    'caspr_rows_update': (c_int, [_P, c_int, c_longlong, c_int, c_int, _P, c_int, _P, c_int, _P]),
+    'caspr_transpose': (c_int, [_P, c_int, c_int, _P, _P]),
     'caspr_chamfer': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P]),
 }
 

@@ -6,8 +6,7 @@ Drop-in mirror of reference caspr/models/caspr.py:22-308: identical constructor 
 (``encoder``, ``latent_ode``, ``point_cnf``) and therefore the identical 238-key state_dict.
 All heavy work runs in libcaspr_b200.so; this file only sequences the calls.
 
-Differences a caller can observe: inference only (the solvers run without autograd; training
-through the adjoint is not implemented yet), CUDA only, and two optional keyword arguments
+Differences a caller can observe: CUDA only, and two optional keyword arguments
 (``y`` and ``e``) to inject the base samples / Hutchinson noise for parity tests.
 """
 import numpy as np
@@ -44,9 +43,17 @@ class CaSPR(nn.Module):
         self.point_cnf = get_point_cnf(self.cnf_args)
 
     # ------------------------------------------------------------------------------ forward
-    @torch.no_grad()
     def forward(self, x, sample_points, aggregate_points=None, e=None):
-        """caspr.py:76-122: -> (nll (B,T,N), tnocs_l1 (B,T,N,4)) or (tnocs_l1,) when pretraining."""
+        """caspr.py:76-122: -> (nll (B,T,N), tnocs_l1 (B,T,N,4)) or (tnocs_l1,) when pretraining.
+
+        In training mode with autograd enabled the result is differentiable: ``loss.backward()``
+        (train_utils.py:173) runs the hand-written encoder backward and the CUDA adjoint solves."""
+        if not (self.training and torch.is_grad_enabled()):
+            with torch.no_grad():
+                return self._forward(x, sample_points, e)
+        return self._forward(x, sample_points, e)
+
+    def _forward(self, x, sample_points, e=None):
         z0, tnocs_pred = self.encode(x)
         B, H = z0.size()
         _, T, N, _ = sample_points.size()

@@ -162,6 +162,43 @@ class CNF(nn.Module):
         return self.odefunc._num_evals.item()
 
 
+class _CnfBlockFunction(torch.autograd.Function):
+    """odeint_adjoint for one CNF block in the forward direction (cnf.py:101-111): forward = caspr_cnf_flow without
+    the MovingBatchNorm layers, backward = caspr_cnf_adjoint (torchdiffeq 0.0.1's OdeintAdjointMethod.backward with the
+    VJP through ODEfunc, odefunc.py:119-142)."""
+
+    @staticmethod
+    def forward(ctx, x, logp, context, e, cnf, engine, sqrt_end_time, *params):
+        pack = cnf.weight_pack()
+        end_time = cnf.end_time()
+        x1, logp1, info, rc = ops.cnf_flow(x, logp, e, context, pack, None, None, end_time, False, cnf.rtol, cnf.atol,
+                                           engine)
+        cnf.odefunc._num_evals += float(info[1])
+        cnf.last_info = info
+        if rc != 0:
+            raise CasprError(rc, 'caspr_cnf_flow')
+        ctx.cnf, ctx.pack, ctx.end_time, ctx.params = cnf, pack, end_time, params
+        ctx.save_for_backward(x1, logp1, e, context, sqrt_end_time)
+        return x1, logp1
+
+    @staticmethod
+    def backward(ctx, gx1, glogp1):
+        x1, logp1, e, context, sqrt_end_time = ctx.saved_tensors
+        cnf = ctx.cnf
+        gx0, glogp0, gctx, gpar, gtimes, info, rc = ops.cnf_adjoint(
+            x1, logp1, gx1.contiguous(), glogp1.contiguous(), e, context, ctx.pack, ctx.end_time, cnf.rtol, cnf.atol)
+        cnf.last_adjoint_info = info
+        if rc != 0:
+            raise CasprError(rc, 'caspr_cnf_adjoint')
+        grads, off = [], 0
+        for p in ctx.params:
+            grads.append(gpar[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        # integration_times = [0, sqrt_end_time^2] (cnf.py:89-91)
+        g_sqrt = (2.0 * sqrt_end_time.detach() * gtimes[1]).reshape(sqrt_end_time.shape) if cnf.train_T else None
+        return (gx0, glogp0, gctx, None, None, None, g_sqrt) + tuple(grads)
+
+
 class SequentialFlow(nn.Module):
     """chain = [MovingBatchNorm1d, CNF x num_blocks, MovingBatchNorm1d] (flow.py:67-74)."""
 
@@ -190,6 +227,8 @@ class SequentialFlow(nn.Module):
         first_bn = mods[0] if isinstance(mods[0], MovingBatchNorm1d) else None
         last_bn = mods[-1] if isinstance(mods[-1], MovingBatchNorm1d) else None
         train_fwd = self.training and not reverse
+        if train_fwd and torch.is_grad_enabled():
+            return self._forward_train(x, context, logp, mods, e, logpx is not None)
         order = list(reversed(cnfs)) if reverse else cnfs
         for i, cnf in enumerate(order):
             is_first, is_last = i == 0, i == len(order) - 1
@@ -222,5 +261,29 @@ class SequentialFlow(nn.Module):
                     x, lp = post_bn(x, None, logp.unsqueeze(-1))
                     logp = lp.squeeze(-1)
         if logpx is None:
+            return x
+        return x, logp.view(F, P, 1)
+
+    def _forward_train(self, x, context, logp, mods, e, want_logp):
+        """Differentiable forward pass of the chain (training, cnf.py:33-48 in chain order): the MovingBatchNorm layers
+        are elementwise torch code, every CNF block is a ``_CnfBlockFunction`` (CUDA solve + CUDA adjoint)."""
+        F, P, _ = x.shape
+        if logp is None:
+            logp = torch.zeros(F, P, dtype=torch.float32, device=x.device)            # cnf.py:71-74
+        for m in mods:
+            if isinstance(m, MovingBatchNorm1d):
+                x, lp = m(x, None, logp.unsqueeze(-1))
+                logp = lp.squeeze(-1)
+                continue
+            m.odefunc.before_odeint(e)
+            noise = e if e is not None else torch.randn_like(x)
+            params = []
+            for l in m.odefunc.diffeq.layers:       # ODEfunc.parameters() order (diffeq_layers.py:79-81)
+                params += [l._layer.weight, l._layer.bias, l._hyper_bias.weight, l._hyper_gate.weight,
+                           l._hyper_gate.bias]
+            s = m.sqrt_end_time if m.train_T else torch.zeros((), device=x.device)
+            x, logp = _CnfBlockFunction.apply(x.contiguous(), logp.contiguous(), context, noise.detach(), m,
+                                              self.engine, s, *params)
+        if not want_logp:
             return x
         return x, logp.view(F, P, 1)

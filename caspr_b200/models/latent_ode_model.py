@@ -58,12 +58,48 @@ class ODESolver(nn.Module):
         net = self.ode_func.dynamics_net
         lin = [net[0], net[2], net[4], net[6]]
         times = t.detach().to(torch.float32).cpu().tolist()        # float32 grid, widened to float64 in the solver
+        if self.training and torch.is_grad_enabled():
+            # training: same forward solve, adjoint backward in CUDA (caspr_latent_ode_adjoint)
+            params = [p for l in lin for p in (l.weight, l.bias)]
+            return _LatentSolveFunction.apply(z0.to(torch.float32), self, times, *params)
         out, info, rc = ops.latent_ode_solve(z0.to(torch.float32), [l.weight for l in lin], [l.bias for l in lin],
                                              times, self.rtol, self.atol)
         self.ode_func._num_evals += float(info[1])
         if rc != 0:
             raise CasprError(rc, 'caspr_latent_ode_solve')
         return out
+
+
+class _LatentSolveFunction(torch.autograd.Function):
+    """odeint_adjoint for the latent ODE (latent_ode_model.py:98): forward = caspr_latent_ode_solve, backward =
+    caspr_latent_ode_adjoint (torchdiffeq 0.0.1's OdeintAdjointMethod.backward)."""
+
+    @staticmethod
+    def forward(ctx, z0, solver, times, *params):
+        out, info, rc = ops.latent_ode_solve(z0, [p.detach() for p in params[0::2]],
+                                             [p.detach() for p in params[1::2]], times, solver.rtol, solver.atol)
+        solver.ode_func._num_evals += float(info[1])
+        if rc != 0:
+            raise CasprError(rc, 'caspr_latent_ode_solve')
+        ctx.solver, ctx.times, ctx.params = solver, times, params
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        out, = ctx.saved_tensors
+        params, solver = ctx.params, ctx.solver
+        gz0, gpar, info, rc = ops.latent_ode_adjoint(out, g_out.contiguous(), [p.detach() for p in params[0::2]],
+                                                     [p.detach() for p in params[1::2]], ctx.times, solver.rtol,
+                                                     solver.atol)
+        solver.last_adjoint_info = info
+        if rc != 0:
+            raise CasprError(rc, 'caspr_latent_ode_adjoint')
+        grads, off = [], 0
+        for p in params:
+            grads.append(gpar[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        return (gz0, None, None) + tuple(grads)
 
 
 class DynamicsNet(nn.Module):

@@ -63,7 +63,13 @@ class TPointNet2(nn.Module):
         if not x.is_cuda:
             raise RuntimeError('caspr_b200 runs on CUDA only (no CPU fallback): move the input to the GPU')
         x = x.to(torch.float32).contiguous()
-        if not self.use_cuda_graph or self.trace is not None or torch.is_grad_enabled() and False:
+        if self.training and torch.is_grad_enabled():
+            # training: forward that keeps activations + hand-written backward (encoder_train.py)
+            from .encoder_train import EncodeFunction
+            params = [p for p in self.parameters() if p.requires_grad]
+            z0, tnocs = EncodeFunction.apply(x, self, *params)
+            return z0, (tnocs if self.regress_tnocs else None)
+        if not self.use_cuda_graph or self.trace is not None:
             return self._forward_eager(x)
         key = (tuple(x.shape), x.device.index, self._param_key())
         entry = self._graphs.get(key)

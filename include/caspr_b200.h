@@ -275,6 +275,50 @@ int caspr_latent_ode_adjoint(const float* zs, const float* gzs, int B, int D, in
                              float* gz0, float* gparams, int32_t* info, int32_t* h_info,
                              void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------- encoder training operators (forward + backward)
+ * What torch autograd does in the reference for the Conv1d(k=1) / GroupNorm / ReLU / max chains
+ * (pointnet2.py:637-642,677-699,471-481,207-212; pointnet.py:27-46; tpointnet2.py:59-62,99-112) and for Kaolin's
+ * group-gather / three_interpolate Functions (pointnet2.py:391,519).  Rows x channels fp32, leading dimensions. */
+
+/* GroupNorm statistics kept for the backward: mean_rstd [samples][groups] (mean, 1/sqrt(var+eps)) pairs. */
+size_t caspr_gn_workspace_bytes(int samples, int rows_per_sample, int C);
+int caspr_gn_moments(const float* X, int ldx, int samples, int rows_per_sample, int C, int groups, float eps,
+                   float* mean_rstd, void* workspace, size_t workspace_bytes, void* stream);
+/* Y = ReLU?((X - mean) * rstd * gamma + beta), out of place (X is kept for the backward). */
+int caspr_gn_apply(const float* X, int ldx, const float* mean_rstd, int samples, int rows_per_sample, int C,
+                   int groups, const float* gamma, const float* beta, int relu, float* Y, int ldy, void* stream);
+/* max over the rows of each sample and the (first) row index attaining it: maxout (samples,C), argmax (samples,C). */
+size_t caspr_rowmax_workspace_bytes(int samples, int rows_per_sample, int C);
+int caspr_rowmax(const float* Y, int ldy, int samples, int rows_per_sample, int C, float* maxout, int ld_max,
+                 int32_t* argmax, void* workspace, size_t workspace_bytes, void* stream);
+/* Backward of [GroupNorm -> ReLU? -> (dense consumer and/or max-pool)]: the output cotangent is
+ * dY (rows,C; may be NULL) + dMax (samples,C; may be NULL) routed to argmax rows.  Writes dX, dgamma, dbeta. */
+int caspr_gn_backward(const float* dY, int lddy, const float* dMax, int ld_dmax, const int32_t* argmax,
+                      const float* X, int ldx, const float* mean_rstd, int samples, int rows_per_sample,
+                      int C, int groups, const float* gamma, const float* beta, int relu, float* dX,
+                      int lddx, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
+                      void* stream);
+/* Conv1d(k=1)/Linear parameter gradients: dW (Cout,Cin) = dY^T . act(X), db (Cout) = column sums of dY (db may be
+ * NULL); relu_x applies ReLU to X on the fly (tpointnet2.py:105).  Deterministic split-row reduction. */
+size_t caspr_linear_wgrad_workspace_bytes(long long rows, int Cout, int Cin);
+int caspr_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, long long rows, int Cout, int Cin,
+                       int relu_x, float* dW, float* db, void* workspace, size_t workspace_bytes, void* stream);
+/* out[c] (+)= sum_r X[r][c] (backward of the repeat at pointnet.py:44). */
+size_t caspr_colsum_workspace_bytes(long long rows, int C);
+int caspr_colsum(const float* X, int ldx, long long rows, int C, float* out, int accumulate, void* workspace,
+                 size_t workspace_bytes, void* stream);
+/* Backward of caspr_group_points wrt the features: dfeat[b][idx][c] += dOut[row][3+c] (atomic adds). */
+int caspr_group_points_bwd(const float* dOut, int ld_out, const int32_t* idx, int B, int N, int M, int C,
+                           int ns, float* dfeat, int ld_feat, void* stream);
+/* Backward of the interpolation part of caspr_three_interp_concat: dprev[b][idx_k][c] += w_k dOut[row][c]. */
+int caspr_three_interp_bwd(const float* dOut, int ld_out, const int32_t* idx, const float* dist, int B, int n,
+                           int m, int Cp, float* dprev, int ld_prev, void* stream);
+/* dst (+)= src, optionally only where relu_ref > 0 (gradient through a ReLU whose output is relu_ref). */
+int caspr_rows_update(const float* src, int ld_src, long long rows, int C, int accumulate, const float* relu_ref,
+                      int ld_ref, float* dst, int ld_dst, void* stream);
+/* dst (cols,rows) = src (rows,cols)^T, contiguous. */
+int caspr_transpose(const float* src, int rows, int cols, float* dst, void* stream);
+
 /* -------------------------------------------------------------------- metric
  * Symmetric squared-NN Chamfer distance (reference utils/evaluations.py:40-43 via
  * tk3dv ChamferDistance): a (B,P,3), b (B,Q,3) -> d_ab (B,P) min sq dist a->b, d_ba (B,Q). */

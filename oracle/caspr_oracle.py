@@ -114,10 +114,13 @@ class CasprOracle(object):
             xyz_list.append(xyz)
             feat_list.append(features)
         self.trace['sa_feat_4'] = feat_list[-1]
+        for lvl in range(1, 6):
+            self.trace['sa_out_%d' % lvl] = feat_list[lvl]
         ti = -2
         for i in range(5):                                                          # :238
             feat_list[ti] = self.feature_propagation(i, xyz_list[ti], xyz_list[ti + 1],
                                                      feat_list[ti], feat_list[ti + 1])
+            self.trace['fp_out_%d' % i] = feat_list[ti]
             ti -= 1
         p = 'encoder.local_extract.final_layers.'
         x = F.relu(self._gn(self._conv(feat_list[0], p + '0'), p + '1'))            # :247
