@@ -7,7 +7,11 @@ mechanism is single-process ``nn.DataParallel`` (caspr/train.py:131-132), whose 
 own adaptive step controller — the same "independent" semantics as here: one process per GPU, rank r
 owns sequences [lo, hi) and solves with its own step sequence.
 
-NCCL (or gloo on CPU) is used only to gather results / timings, never inside the hot path.
+NCCL (or gloo on CPU) is used only to gather results / timings, never inside the reconstruction hot path.
+Training (BASELINE config 5) adds the one real exchange step of the reference's multi-GPU path: the gradient
+reduction DataParallel performs when it scatters the batch and gathers the replicas' gradients
+(``train.py:131-132``).  Here it is ONE sum all-reduce of a flat fp32 gradient buffer (16.26 M floats, 65 MB)
+over NCCL / NVLink per step, followed by the identical optimizer step on every rank.
 """
 import torch
 import torch.distributed as dist
@@ -67,3 +71,56 @@ def max_over_ranks(value, device, group=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+def allreduce_gradients(parameters, group=None, average=True):
+    """Sum (or average) the ``.grad`` of ``parameters`` over ranks with ONE all-reduce of a flat buffer.
+
+    Parameters that received no gradient on this rank (``grad is None``) contribute zeros, so every rank reduces the
+    same layout even when a rank's shard was empty.  Returns the number of elements reduced."""
+    params = [p for p in parameters if p.requires_grad]
+    if not params:
+        return 0
+    world = dist.get_world_size(group)
+    flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=params[0].device)
+    off = 0
+    for p in params:
+        if p.grad is not None:
+            flat[off:off + p.numel()].copy_(p.grad.reshape(-1))
+        off += p.numel()
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat /= world
+    off = 0
+    for p in params:
+        g = flat[off:off + p.numel()].view_as(p)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        off += p.numel()
+    return flat.numel()
+
+
+def train_step_sharded(model, optimizer, x, sample_points, loss_fn, group=None, **forward_kwargs):
+    """One data-parallel training step (train_utils.py:118-175 under ``--parallel``): rank r runs forward + backward on
+    its slice of the batch, gradients are averaged with one all-reduce, every rank applies the same optimizer step.
+
+    ``loss_fn(nll, tnocs_l1) -> scalar`` must be a MEAN over the sequences it is given; shards of equal size then
+    reproduce the single-process gradient.  Returns this rank's loss (python float; nan for an empty shard)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    lo, hi = shard_range(x.shape[0], rank, world)
+    optimizer.zero_grad()
+    loss_value = float('nan')
+    if hi > lo:
+        kw = dict(forward_kwargs)
+        if kw.get('e') is not None:
+            T = x.shape[1]
+            kw['e'] = kw['e'].reshape(x.shape[0] * T, *kw['e'].shape[-2:])[lo * T:hi * T]
+        losses = model(x[lo:hi], sample_points[lo:hi], **kw)
+        loss = loss_fn(*losses)
+        loss.backward()
+        loss_value = float(loss.detach())
+    allreduce_gradients(model.parameters(), group=group, average=True)
+    optimizer.step()
+    return loss_value

@@ -8,7 +8,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from caspr_b200.sharding import shard_range, gather_batch, reconstruct_sharded, max_over_ranks
+from caspr_b200.sharding import (shard_range, gather_batch, reconstruct_sharded, max_over_ranks,
+                                 allreduce_gradients, train_step_sharded)
 
 
 def test_shard_range_partitions():
@@ -83,6 +84,75 @@ def test_world_size_2_gloo(B):
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, B, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]
+
+
+class _TinyTrainModel(torch.nn.Module):
+    """Stands in for CaSPR.forward in training mode: per-sequence losses from a linear map."""
+
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(0)
+        self.lin = torch.nn.Linear(4, 3)
+        self.unused = torch.nn.Parameter(torch.zeros(2))         # never receives a gradient
+
+    def forward(self, x, sample_points, e=None):
+        y = self.lin(x)                                           # (B,T,N,3)
+        nll = (y ** 2).sum(-1)
+        if e is not None:
+            nll = nll + (y * e.view(x.shape[0], x.shape[1], -1, 3)).sum(-1)
+        return nll, (y - sample_points[..., :3]).abs()
+
+
+def _loss(nll, tl1):
+    return 0.01 * nll.sum(2).mean() + 100.0 * tl1.mean()
+
+
+def _train_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(1)
+        B, T, N = 4, 2, 5
+        x = torch.randn(B, T, N, 4, generator=g)
+        nocs = torch.randn(B, T, N, 4, generator=g)
+        e = torch.randn(B * T, N, 3, generator=g)
+        ref = _TinyTrainModel()
+        opt_ref = torch.optim.SGD(ref.parameters(), lr=0.1)
+        opt_ref.zero_grad()
+        _loss(*ref(x, nocs, e=e)).backward()
+        opt_ref.step()
+        model = _TinyTrainModel()
+        opt = torch.optim.SGD(model.parameters(), lr=0.1)
+        loss = train_step_sharded(model, opt, x, nocs, _loss, e=e)
+        ok = all(torch.allclose(a, b, atol=1e-6) for a, b in zip(model.parameters(), ref.parameters()))
+        ok = ok and loss == loss
+        # gradient layout with a missing gradient on one rank only
+        m2 = _TinyTrainModel()
+        if rank == 0:
+            m2.lin.weight.grad = torch.ones_like(m2.lin.weight)
+        n = allreduce_gradients(m2.parameters(), average=False)
+        ok = ok and n == sum(p.numel() for p in m2.parameters())
+        ok = ok and torch.equal(m2.lin.weight.grad, torch.ones_like(m2.lin.weight))
+        ok = ok and torch.equal(m2.unused.grad, torch.zeros(2))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world_size_2_gloo():
+    """Sharded training step == single-process step on the full batch (equal shards, mean loss)."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
