@@ -81,7 +81,7 @@ SIGNATURES = {
     'caspr_cnf_param_count': (c_size_t, [c_int, c_int]),
     'caspr_cnf_adjoint_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
     'caspr_cnf_adjoint': (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, POINTER(CnfWeights), c_float, c_float,
-                                  c_float, _P, _P, _P, _P, _P, _P, POINTER(c_int32), _P, c_size_t, _P]),
+                                  c_float, c_int, _P, _P, _P, _P, _P, _P, POINTER(c_int32), _P, c_size_t, _P]),
     'caspr_latent_ode_param_count': (c_size_t, [c_int, c_int]),
     'caspr_latent_ode_adjoint_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'caspr_latent_ode_adjoint': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P,
@@ -96,6 +96,8 @@ SIGNATURES = {
                                   c_int, _P, c_int, _P, _P, _P, c_size_t, _P]),
     'caspr_linear_wgrad_workspace_bytes': (c_size_t, [c_longlong, c_int, c_int]),
     'caspr_linear_wgrad': (c_int, [_P, c_int, _P, c_int, c_longlong, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    'caspr_linear_wgrad_tc_workspace_bytes': (c_size_t, [c_longlong, c_int, c_int]),
+    'caspr_linear_wgrad_tc': (c_int, [_P, c_int, _P, c_int, c_longlong, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     'caspr_colsum_workspace_bytes': (c_size_t, [c_longlong, c_int]),
     'caspr_colsum': (c_int, [_P, c_int, c_longlong, c_int, _P, c_int, _P, c_size_t, _P]),
     'caspr_group_points_bwd': (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P]),

@@ -14,7 +14,9 @@
 //              u3 = adj_x, v3 = -adj_logp * e:  two H x H data-gradient products, two H x H weight-gradient
 //              products (split over the points, reduced deterministically), per-frame gate / bias cotangents,
 //              then the hyper-network gradients (weights, context, time).
-// Everything is exact fp32 SIMT in this version.
+// Engines: CASPR_CNF_SIMT_FP32 runs everything as exact fp32 SIMT; CASPR_CNF_TC_FP16X3 sends the forward and the
+// data-gradient H x H products through caspr_linear_tc and the weight gradients through the split-K
+// caspr_linear_wgrad_tc (all six products of an evaluation on the tcgen05 fp16x3 GEMM of gemm_tc.cu).
 #include "cnf_kernels.cuh"
 #include "rk_flat.cuh"
 
@@ -88,6 +90,37 @@ __device__ __forceinline__ void through_activation(float hb, float hdb, float a,
   vbar = hdb * d1;
   gsum += ubar * (a + blayer) + vbar * ad;
   bsum += ubar;
+}
+
+// Tensor-core engine: the H x H products come back raw from caspr_linear_tc; this applies the ConcatSquash gate /
+// bias, softplus and the tangent's chain rule (the epilogue of cnf_mid_layer_kernel<kMidForward>).
+__global__ void __launch_bounds__(256)
+adj_act_kernel(const float* __restrict__ A, const float* __restrict__ Ad, const float* __restrict__ gate,
+               const float* __restrict__ biasf, int ld, int H, int P, long long total4,
+               const CnfState* __restrict__ st, float* __restrict__ Hn, float* __restrict__ Vn) {
+  if (st->done) return;
+  const int h4 = H / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const long long pt = i / h4;
+    const int c = (int)(i - pt * h4) * 4;
+    const int f = (int)(pt / P);
+    const float4 a4 = *reinterpret_cast<const float4*>(A + pt * H + c);
+    const float4 d4 = *reinterpret_cast<const float4*>(Ad + pt * H + c);
+    const float4 g4 = *reinterpret_cast<const float4*>(gate + (size_t)f * ld + c);
+    const float4 b4 = *reinterpret_cast<const float4*>(biasf + (size_t)f * ld + c);
+    const float a[4] = {a4.x, a4.y, a4.z, a4.w}, d[4] = {d4.x, d4.y, d4.z, d4.w};
+    const float g[4] = {g4.x, g4.y, g4.z, g4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+    float ho[4], vo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float sp, dsp;
+      softplus_and_grad(fmaf(a[j], g[j], b[j]), sp, dsp);
+      ho[j] = sp;
+      vo[j] = dsp * g[j] * d[j];
+    }
+    *reinterpret_cast<float4*>(Hn + pt * H + c) = make_float4(ho[0], ho[1], ho[2], ho[3]);
+    *reinterpret_cast<float4*>(Vn + pt * H + c) = make_float4(vo[0], vo[1], vo[2], vo[3]);
+  }
 }
 
 constexpr int kChunkMax = 64;       // points per chunk of the thread-per-channel kernels
@@ -584,6 +617,11 @@ struct AdjWorkspace {
   float *A1, *Ad1, *H2, *V2, *A2, *Ad2, *H3, *V3, *raw8;
   float *Gh, *Gv, *Ab, *Av;
   float *W1t, *W2t;
+  char* tc_ws;                       // caspr_linear_tc operand planes for a (2n x H) activation / tangent stack
+  size_t tc_ws_bytes, prep_bytes;
+  char* prep[4];                     // fp16 hi/lo planes of W1, W2, W1^T, W2^T
+  char* wg_ws;                       // caspr_linear_wgrad_tc workspace
+  size_t wg_ws_bytes;
   float *gpart, *bpart, *w0part, *w3part, *wpart, *Ghat, *Bhat, *cpart;
   double* sums;
   float* scratch_x;                  // x(t0), logp(t0) written by the state finalize (not returned)
@@ -595,7 +633,6 @@ AdjWorkspace adj_carve(void* base, int frames, int pts, int H, int C) {
   AdjWorkspace w;
   memset(&w, 0, sizeof(w));
   const size_t n = (size_t)frames * pts;
-  const size_t n_pad = (n + 63) / 64 * 64;
   const size_t ctot = hyper_ld(H);
   const ParamLayout pl = param_layout(H, C);
   // chunks of points per frame for the thread-per-channel kernels: enough CTAs for two waves, <= 64 points each
@@ -621,8 +658,12 @@ AdjWorkspace adj_carve(void* base, int frames, int pts, int H, int C) {
   b.y0 = (float4*)take(n * 16);
   b.y1 = (float4*)take(n * 16);
   b.kbuf = (float4*)take(7 * n * 16);
-  b.Ha = (float*)take(n_pad * H * 4);
-  b.Va = (float*)take(n_pad * H * 4);
+  // activation and tangent of a layer are stored back to back, so that [h ; v] is ONE (2n x H) row-major operand
+  auto take_pair = [&](float** a, float** v) {
+    *a = (float*)take((size_t)2 * n * H * 4);
+    *v = *a + n * H;
+  };
+  take_pair(&b.Ha, &b.Va);
   w.adj0 = (float4*)take(n * 16);
   w.kadj = (float4*)take(7 * n * 16);
   w.adj_out = (float4*)take(n * 16);
@@ -633,8 +674,19 @@ AdjWorkspace adj_carve(void* base, int frames, int pts, int H, int C) {
   w.U0 = (float*)take(w.nu * 4);
   w.kU = (float*)take(7 * w.nu * 4);
   w.Uout = (float*)take(w.nu * 4);
-  float** act[] = {&w.A1, &w.Ad1, &w.H2, &w.V2, &w.A2, &w.Ad2, &w.H3, &w.V3, &w.Gh, &w.Gv, &w.Ab, &w.Av};
-  for (float** a : act) *a = (float*)take(n_pad * H * 4);
+  take_pair(&w.A1, &w.Ad1);
+  take_pair(&w.H2, &w.V2);
+  take_pair(&w.A2, &w.Ad2);
+  take_pair(&w.H3, &w.V3);
+  take_pair(&w.Gh, &w.Gv);
+  take_pair(&w.Ab, &w.Av);
+  auto take1k = [&](size_t bytes) { p = (char*)align_up((size_t)p, 1024); char* r = p; p += align_up(bytes, 1024); return r; };
+  w.tc_ws_bytes = caspr_linear_tc_workspace_bytes((int)(2 * n), H, H);
+  w.tc_ws = take1k(w.tc_ws_bytes);
+  w.prep_bytes = caspr_linear_tc_weight_bytes(H, H);
+  for (int i = 0; i < 4; ++i) w.prep[i] = take1k(w.prep_bytes);
+  w.wg_ws_bytes = caspr_linear_wgrad_tc_workspace_bytes((long long)(2 * n), H, H);
+  w.wg_ws = take1k(w.wg_ws_bytes);
   w.raw8 = (float*)take(n * 8 * 4);
   w.W1t = (float*)take((size_t)H * H * 4);
   w.W2t = (float*)take((size_t)H * H * 4);
@@ -655,7 +707,7 @@ AdjWorkspace adj_carve(void* base, int frames, int pts, int H, int C) {
 
 // One augmented evaluation at RK stage `stage` (hyper gates of that stage must be in place).
 int enqueue_aug_eval(const AdjWorkspace& w, const caspr_cnf_weights* cw, const float* e, const float* ctx, int frames,
-                     int pts, int stage, cudaStream_t s) {
+                     int pts, int stage, int engine, cudaStream_t s) {
   const int H = cw->hidden, C = cw->ctx_dim;
   const int n = frames * pts;
   const int ctot = hyper_ld(H);
@@ -674,10 +726,27 @@ int enqueue_aug_eval(const AdjWorkspace& w, const caspr_cnf_weights* cw, const f
   CASPR_COUNT(); cnf_layer0_kernel<<<blocks_for(n, 8, 148 * 16), 256, 0, s>>>(
       b.y0, b.kbuf, (size_t)n, e, cw->W[0], H, n, pts, stage, gate, biasf, ctot, b.st, b.Ha, b.Va);
   const dim3 ggrid(ceil_div(n, kMidBM), H / kMidBN);
-  CASPR_COUNT(); cnf_mid_layer_kernel<kMidForwardKeepRaw><<<ggrid, 256, 0, s>>>(
-      b.Ha, b.Va, cw->W[1], H, n, pts, gate + H, biasf + H, ctot, b.st, w.H2, w.V2, w.A1, w.Ad1);
-  CASPR_COUNT(); cnf_mid_layer_kernel<kMidForwardKeepRaw><<<ggrid, 256, 0, s>>>(
-      w.H2, w.V2, cw->W[2], H, n, pts, gate + 2 * H, biasf + 2 * H, ctot, b.st, w.H3, w.V3, w.A2, w.Ad2);
+  const bool tc = engine == CASPR_CNF_TC_FP16X3;
+  const long long total4 = (long long)n * H / 4;
+  const int agrid = blocks_for(total4, 256 * 2, 148 * 16);
+  // (2n x H) . W^T on the tcgen05 fp16x3 GEMM: rows [0,n) = activations, rows [n,2n) = tangents
+  auto tc_product = [&](const float* X, int widx, float* Y) {
+    return caspr_linear_tc(X, H, nullptr, H, nullptr, Y, H, 2 * n, H, H, CASPR_ACT_NONE, CASPR_ACT_NONE, w.prep[widx],
+                           nullptr, nullptr, w.tc_ws, w.tc_ws_bytes, s);
+  };
+  if (tc) {
+    int rc = tc_product(b.Ha, 0, w.A1);
+    if (rc) return rc;
+    CASPR_COUNT(); adj_act_kernel<<<agrid, 256, 0, s>>>(w.A1, w.Ad1, gate + H, biasf + H, ctot, H, pts, total4, b.st, w.H2, w.V2);
+    rc = tc_product(w.H2, 1, w.A2);
+    if (rc) return rc;
+    CASPR_COUNT(); adj_act_kernel<<<agrid, 256, 0, s>>>(w.A2, w.Ad2, gate + 2 * H, biasf + 2 * H, ctot, H, pts, total4, b.st, w.H3, w.V3);
+  } else {
+    CASPR_COUNT(); cnf_mid_layer_kernel<kMidForwardKeepRaw><<<ggrid, 256, 0, s>>>(
+        b.Ha, b.Va, cw->W[1], H, n, pts, gate + H, biasf + H, ctot, b.st, w.H2, w.V2, w.A1, w.Ad1);
+    CASPR_COUNT(); cnf_mid_layer_kernel<kMidForwardKeepRaw><<<ggrid, 256, 0, s>>>(
+        w.H2, w.V2, cw->W[2], H, n, pts, gate + 2 * H, biasf + 2 * H, ctot, b.st, w.H3, w.V3, w.A2, w.Ad2);
+  }
   CASPR_COUNT(); cnf_last_layer_kernel<<<blocks_for(n, 8, 148 * 16), 256, 0, s>>>(
       w.H3, w.V3, cw->W[3], H, n, pts, e, gate + 3 * H, biasf + 3 * H, ctot, 1, b.st, b.kbuf + (size_t)stage * n,
       w.raw8);
@@ -689,18 +758,38 @@ int enqueue_aug_eval(const AdjWorkspace& w, const caspr_cnf_weights* cw, const f
   CASPR_COUNT(); adj_bwd_last_kernel<<<egrid, H, 0, s>>>(
       w.adj0, w.kadj, (size_t)n, stage, b.st, e, cw->W[3], w.raw8, w.A2, w.Ad2, w.H3, w.V3, gate, biasf, b.lbias,
       ctot, H, pts, w.L, w.Ab, w.Av, w.gpart, w.bpart, w.w3part);
-  CASPR_COUNT(); adj_wgrad_kernel<<<wgrid, 256, 0, s>>>(w.Ab, w.Av, w.H2, w.V2, H, n, w.pts_per_split, b.st, w.wpart);
-  CASPR_COUNT(); adj_reduce_parts_kernel<<<(unsigned)((hh + 255) / 256), 256, 0, s>>>(w.wpart, w.nsplit, hh, b.st,
-                                                                                       kpar + pl.W[2]);
-  CASPR_COUNT(); cnf_mid_layer_kernel<kMidPlain><<<ggrid, 256, 0, s>>>(
-      w.Ab, w.Av, w.W2t, H, n, pts, nullptr, nullptr, ctot, b.st, w.Gh, w.Gv, nullptr, nullptr);
+  // weight gradient of an H x H layer: [Ab ; Av]^T . [h ; v] over the 2n stacked rows
+  auto wgrad = [&](const float* Hin, const float* Vin, float* dst) {
+    if (tc)
+      return caspr_linear_wgrad_tc(w.Ab, H, Hin, H, 2ll * n, H, H, 0, dst, w.wg_ws, w.wg_ws_bytes, s);
+    CASPR_COUNT(); adj_wgrad_kernel<<<wgrid, 256, 0, s>>>(w.Ab, w.Av, Hin, Vin, H, n, w.pts_per_split, b.st, w.wpart);
+    CASPR_COUNT(); adj_reduce_parts_kernel<<<(unsigned)((hh + 255) / 256), 256, 0, s>>>(w.wpart, w.nsplit, hh, b.st, dst);
+    return (int)CASPR_OK;
+  };
+  {
+    const int rc = wgrad(w.H2, w.V2, kpar + pl.W[2]);
+    if (rc) return rc;
+  }
+  if (tc) {
+    const int rc = tc_product(w.Ab, 3, w.Gh);
+    if (rc) return rc;
+  } else {
+    CASPR_COUNT(); cnf_mid_layer_kernel<kMidPlain><<<ggrid, 256, 0, s>>>(
+        w.Ab, w.Av, w.W2t, H, n, pts, nullptr, nullptr, ctot, b.st, w.Gh, w.Gv, nullptr, nullptr);
+  }
   CASPR_COUNT(); adj_bwd_mid_kernel<<<egrid, H, 0, s>>>(w.Gh, w.Gv, w.A1, w.Ad1, gate, biasf, b.lbias, ctot, H, pts,
                                                         w.L, 1, b.st, w.Ab, w.Av, w.gpart, w.bpart);
-  CASPR_COUNT(); adj_wgrad_kernel<<<wgrid, 256, 0, s>>>(w.Ab, w.Av, b.Ha, b.Va, H, n, w.pts_per_split, b.st, w.wpart);
-  CASPR_COUNT(); adj_reduce_parts_kernel<<<(unsigned)((hh + 255) / 256), 256, 0, s>>>(w.wpart, w.nsplit, hh, b.st,
-                                                                                       kpar + pl.W[1]);
-  CASPR_COUNT(); cnf_mid_layer_kernel<kMidPlain><<<ggrid, 256, 0, s>>>(
-      w.Ab, w.Av, w.W1t, H, n, pts, nullptr, nullptr, ctot, b.st, w.Gh, w.Gv, nullptr, nullptr);
+  {
+    const int rc = wgrad(b.Ha, b.Va, kpar + pl.W[1]);
+    if (rc) return rc;
+  }
+  if (tc) {
+    const int rc = tc_product(w.Ab, 2, w.Gh);
+    if (rc) return rc;
+  } else {
+    CASPR_COUNT(); cnf_mid_layer_kernel<kMidPlain><<<ggrid, 256, 0, s>>>(
+        w.Ab, w.Av, w.W1t, H, n, pts, nullptr, nullptr, ctot, b.st, w.Gh, w.Gv, nullptr, nullptr);
+  }
   CASPR_COUNT(); adj_bwd_layer0_kernel<<<egrid, H, 0, s>>>(
       b.y0, b.kbuf, (size_t)n, stage, b.st, e, cw->W[0], w.Gh, w.Gv, gate, biasf, b.lbias, ctot, H, pts, w.L,
       w.kadj + (size_t)stage * n, w.gpart, w.bpart, w.w0part);
@@ -751,7 +840,7 @@ extern "C" size_t caspr_cnf_adjoint_workspace_bytes(int frames, int pts, int hid
 
 extern "C" int caspr_cnf_adjoint(const float* x1, const float* logp1, const float* gx1, const float* glogp1,
                                  const float* e, const float* ctx, int frames, int pts,
-                                 const caspr_cnf_weights* cw, float end_time, float rtol, float atol,
+                                 const caspr_cnf_weights* cw, float end_time, float rtol, float atol, int engine,
                                  float* gx0, float* glogp0, float* gctx, float* gparams, float* gtimes,
                                  int32_t* info, int32_t* h_info, void* workspace, size_t workspace_bytes,
                                  void* stream) {
@@ -760,7 +849,8 @@ extern "C" int caspr_cnf_adjoint(const float* x1, const float* logp1, const floa
   CASPR_REQUIRE(frames > 0 && pts > 0 && (long long)frames * pts < (1ll << 30));
   CASPR_REQUIRE(weights_ok(cw) && cw->hidden <= 512);
   CASPR_REQUIRE(end_time > 0.f);
-  CASPR_REQUIRE(((uintptr_t)workspace & 255) == 0);
+  CASPR_REQUIRE(engine == CASPR_CNF_SIMT_FP32 || engine == CASPR_CNF_TC_FP16X3);
+  CASPR_REQUIRE(((uintptr_t)workspace & 1023) == 0);
   const int H = cw->hidden, C = cw->ctx_dim;
   if (workspace_bytes < caspr_cnf_adjoint_workspace_bytes(frames, pts, H, C)) return CASPR_EWORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
@@ -775,6 +865,14 @@ extern "C" int caspr_cnf_adjoint(const float* x1, const float* logp1, const floa
     const dim3 tg(ceil_div(H, 32), ceil_div(H, 32)), tb(32, 8);
     CASPR_COUNT(); transpose_kernel<<<tg, tb, 0, s>>>(cw->W[1], H, H, w.W1t);
     CASPR_COUNT(); transpose_kernel<<<tg, tb, 0, s>>>(cw->W[2], H, H, w.W2t);
+    CASPR_CHECK_LAUNCH();
+  }
+  if (engine == CASPR_CNF_TC_FP16X3) {
+    const float* mats[4] = {cw->W[1], cw->W[2], w.W1t, w.W2t};
+    for (int i = 0; i < 4; ++i) {
+      rc = caspr_linear_tc_prepare_weights(mats[i], H, H, H, w.prep[i], w.prep_bytes, s);
+      if (rc) return rc;
+    }
   }
   const MbnDev none = load_mbn(nullptr, nullptr);
   CASPR_COUNT(); cnf_init_state_kernel<<<ceil_div(n, 256), 256, 0, s>>>(x1, logp1, n, none, 0, b.y0);
@@ -793,7 +891,7 @@ extern "C" int caspr_cnf_adjoint(const float* x1, const float* logp1, const floa
   }
   rc = enqueue_hyper_stages(w, frames, H, 0, 0, s);
   if (rc) return rc;
-  rc = enqueue_aug_eval(w, cw, e, ctx, frames, pts, 0, s);
+  rc = enqueue_aug_eval(w, cw, e, ctx, frames, pts, 0, engine, s);
   if (rc) return rc;
   const int eb = blocks_for(n, 256, 148 * 8);
   // dL/dt1 and adj_time(t1) = -dL/dt1 (needs f(t1, y1) = -k0)
@@ -822,7 +920,7 @@ extern "C" int caspr_cnf_adjoint(const float* x1, const float* logp1, const floa
     rc = enqueue_hyper_stages(w, frames, H, 1, 6, s);
     if (rc) return rc;
     for (int stage = 1; stage <= 6; ++stage) {
-      rc = enqueue_aug_eval(w, cw, e, ctx, frames, pts, stage, s);
+      rc = enqueue_aug_eval(w, cw, e, ctx, frames, pts, stage, engine, s);
       if (rc) return rc;
     }
     CASPR_COUNT(); cnf_error_kernel<<<eb, 256, 0, s>>>(b.y0, b.kbuf, (size_t)n, n, rtol, atol, b.st, b.y1);

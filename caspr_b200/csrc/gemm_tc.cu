@@ -252,7 +252,220 @@ Layout make_layout(long long rows, int cin, int cout) {
 }
 
 bool g_linear_attr_set = false;
+bool g_wgrad_attr_set = false;
 
+// ------------------------------------------------------------------ weight gradient (split-K, transposed operands)
+// dW[o][i] = sum_r dY[r][o] X[r][i]: both operands are needed with the ROW index as the contraction (K) dimension, i.e.
+// transposed.  colmax -> per-column power-of-two scale; transpose_split writes the fp16 hi/lo planes [C_pad][R_pad].
+__global__ void __launch_bounds__(128)
+colmax_partial_kernel(const float* __restrict__ X, int ldx, long long rows, int C, long long rows_per_split, int relu,
+                      float* __restrict__ partial) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const long long r0 = blockIdx.y * rows_per_split;
+  const long long r1 = r0 + rows_per_split < rows ? r0 + rows_per_split : rows;
+  float m = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    float v = X[r * ldx + c];
+    if (relu) v = fmaxf(v, 0.f);
+    m = fmaxf(m, fabsf(v));
+  }
+  partial[(size_t)blockIdx.y * C + c] = m;
+}
+// scale[c] = 2^(14-e), inv[c] = 2^(e-14) with max|column| < 2^e; padded channels get 0
+__global__ void colscale_kernel(const float* __restrict__ partial, int nsplit, int C, int C_pad, float* __restrict__ scale,
+                                float* __restrict__ inv) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C_pad) return;
+  float m = 0.f;
+  if (c < C)
+    for (int p = 0; p < nsplit; ++p) m = fmaxf(m, partial[(size_t)p * C + c]);
+  float s = 1.f, iv = c < C ? 1.f : 0.f;
+  if (m > 0.f && m < 3.0e38f) {
+    int e;
+    frexpf(m, &e);
+    s = ldexpf(1.f, 14 - e);
+    iv = ldexpf(1.f, e - 14);
+  }
+  scale[c] = s;
+  inv[c] = iv;
+}
+// planes[c][r] = split(X[r][c] * scale[c]) for a 64 (rows) x 64 (channels) tile through shared memory; zero padding
+__global__ void __launch_bounds__(256)
+transpose_split_kernel(const float* __restrict__ X, int ldx, long long rows, int C, long long rows_pad, int relu,
+                       const float* __restrict__ scale, __half* __restrict__ hi, __half* __restrict__ lo) {
+  __shared__ float tile[64][65];
+  const long long r0 = (long long)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
+  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+    const int rr = i >> 6, cc = i & 63;
+    const long long r = r0 + rr;
+    const int c = c0 + cc;
+    float v = (r < rows && c < C) ? X[r * ldx + c] : 0.f;
+    if (relu) v = fmaxf(v, 0.f);
+    tile[rr][cc] = v;
+  }
+  __syncthreads();
+  // thread -> (channel cc, row pair rp): 64 channels x 32 pairs = 2048 half2 per plane, 8 per thread
+  for (int i = threadIdx.x; i < 64 * 32; i += 256) {
+    const int cc = i >> 5, rp = i & 31;
+    const int c = c0 + cc;
+    const float s = scale[c];
+    const float a = tile[2 * rp][cc] * s, b = tile[2 * rp + 1][cc] * s;
+    const __half2 hh = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(hh);
+    const size_t off = ((size_t)c * rows_pad + r0) / 2 + rp;
+    reinterpret_cast<__half2*>(hi)[off] = hh;
+    reinterpret_cast<__half2*>(lo)[off] = __floats2half2_rn(a - hf.x, b - hf.y);
+  }
+}
+
+// partial[split][o][i] = acc * inv_dy[o] * inv_x[i]
+struct WgradEpilogue {
+  const float* a_inv;     // per output channel o (rows of the A operand)
+  const float* w_inv;     // per input channel i
+  float* part;            // [k_splits][cout][cin]
+  int cout, cin, m_tiles;
+  long long row;
+  int col0, split;
+  float inv;
+  __device__ __forceinline__ void setup(uint8_t*, const CUtensorMap*, const CUtensorMap*, int) {}
+  __device__ __forceinline__ void tile_begin(int m_tile_epi, int n_tile, int q, int lane) {
+    split = m_tile_epi / m_tiles;
+    row = (long long)(m_tile_epi - split * m_tiles) * kBM + q * 32 + lane;
+    col0 = n_tile * kBN;
+    inv = a_inv[row];
+  }
+  __device__ __forceinline__ void chunk(int chunk, uint32_t (&r)[32]) {
+    const int c = col0 + chunk * 32;
+    if (c >= cin || row >= cout) return;
+    float* y = part + ((size_t)split * cout + row) * cin + c;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (c + j < cin) y[j] = __uint_as_float(r[j]) * (inv * w_inv[c + j]);
+  }
+  __device__ __forceinline__ void finish() {}
+};
+
+struct WgradLayout {
+  long long r_pad;          // contraction length padded to k_splits * k_chunks * 64
+  int k_splits, k_chunks, cout_pad, cin_pad, colmax_splits;
+  size_t off_cmax, off_ascale, off_ainv, off_wscale, off_winv, off_ahi, off_alo, off_whi, off_wlo, off_part, total;
+};
+WgradLayout make_wgrad_layout(long long rows, int cout, int cin) {
+  WgradLayout l;
+  l.cout_pad = (cout + kBM - 1) / kBM * kBM;
+  l.cin_pad = (cin + kBN - 1) / kBN * kBN;
+  const long long chunks_total = (rows + kBK - 1) / kBK;
+  // at most 64 k-chunks (4096 rows) per split: bounds the truncation error of the fp32 accumulation in TMEM and
+  // gives enough work items to fill the GPU
+  long long splits = (chunks_total + 63) / 64;
+  const long long tiles = (long long)(l.cout_pad / kBM) * (l.cin_pad / kBN);
+  while (splits * tiles < 148 && splits < chunks_total) ++splits;
+  l.k_splits = (int)splits;
+  l.k_chunks = (int)((chunks_total + splits - 1) / splits);
+  l.r_pad = (long long)l.k_splits * l.k_chunks * kBK;
+  long long cs = (2 * 148) / ((cout > cin ? cout : cin) / 128 + 1);
+  const long long maxs = (rows + 255) / 256;
+  if (cs > maxs) cs = maxs;
+  if (cs < 1) cs = 1;
+  l.colmax_splits = (int)cs;
+  size_t p = 0;
+  auto take = [&](size_t bytes) { size_t r = p; p += align_up(bytes, 1024); return r; };
+  const int cmax = l.cout_pad > l.cin_pad ? l.cout_pad : l.cin_pad;
+  l.off_cmax = take((size_t)l.colmax_splits * cmax * 4);
+  l.off_ascale = take((size_t)l.cout_pad * 4);
+  l.off_ainv = take((size_t)l.cout_pad * 4);
+  l.off_wscale = take((size_t)l.cin_pad * 4);
+  l.off_winv = take((size_t)l.cin_pad * 4);
+  l.off_ahi = take((size_t)l.cout_pad * l.r_pad * 2);
+  l.off_alo = take((size_t)l.cout_pad * l.r_pad * 2);
+  l.off_whi = take((size_t)l.cin_pad * l.r_pad * 2);
+  l.off_wlo = take((size_t)l.cin_pad * l.r_pad * 2);
+  l.off_part = take((size_t)l.k_splits * cout * cin * 4);
+  l.total = p;
+  return l;
+}
+
+__global__ void __launch_bounds__(256)
+wgrad_sum_parts_kernel(const float* __restrict__ part, int nparts, size_t nelem, float* __restrict__ dst) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nelem) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += part[(size_t)p * nelem + i];
+  dst[i] = s;
+}
+
+}  // namespace
+
+extern "C" size_t caspr_linear_wgrad_tc_workspace_bytes(long long rows, int Cout, int Cin) {
+  if (rows <= 0 || Cout <= 0 || Cin <= 0) return 0;
+  return make_wgrad_layout(rows, Cout, Cin).total;
+}
+
+extern "C" int caspr_linear_wgrad_tc(const float* dY, int lddy, const float* X, int ldx, long long rows, int Cout,
+                                     int Cin, int relu_x, float* dW, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+  CASPR_REQUIRE(dY && X && dW && workspace && rows > 0 && Cout > 0 && Cin > 0 && lddy >= Cout && ldx >= Cin);
+  CASPR_REQUIRE(((uintptr_t)workspace & 1023) == 0);
+  const WgradLayout l = make_wgrad_layout(rows, Cout, Cin);
+  if (workspace_bytes < l.total) return CASPR_EWORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  char* base = (char*)workspace;
+  float* cmax = (float*)(base + l.off_cmax);
+  float* ascale = (float*)(base + l.off_ascale);
+  float* ainv = (float*)(base + l.off_ainv);
+  float* wscale = (float*)(base + l.off_wscale);
+  float* winv = (float*)(base + l.off_winv);
+  __half* ahi = (__half*)(base + l.off_ahi);
+  __half* alo = (__half*)(base + l.off_alo);
+  __half* whi = (__half*)(base + l.off_whi);
+  __half* wlo = (__half*)(base + l.off_wlo);
+  float* part = (float*)(base + l.off_part);
+  const long long rps = (rows + l.colmax_splits - 1) / l.colmax_splits;
+  CASPR_REQUIRE(l.r_pad / 64 < (1ll << 31));
+  // operand A = dY^T
+  CASPR_COUNT(); colmax_partial_kernel<<<dim3(ceil_div(Cout, 128), l.colmax_splits), 128, 0, s>>>(dY, lddy, rows, Cout, rps, 0, cmax);
+  CASPR_COUNT(); colscale_kernel<<<ceil_div(l.cout_pad, 128), 128, 0, s>>>(cmax, l.colmax_splits, Cout, l.cout_pad, ascale, ainv);
+  CASPR_COUNT(); transpose_split_kernel<<<dim3((unsigned)(l.r_pad / 64), l.cout_pad / 64), 256, 0, s>>>(
+      dY, lddy, rows, Cout, l.r_pad, 0, ascale, ahi, alo);
+  // operand W = X^T
+  CASPR_COUNT(); colmax_partial_kernel<<<dim3(ceil_div(Cin, 128), l.colmax_splits), 128, 0, s>>>(X, ldx, rows, Cin, rps, relu_x, cmax);
+  CASPR_COUNT(); colscale_kernel<<<ceil_div(l.cin_pad, 128), 128, 0, s>>>(cmax, l.colmax_splits, Cin, l.cin_pad, wscale, winv);
+  CASPR_COUNT(); transpose_split_kernel<<<dim3((unsigned)(l.r_pad / 64), l.cin_pad / 64), 256, 0, s>>>(
+      X, ldx, rows, Cin, l.r_pad, relu_x, wscale, whi, wlo);
+  CASPR_CHECK_LAUNCH();
+  CUtensorMap tm_ahi, tm_alo, tm_whi, tm_wlo;
+  bool ok = true;
+  ok &= caspr_make_tmap_f16(&tm_ahi, ahi, (uint64_t)l.cout_pad, (uint64_t)l.r_pad, kBM);
+  ok &= caspr_make_tmap_f16(&tm_alo, alo, (uint64_t)l.cout_pad, (uint64_t)l.r_pad, kBM);
+  ok &= caspr_make_tmap_f16(&tm_whi, whi, (uint64_t)l.cin_pad, (uint64_t)l.r_pad, kBN);
+  ok &= caspr_make_tmap_f16(&tm_wlo, wlo, (uint64_t)l.cin_pad, (uint64_t)l.r_pad, kBN);
+  if (!ok) return CASPR_ELAUNCH;
+  if (!g_wgrad_attr_set) {
+    if (cudaFuncSetAttribute(tcg::gemm_fp16x3_kernel<WgradEpilogue>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             tcg::kSmemBytes) != cudaSuccess)
+      return CASPR_ELAUNCH;
+    g_wgrad_attr_set = true;
+  }
+  int dev = 0, num_sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return CASPR_ELAUNCH;
+  const int m_tiles = l.cout_pad / kBM, n_tiles = l.cin_pad / kBN;
+  WgradEpilogue epi{};
+  epi.a_inv = ainv; epi.w_inv = winv; epi.part = part; epi.cout = Cout; epi.cin = Cin; epi.m_tiles = m_tiles;
+  long long grid = (long long)m_tiles * n_tiles * l.k_splits;
+  if (grid > num_sms) grid = num_sms;
+  CASPR_COUNT(); tcg::gemm_fp16x3_kernel<WgradEpilogue><<<(int)grid, tcg::kThreads, tcg::kSmemBytes, s>>>(
+      tm_ahi, tm_alo, tm_whi, tm_wlo, tm_ahi, tm_alo, 0, m_tiles, n_tiles, l.k_chunks, nullptr, epi, l.k_splits);
+  const size_t nelem = (size_t)Cout * Cin;
+  CASPR_COUNT(); wgrad_sum_parts_kernel<<<(unsigned)((nelem + 255) / 256), 256, 0, s>>>(part, l.k_splits, nelem, dW);
+  CASPR_CHECK_LAUNCH();
+  return CASPR_OK;
+}
+
+namespace {
 }  // namespace
 
 extern "C" size_t caspr_linear_tc_workspace_bytes(int rows, int Cin, int Cout) {

@@ -42,7 +42,7 @@ gemm_fp16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                    const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                    const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
                    int m_tile0, int m_tiles, int n_tiles, int k_chunks, const int* __restrict__ skip_flag,
-                   Epilogue epi) {
+                   Epilogue epi, int k_splits = 1) {
   if (skip_flag && *skip_flag) return;       // device-side "solve finished" flag (CNF solver)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -55,7 +55,10 @@ gemm_fp16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = m_tiles * n_tiles;
+  // split-K (weight gradients): work item = (k split, row tile, column tile); split s covers the k-chunks
+  // [s*k_chunks, (s+1)*k_chunks) and the epilogue sees it as row tile m_tile + s*m_tiles (partial outputs stacked).
+  const int mn_tiles = m_tiles * n_tiles;
+  const int total_tiles = mn_tiles * k_splits;
 
   if (threadIdx.x == 0) {
     tc::prefetch_tmap(&tm_a_hi);
@@ -83,16 +86,18 @@ gemm_fp16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_local = tile / n_tiles, n_tile = tile - m_local * n_tiles;
+        const int split = tile / mn_tiles, mn = tile - split * mn_tiles;
+        const int m_local = mn / n_tiles, n_tile = mn - m_local * n_tiles;
         const int m_tile = m_tile0 + m_local;
+        const int kc0 = split * k_chunks;
         for (int kc = 0; kc < k_chunks; ++kc) {
           tc::mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sb = smem + stage * kStageBytes;
           tc::mbar_arrive_expect_tx(&full[stage], kStageBytes);
-          tc::tma_load_2d(sb, &tm_a_hi, &full[stage], kc * kBK, m_tile * kBM);
-          tc::tma_load_2d(sb + kATile, &tm_a_lo, &full[stage], kc * kBK, m_tile * kBM);
-          tc::tma_load_2d(sb + 2 * kATile, &tm_w_hi, &full[stage], kc * kBK, n_tile * kBN);
-          tc::tma_load_2d(sb + 2 * kATile + kWTile, &tm_w_lo, &full[stage], kc * kBK, n_tile * kBN);
+          tc::tma_load_2d(sb, &tm_a_hi, &full[stage], (kc0 + kc) * kBK, m_tile * kBM);
+          tc::tma_load_2d(sb + kATile, &tm_a_lo, &full[stage], (kc0 + kc) * kBK, m_tile * kBM);
+          tc::tma_load_2d(sb + 2 * kATile, &tm_w_hi, &full[stage], (kc0 + kc) * kBK, n_tile * kBN);
+          tc::tma_load_2d(sb + 2 * kATile + kWTile, &tm_w_lo, &full[stage], (kc0 + kc) * kBK, n_tile * kBN);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -135,8 +140,9 @@ gemm_fp16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     epi.setup(staging, &tm_o_hi, &tm_o_lo, (int)threadIdx.x - 64);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int m_local = tile / n_tiles, n_tile = tile - m_local * n_tiles;
-      const int m_tile = m_tile0 + m_local;
+      const int split = tile / mn_tiles, mn = tile - split * mn_tiles;
+      const int m_local = mn / n_tiles, n_tile = mn - m_local * n_tiles;
+      const int m_tile = m_tile0 + m_local + split * m_tiles;
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       epi.tile_begin(m_tile, n_tile, q, lane);

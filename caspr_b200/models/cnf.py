@@ -177,7 +177,7 @@ class _CnfBlockFunction(torch.autograd.Function):
         cnf.last_info = info
         if rc != 0:
             raise CasprError(rc, 'caspr_cnf_flow')
-        ctx.cnf, ctx.pack, ctx.end_time, ctx.params = cnf, pack, end_time, params
+        ctx.cnf, ctx.pack, ctx.end_time, ctx.params, ctx.engine = cnf, pack, end_time, params, engine
         ctx.save_for_backward(x1, logp1, e, context, sqrt_end_time)
         return x1, logp1
 
@@ -186,7 +186,8 @@ class _CnfBlockFunction(torch.autograd.Function):
         x1, logp1, e, context, sqrt_end_time = ctx.saved_tensors
         cnf = ctx.cnf
         gx0, glogp0, gctx, gpar, gtimes, info, rc = ops.cnf_adjoint(
-            x1, logp1, gx1.contiguous(), glogp1.contiguous(), e, context, ctx.pack, ctx.end_time, cnf.rtol, cnf.atol)
+            x1, logp1, gx1.contiguous(), glogp1.contiguous(), e, context, ctx.pack, ctx.end_time, cnf.rtol, cnf.atol,
+            engine=ctx.engine)
         cnf.last_adjoint_info = info
         if rc != 0:
             raise CasprError(rc, 'caspr_cnf_adjoint')

@@ -450,7 +450,7 @@ def cnf_param_count(pack):
     return int(lib.caspr_cnf_param_count(pack.struct.hidden, pack.struct.ctx_dim))
 
 
-def cnf_adjoint(x1, logp1, gx1, glogp1, e, ctx, pack, end_time, rtol=1e-5, atol=1e-5):
+def cnf_adjoint(x1, logp1, gx1, glogp1, e, ctx, pack, end_time, rtol=1e-5, atol=1e-5, engine=CNF_SIMT_FP32):
     """Adjoint backward of the CNF block (forward direction).  x1 (F,P,3), logp1 (F,P): block outputs at t1;
     gx1, glogp1: their gradients.  Returns gx0 (F,P,3), glogp0 (F,P), gctx (F,ctx), gparams (flat, ODEfunc
     parameters() order), gtimes (2,), info list, status."""
@@ -467,12 +467,12 @@ def cnf_adjoint(x1, logp1, gx1, glogp1, e, ctx, pack, end_time, rtol=1e-5, atol=
     info = torch.zeros(8, dtype=torch.int32, device=dev)
     h_info = (ctypes.c_int32 * 8)()
     ws_bytes = lib.caspr_cnf_adjoint_workspace_bytes(F, P, H, C)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    ws, ws_ptr = _aligned_bytes(ws_bytes, dev)
     _count('cnf_adjoint')
     rc = lib.caspr_cnf_adjoint(_p(x1), _p(logp1), _p(gx1), _p(glogp1), _p(e), _p(ctx), F, P,
-                               ctypes.byref(pack.struct), float(end_time), float(rtol), float(atol),
+                               ctypes.byref(pack.struct), float(end_time), float(rtol), float(atol), int(engine),
                                _p(gx0), _p(glogp0), _p(gctx), _p(gparams), _p(gtimes), _p(info), h_info,
-                               _p(ws), ws_bytes, _stream())
+                               ctypes.c_void_p(ws_ptr), ws_bytes, _stream())
     return gx0, glogp0, gctx, gparams, gtimes, list(h_info), rc
 
 

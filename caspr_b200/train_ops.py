@@ -79,8 +79,12 @@ def gn_backward(x, mr, samples, rows_per_sample, groups, gamma, beta, relu, d_ou
     return dx, dgamma, dbeta
 
 
-def linear_wgrad(d_y, x, relu_x=False, want_bias=True):
-    """dW (Cout,Cin) = d_y^T . act(x), db (Cout) = column sums of d_y."""
+WGRAD_ENGINE = 'auto'          # 'auto' | 'tc' | 'simt' (accuracy studies)
+
+
+def linear_wgrad(d_y, x, relu_x=False, want_bias=True, engine=None):
+    """dW (Cout,Cin) = d_y^T . act(x), db (Cout) = column sums of d_y.  Large layers (rows >= 2048, Cout, Cin >= 64)
+    run on the split-K tcgen05 fp16x3 GEMM, the rest on the exact-fp32 SIMT kernel."""
     d_y, lddy = _rows2d(d_y, 'd_y')
     x, ldx = _rows2d(x, 'x')
     rows, cout = d_y.shape
@@ -88,6 +92,19 @@ def linear_wgrad(d_y, x, relu_x=False, want_bias=True):
     assert x.shape[0] == rows
     dW = torch.empty(cout, cin, dtype=torch.float32, device=x.device)
     db = torch.empty(cout, dtype=torch.float32, device=x.device) if want_bias else None
+    engine = engine or WGRAD_ENGINE
+    if engine == 'auto':
+        engine = 'tc' if (rows >= 2048 and cout >= 64 and cin >= 64) else 'simt'
+    if engine == 'tc':
+        nb = lib.caspr_linear_wgrad_tc_workspace_bytes(rows, cout, cin)
+        buf = torch.empty(nb + 1024, dtype=torch.uint8, device=x.device)
+        ptr = (buf.data_ptr() + 1023) // 1024 * 1024
+        _count('linear_wgrad_tc')
+        check(lib.caspr_linear_wgrad_tc(_p(d_y), lddy, _p(x), ldx, rows, cout, cin, int(relu_x), _p(dW),
+                                        ctypes.c_void_p(ptr), nb, _stream()), 'caspr_linear_wgrad_tc')
+        if want_bias:
+            colsum(d_y, db)
+        return dW, db
     nb = lib.caspr_linear_wgrad_workspace_bytes(rows, cout, cin)
     ws = _ws(nb, x.device)
     _count('linear_wgrad')

@@ -249,13 +249,15 @@ int caspr_cnf_feval(const float* y, const float* e, const float* ctx, int frames
  *   gx0 (frames,pts,3), glogp0 (frames,pts), gctx (frames,ctx_dim): dL/d(x0), dL/d(logp0), dL/d(ctx);
  *   gparams: caspr_cnf_param_count(hidden, ctx_dim) floats in ODEfunc.parameters() order — per layer
  *            _layer.weight, _layer.bias, _hyper_bias.weight, _hyper_gate.weight, _hyper_gate.bias;
- *   gtimes (2 floats, device): dL/dt0, dL/dt1 (dL/d sqrt_end_time = 2 sqrt_end_time gtimes[1], cnf.py:89-91).
+ *   gtimes (2 floats, device): dL/dt0, dL/dt1 (dL/d sqrt_end_time = 2 sqrt_end_time gtimes[1], cnf.py:89-91);
+ *   engine: CASPR_CNF_SIMT_FP32 (exact fp32) or CASPR_CNF_TC_FP16X3 (all six H x H products of an evaluation —
+ *           forward, data gradient, weight gradient — on the tcgen05 fp16x3 GEMM); workspace 1024-byte aligned.
  * Synchronises `stream` once per attempted step (polls the device-side controller). */
 size_t caspr_cnf_param_count(int hidden, int ctx_dim);
 size_t caspr_cnf_adjoint_workspace_bytes(int frames, int pts, int hidden, int ctx_dim);
 int caspr_cnf_adjoint(const float* x1, const float* logp1, const float* gx1, const float* glogp1,
                       const float* e, const float* ctx, int frames, int pts,
-                      const caspr_cnf_weights* w, float end_time, float rtol, float atol,
+                      const caspr_cnf_weights* w, float end_time, float rtol, float atol, int engine,
                       float* gx0, float* glogp0, float* gctx, float* gparams, float* gtimes,
                       int32_t* info, int32_t* h_info, void* workspace, size_t workspace_bytes, void* stream);
 
@@ -303,6 +305,12 @@ int caspr_gn_backward(const float* dY, int lddy, const float* dMax, int ld_dmax,
 size_t caspr_linear_wgrad_workspace_bytes(long long rows, int Cout, int Cin);
 int caspr_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, long long rows, int Cout, int Cin,
                        int relu_x, float* dW, float* db, void* workspace, size_t workspace_bytes, void* stream);
+/* The same dW on the tensor cores: both operands are transposed into fp16 hi/lo planes with the ROW index as the
+ * contraction dimension (per-channel power-of-two scales), split-K tcgen05 fp16x3 GEMM (at most 4096 rows per
+ * split), ordered reduction of the partials.  Meant for Cout, Cin >= 64; workspace 1024-byte aligned. */
+size_t caspr_linear_wgrad_tc_workspace_bytes(long long rows, int Cout, int Cin);
+int caspr_linear_wgrad_tc(const float* dY, int lddy, const float* X, int ldx, long long rows, int Cout, int Cin,
+                          int relu_x, float* dW, void* workspace, size_t workspace_bytes, void* stream);
 /* out[c] (+)= sum_r X[r][c] (backward of the repeat at pointnet.py:44). */
 size_t caspr_colsum_workspace_bytes(long long rows, int C);
 int caspr_colsum(const float* X, int ldx, long long rows, int C, float* out, int accumulate, void* workspace,

@@ -46,25 +46,27 @@ def test_cnf_adjoint_matches_oracle(weights):
     model.load_state_dict(weights)
     cnf = model.point_cnf.chain[1]
     pack, T = cnf.weight_pack(), cnf.end_time()
-    for engine in (ops.CNF_SIMT_FP32, ops.CNF_TC_FP16X3):
+    # exact-fp32 engine: a fraction of the solver tolerance; tcgen05 fp16x3 engine: three fp16 products per MAC and
+    # truncating fp32 accumulation in TMEM, measured 3e-4 on these gradients (same accept / reject trace)
+    for engine, tol in ((ops.CNF_SIMT_FP32, 2e-4), (ops.CNF_TC_FP16X3, 1e-3)):
         x1, lp1, info, rc = ops.cnf_flow(x.cuda(), torch.zeros(F_, P_, device='cuda'), e.cuda(), ctx.cuda(), pack, None,
                                          None, T, False, 1e-5, 1e-5, engine)
         assert rc == 0 and _rel(x1, y.detach()) < 1e-4
         gx0, gl0, gctx, gpar, gt, info, rc = ops.cnf_adjoint(x1, lp1, gx1.cuda(), gl1.cuda(), e.cuda(), ctx.cuda(),
-                                                             pack, T)
+                                                             pack, T, engine=engine)
         assert rc == 0
         assert info[2] + info[3] == len(log) and info[2] == sum(1 for s in log if s[2])    # same accept / reject trace
-        assert _rel(gx0, xo.grad) < 2e-4
+        assert _rel(gx0, xo.grad) < tol
         assert _rel(gl0, lo.grad.squeeze(-1)) < 1e-5
-        assert _rel(gctx, co.grad) < 2e-4
+        assert _rel(gctx, co.grad) < tol
         off = 0
         for name in orc._cnf_func.names:
             ref = orc.sd[name].grad
-            assert _rel(gpar[off:off + ref.numel()].view_as(ref), ref) < 2e-4, name
+            assert _rel(gpar[off:off + ref.numel()].view_as(ref), ref) < tol, name
             off += ref.numel()
         assert off == gpar.numel()
         s = orc.sd['point_cnf.chain.1.sqrt_end_time']
-        assert abs(float(gt[1]) * 2 * float(s) - float(s.grad)) < 2e-4 * abs(float(s.grad))
+        assert abs(float(gt[1]) * 2 * float(s.detach()) - float(s.grad)) < tol * abs(float(s.grad))
 
 
 @pytest.mark.parametrize('B,T', [(5, 5), (1, 2), (9, 10)])

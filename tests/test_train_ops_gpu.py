@@ -58,16 +58,18 @@ def test_groupnorm_forward_backward(tops, samples, rps, C, relu):
     assert _rel(dbeta, bd.grad) < 2e-4
 
 
-@pytest.mark.parametrize('rows,cin,cout', [(5000, 9, 16), (4096, 99, 32), (777, 515, 256), (20480, 1600, 1600), (3000, 64, 4)])
+@pytest.mark.parametrize('rows,cin,cout', [(5000, 9, 16), (4096, 99, 32), (777, 515, 256), (20480, 1600, 1600), (3000, 64, 4), (81920, 512, 512)])
 def test_linear_wgrad(tops, rows, cin, cout):
     g = torch.Generator().manual_seed(rows)
     x = torch.randn(rows, cin + 3, generator=g).cuda()[:, 1:1 + cin]
     dy = torch.randn(rows, cout, generator=g).cuda()
-    dW, db = tops.linear_wgrad(dy, x)
-    assert _rel(dW, dy.double().t() @ x.double()) < 1e-5
-    assert _rel(db, dy.double().sum(0)) < 1e-5
-    dW2, _ = tops.linear_wgrad(dy, x, relu_x=True)
-    assert _rel(dW2, dy.double().t() @ x.double().clamp_min(0)) < 1e-5
+    ref = dy.double().t() @ x.double()
+    for engine, tol in (('simt', 1e-5), ('tc', 3e-5)):
+        dW, db = tops.linear_wgrad(dy, x, engine=engine)
+        assert _rel(dW, ref) < tol, engine
+        assert _rel(db, dy.double().sum(0)) < 1e-5
+        dW2, _ = tops.linear_wgrad(dy, x, relu_x=True, engine=engine)
+        assert _rel(dW2, dy.double().t() @ x.double().clamp_min(0)) < tol, engine
 
 
 def test_gather_backwards(tops):
