@@ -264,13 +264,23 @@ colmax_partial_kernel(const float* __restrict__ X, int ldx, long long rows, int 
   if (c >= C) return;
   const long long r0 = blockIdx.y * rows_per_split;
   const long long r1 = r0 + rows_per_split < rows ? r0 + rows_per_split : rows;
-  float m = 0.f;
-  for (long long r = r0; r < r1; ++r) {
-    float v = X[r * ldx + c];
-    if (relu) v = fmaxf(v, 0.f);
-    m = fmaxf(m, fabsf(v));
+  // eight independent loads in flight per thread; with relu the negative values count as 0
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = 0.f;
+  long long r = r0;
+  for (; r + 7 < r1; r += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = X[(r + j) * ldx + c];
+      m[j] = fmaxf(m[j], relu ? v : fabsf(v));
+    }
   }
-  partial[(size_t)blockIdx.y * C + c] = m;
+  for (; r < r1; ++r) {
+    const float v = X[r * ldx + c];
+    m[0] = fmaxf(m[0], relu ? v : fabsf(v));
+  }
+  partial[(size_t)blockIdx.y * C + c] = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
 }
 // scale[c] = 2^(14-e), inv[c] = 2^(e-14) with max|column| < 2^e; padded channels get 0
 __global__ void colscale_kernel(const float* __restrict__ partial, int nsplit, int C, int C_pad, float* __restrict__ scale,
@@ -362,11 +372,18 @@ WgradLayout make_wgrad_layout(long long rows, int cout, int cin) {
   long long splits = (chunks_total + 63) / 64;
   const long long tiles = (long long)(l.cout_pad / kBM) * (l.cin_pad / kBN);
   while (splits * tiles < 148 && splits < chunks_total) ++splits;
+  {
+    // fill whole waves of 148 CTAs: as many splits as fit into the number of waves the minimum needs
+    const long long waves = (splits * tiles + 147) / 148;
+    long long cand = waves * 148 / tiles;
+    if (cand > chunks_total) cand = chunks_total;
+    if (cand > splits) splits = cand;
+  }
   l.k_splits = (int)splits;
   l.k_chunks = (int)((chunks_total + splits - 1) / splits);
   l.r_pad = (long long)l.k_splits * l.k_chunks * kBK;
-  long long cs = (2 * 148) / ((cout > cin ? cout : cin) / 128 + 1);
-  const long long maxs = (rows + 255) / 256;
+  long long cs = (8 * 148) / ((cout > cin ? cout : cin) / 128 + 1);
+  const long long maxs = (rows + 127) / 128;
   if (cs > maxs) cs = maxs;
   if (cs < 1) cs = 1;
   l.colmax_splits = (int)cs;
