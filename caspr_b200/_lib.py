@@ -33,6 +33,14 @@ class GnStats(Structure):
     _fields_ = [('stats', c_void_p), ('rows_per_sample', c_int), ('groups', c_int)]
 
 
+ALLREDUCE_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_int, c_void_p, c_void_p)
+
+
+class CnfSync(Structure):
+    _fields_ = [('n_global', ctypes.c_longlong), ('stage', c_void_p), ('allreduce_sum', ALLREDUCE_FN),
+                ('user', c_void_p)]
+
+
 class MbnParams(Structure):
     _fields_ = [('weight', c_void_p), ('bias', c_void_p), ('running_mean', c_void_p),
                 ('running_var', c_void_p)]
@@ -76,6 +84,9 @@ SIGNATURES = {
     'caspr_cnf_flow': (c_int, [_P, _P, _P, _P, c_int, c_int, POINTER(CnfWeights), POINTER(MbnParams),
                                POINTER(MbnParams), c_float, c_int, c_float, c_float, c_int, _P, _P, _P,
                                POINTER(c_int32), _P, c_size_t, _P]),
+    'caspr_cnf_flow_lockstep': (c_int, [_P, _P, _P, _P, c_int, c_int, POINTER(CnfWeights), POINTER(MbnParams),
+                                        POINTER(MbnParams), c_float, c_int, c_float, c_float, c_int, _P, _P, _P,
+                                        POINTER(c_int32), _P, c_size_t, _P, POINTER(CnfSync)]),
     'caspr_cnf_feval': (c_int, [_P, _P, _P, c_int, c_int, POINTER(CnfWeights), c_float, c_int, _P, _P,
                                 _P, c_size_t, _P]),
     'caspr_cnf_param_count': (c_size_t, [c_int, c_int]),

@@ -35,12 +35,27 @@ extern "C" size_t caspr_cnf_workspace_bytes(int frames, int pts, int hidden, int
   return carve(nullptr, frames, pts, hidden).bytes;
 }
 
-extern "C" int caspr_cnf_flow(const float* x_in, const float* logp_in, const float* e, const float* ctx,
-                              int frames, int pts, const caspr_cnf_weights* cw,
-                              const caspr_mbn_params* mbn0, const caspr_mbn_params* mbn2,
-                              float end_time, int reverse, float rtol, float atol, int engine,
-                              float* x_out, float* logp_out, int32_t* info, int32_t* h_info,
-                              void* workspace, size_t workspace_bytes, void* stream) {
+namespace {
+
+// Lock-step step control over ranks: sum the two error-ratio accumulators (CnfState.sum_x, sum_l: adjacent doubles)
+// over all ranks before the controller looks at them.  The library stays free of NCCL: the sums are staged in a
+// caller-owned device buffer and the caller's hook performs the all-reduce on `stream`.
+int sync_sums(const caspr_cnf_sync* sync, CnfState* st, cudaStream_t s) {
+  if (!sync) return CASPR_OK;
+  if (cudaMemcpyAsync(sync->stage, &st->sum_x, 2 * sizeof(double), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+    return CASPR_ELAUNCH;
+  if (sync->allreduce_sum(sync->stage, 2, sync->user, (void*)s) != 0) return CASPR_ELAUNCH;
+  if (cudaMemcpyAsync(&st->sum_x, sync->stage, 2 * sizeof(double), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+    return CASPR_ELAUNCH;
+  return CASPR_OK;
+}
+
+int cnf_flow_impl(const float* x_in, const float* logp_in, const float* e, const float* ctx,
+                  int frames, int pts, const caspr_cnf_weights* cw,
+                  const caspr_mbn_params* mbn0, const caspr_mbn_params* mbn2,
+                  float end_time, int reverse, float rtol, float atol, int engine,
+                  float* x_out, float* logp_out, int32_t* info, int32_t* h_info,
+                  void* workspace, size_t workspace_bytes, void* stream, const caspr_cnf_sync* sync) {
   CASPR_REQUIRE(x_in && e && ctx && x_out && info && h_info && workspace);
   CASPR_REQUIRE(frames > 0 && pts > 0 && (long long)frames * pts < (1ll << 30));
   CASPR_REQUIRE(weights_ok(cw));
@@ -91,8 +106,12 @@ extern "C" int caspr_cnf_flow(const float* x_in, const float* logp_in, const flo
   }
   rc = enqueue_stages(w, cw, e, frames, pts, 0, 0, reverse, engine, &plan, num_sms, s);
   if (rc) return rc;
+  // number of points the controller's means run over: this rank's, or all ranks' in lock-step mode
+  const int n_ctrl = sync ? (int)sync->n_global : n;
   CASPR_COUNT(); cnf_init_norm_kernel<<<eb, 256, 0, s>>>(w.y0, w.kbuf, n, rtol, atol, w.st);
-  CASPR_COUNT(); cnf_init_controller_kernel<<<1, 1, 0, s>>>(w.st, n, t_start, t_stop);
+  rc = sync_sums(sync, w.st, s);
+  if (rc) return rc;
+  CASPR_COUNT(); cnf_init_controller_kernel<<<1, 1, 0, s>>>(w.st, n_ctrl, t_start, t_stop);
   CASPR_CHECK_LAUNCH();
 
   const int have_logp = logp_in != nullptr;
@@ -108,7 +127,9 @@ extern "C" int caspr_cnf_flow(const float* x_in, const float* logp_in, const flo
       rc = enqueue_stages(w, cw, e, frames, pts, 1, 6, reverse, engine, &plan, num_sms, s);
       if (rc) return rc;
       CASPR_COUNT(); cnf_error_kernel<<<eb, 256, 0, s>>>(w.y0, w.kbuf, (size_t)n, n, rtol, atol, w.st, w.y1);
-      CASPR_COUNT(); cnf_controller_kernel<<<1, 1, 0, s>>>(w.st, n, step_id);
+      rc = sync_sums(sync, w.st, s);
+      if (rc) return rc;
+      CASPR_COUNT(); cnf_controller_kernel<<<1, 1, 0, s>>>(w.st, n_ctrl, step_id);
       CASPR_COUNT(); cnf_finalize_kernel<<<eb, 256, 0, s>>>(w.y0, w.kbuf, (size_t)n, w.y1, n, step_id, w.st, post, reverse,
                                              have_logp, x_out, logp_out);
       CASPR_CHECK_LAUNCH();
@@ -135,6 +156,31 @@ extern "C" int caspr_cnf_flow(const float* x_in, const float* logp_in, const flo
     return CASPR_ELAUNCH;
   if (cudaStreamSynchronize(s) != cudaSuccess) return CASPR_ELAUNCH;
   return hst.status;
+}
+
+}  // namespace
+
+extern "C" int caspr_cnf_flow(const float* x_in, const float* logp_in, const float* e, const float* ctx,
+                              int frames, int pts, const caspr_cnf_weights* cw,
+                              const caspr_mbn_params* mbn0, const caspr_mbn_params* mbn2,
+                              float end_time, int reverse, float rtol, float atol, int engine,
+                              float* x_out, float* logp_out, int32_t* info, int32_t* h_info,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  return cnf_flow_impl(x_in, logp_in, e, ctx, frames, pts, cw, mbn0, mbn2, end_time, reverse, rtol, atol, engine,
+                       x_out, logp_out, info, h_info, workspace, workspace_bytes, stream, nullptr);
+}
+
+extern "C" int caspr_cnf_flow_lockstep(const float* x_in, const float* logp_in, const float* e, const float* ctx,
+                                       int frames, int pts, const caspr_cnf_weights* cw,
+                                       const caspr_mbn_params* mbn0, const caspr_mbn_params* mbn2,
+                                       float end_time, int reverse, float rtol, float atol, int engine,
+                                       float* x_out, float* logp_out, int32_t* info, int32_t* h_info,
+                                       void* workspace, size_t workspace_bytes, void* stream,
+                                       const caspr_cnf_sync* sync) {
+  CASPR_REQUIRE(sync && sync->allreduce_sum && sync->stage && sync->n_global >= (long long)frames * pts &&
+                sync->n_global < (1ll << 30));
+  return cnf_flow_impl(x_in, logp_in, e, ctx, frames, pts, cw, mbn0, mbn2, end_time, reverse, rtol, atol, engine,
+                       x_out, logp_out, info, h_info, workspace, workspace_bytes, stream, sync);
 }
 
 extern "C" int caspr_cnf_feval(const float* y, const float* e, const float* ctx, int frames, int pts,

@@ -93,8 +93,17 @@ class CaSPR(nn.Module):
         z_global = z_global.unsqueeze(1).expand(B, T, z_global.size(1))
         return torch.cat([sample_feats, z_global], dim=2)
 
+    lockstep_group = False      # set by sharding.lockstep(): ranks of this group share one latent step sequence
+
     def gen_latent(self, z0, timestamps):
-        return self.latent_ode(z0, timestamps)
+        if self.lockstep_group is False:
+            return self.latent_ode(z0, timestamps)
+        # lock-step over a sharded batch: the latent controller is batch-global, the state is tiny (B x 64), so
+        # every rank solves the FULL batch (all-gather of z0) and keeps its own rows: identical step decisions
+        import torch.distributed as dist
+        from ..sharding import gather_rows
+        full, lo, hi = gather_rows(z0.contiguous(), self.lockstep_group)
+        return self.latent_ode(full, timestamps)[lo:hi]
 
     def get_nfe(self):
         return np.array([count_nfe(self.latent_ode), count_nfe(self.point_cnf)])

@@ -204,6 +204,7 @@ class SequentialFlow(nn.Module):
     """chain = [MovingBatchNorm1d, CNF x num_blocks, MovingBatchNorm1d] (flow.py:67-74)."""
 
     engine = ops.CNF_TC_FP16X3      # tcgen05 fp16x3 engine; ops.CNF_SIMT_FP32 is the exact-fp32 SIMT engine
+    lockstep_group = False          # set by sharding.lockstep(): process group whose ranks share one step sequence
 
     def __init__(self, layer_list, use_bn=True):
         super(SequentialFlow, self).__init__()
@@ -247,8 +248,14 @@ class SequentialFlow(nn.Module):
             cnf.odefunc.before_odeint(e)
             noise = e if e is not None else torch.randn_like(x)
             rtol, atol = (cnf.rtol, cnf.atol) if self.training else (cnf.test_rtol, cnf.test_atol)
+            sync = None
+            if self.lockstep_group is not False:
+                import torch.distributed as dist
+                n_all = torch.tensor([F * P], dtype=torch.int64, device=x.device)
+                dist.all_reduce(n_all, group=self.lockstep_group)
+                sync = ops.LockstepSync(int(n_all.item()), x.device, self.lockstep_group)
             x_out, logp_out, info, rc = ops.cnf_flow(x, logp, noise, context, cnf.weight_pack(), mbn0, mbn2,
-                                                     cnf.end_time(), reverse, rtol, atol, self.engine)
+                                                     cnf.end_time(), reverse, rtol, atol, self.engine, sync=sync)
             cnf.odefunc._num_evals += float(info[1])
             self.last_info = info
             if rc != 0:

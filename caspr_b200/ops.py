@@ -407,9 +407,31 @@ def _mbn_struct(m):
     return s, keep
 
 
-def cnf_flow(x, logp, e, ctx, pack, mbn0, mbn2, end_time, reverse, rtol=1e-5, atol=1e-5, engine=CNF_SIMT_FP32):
+class LockstepSync(object):
+    """Step-control synchronisation over the ranks of `group` for caspr_cnf_flow_lockstep: holds the staging buffer
+    and the ctypes callback that all-reduces it with torch.distributed on the current stream."""
+
+    def __init__(self, n_global, device, group=None):
+        import torch.distributed as dist
+        self.stage = torch.zeros(2, dtype=torch.float64, device=device)
+        self.calls = 0
+
+        def _allreduce(ptr, count, user, stream):
+            try:
+                assert ptr == self.stage.data_ptr() and count == 2
+                dist.all_reduce(self.stage, op=dist.ReduceOp.SUM, group=group)
+                self.calls += 1
+                return 0
+            except Exception:            # never unwind through the C frames
+                return 1
+        self._cb = _lib.ALLREDUCE_FN(_allreduce)
+        self.struct = _lib.CnfSync(int(n_global), self.stage.data_ptr(), self._cb, None)
+
+
+def cnf_flow(x, logp, e, ctx, pack, mbn0, mbn2, end_time, reverse, rtol=1e-5, atol=1e-5, engine=CNF_SIMT_FP32,
+             sync=None):
     """One pass through [MBN, CNF, MBN] (or its inverse).  x (F,P,3), logp (F,P) or None, e (F,P,3),
-    ctx (F,ctx_dim).  Returns x_out, logp_out (or None), info list, status."""
+    ctx (F,ctx_dim).  Returns x_out, logp_out (or None), info list, status.  sync: LockstepSync or None."""
     x, e, ctx = _f32(x, 'x').contiguous(), _f32(e, 'e').contiguous(), _f32(ctx, 'ctx').contiguous()
     F, P, _ = x.shape
     if logp is not None:
@@ -423,11 +445,14 @@ def cnf_flow(x, logp, e, ctx, pack, mbn0, mbn2, end_time, reverse, rtol=1e-5, at
     s0, k0 = _mbn_struct(mbn0)
     s2, k2 = _mbn_struct(mbn2)
     _count('cnf_flow')
-    rc = lib.caspr_cnf_flow(_p(x), _p(logp), _p(e), _p(ctx), F, P, ctypes.byref(pack.struct),
-                            ctypes.byref(s0) if s0 is not None else None,
-                            ctypes.byref(s2) if s2 is not None else None,
-                            float(end_time), int(bool(reverse)), float(rtol), float(atol), int(engine),
-                            _p(x_out), _p(logp_out), _p(info), h_info, _p(ws), ws_bytes, _stream())
+    args = (_p(x), _p(logp), _p(e), _p(ctx), F, P, ctypes.byref(pack.struct),
+            ctypes.byref(s0) if s0 is not None else None, ctypes.byref(s2) if s2 is not None else None,
+            float(end_time), int(bool(reverse)), float(rtol), float(atol), int(engine),
+            _p(x_out), _p(logp_out), _p(info), h_info, _p(ws), ws_bytes, _stream())
+    if sync is not None:
+        rc = lib.caspr_cnf_flow_lockstep(*args, ctypes.byref(sync.struct))
+    else:
+        rc = lib.caspr_cnf_flow(*args)
     del k0, k2
     return x_out, logp_out, list(h_info), rc
 

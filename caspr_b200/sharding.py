@@ -39,6 +39,42 @@ def gather_batch(local, n_items, group=None):
     return torch.cat([b[:hi - lo] for b, (lo, hi) in zip(bufs, sizes)], dim=0)
 
 
+def gather_rows(local, group=None):
+    """All-gather row blocks of possibly different sizes: returns (all rows in rank order, lo, hi) with
+    full[lo:hi] == local."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c.item()) for c in counts]
+    pad = torch.zeros((max(counts),) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    lo = sum(counts[:rank])
+    return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0), lo, lo + counts[rank]
+
+
+class lockstep(object):
+    """Context manager: inside it the adaptive solvers of `model` take their step decisions over ALL ranks of `group`
+    (one all-reduce of two doubles per attempted CNF step, full-batch latent solve), so a sharded batch follows the
+    step sequence of the unsharded batch ("lock-step").  Every rank must own at least one sequence
+    and make the same sequence of model calls."""
+
+    def __init__(self, model, group=None):
+        self.model, self.group = model, group
+
+    def __enter__(self):
+        self.model.lockstep_group = self.group
+        self.model.point_cnf.lockstep_group = self.group
+        return self
+
+    def __exit__(self, *exc):
+        self.model.lockstep_group = False
+        self.model.point_cnf.lockstep_group = False
+        return False
+
+
 def reconstruct_sharded(model, x, gather=True, group=None, **kwargs):
     """``model.reconstruct`` over this rank's slice of the batch.  Per-sequence keyword tensors ``y`` (base
     samples) and ``e`` (Hutchinson noise) given for the FULL batch are sliced consistently.

@@ -232,6 +232,25 @@ int caspr_cnf_flow(const float* x_in, const float* logp_in, const float* e, cons
                    float* x_out, float* logp_out, int32_t* info, int32_t* h_info,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* Lock-step step control for a batch sharded over ranks: torchdiffeq's controller takes the mean
+ * error ratio over the WHOLE state tensor, so an unsharded batch shares one step sequence.  With this variant every
+ * rank sums its two error-ratio accumulators with all other ranks before each accept / reject decision (and in the
+ * initial-step heuristic), which reproduces the unsharded step sequence.  The library does not link NCCL: the two
+ * doubles are staged in `stage` (device, caller-owned) and `allreduce_sum(stage, 2, user, stream)` must enqueue an
+ * in-place sum all-reduce on `stream` and return 0.  n_global = total number of points over all ranks. */
+typedef struct {
+  long long n_global;
+  double* stage;
+  int (*allreduce_sum)(double* device_values, int count, void* user, void* stream);
+  void* user;
+} caspr_cnf_sync;
+int caspr_cnf_flow_lockstep(const float* x_in, const float* logp_in, const float* e, const float* ctx,
+                            int frames, int pts, const caspr_cnf_weights* w,
+                            const caspr_mbn_params* mbn0, const caspr_mbn_params* mbn2,
+                            float end_time, int reverse, float rtol, float atol, int engine,
+                            float* x_out, float* logp_out, int32_t* info, int32_t* h_info,
+                            void* workspace, size_t workspace_bytes, void* stream, const caspr_cnf_sync* sync);
+
 /* One dynamics evaluation (dy, -div) = ODEfunc(t, (y, logp, ctx)) for testing/profiling:
  * y (frames,pts,3), e (frames,pts,3) -> dy (frames,pts,3), neg_div (frames,pts). */
 int caspr_cnf_feval(const float* y, const float* e, const float* ctx, int frames, int pts,

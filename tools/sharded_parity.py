@@ -9,7 +9,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from caspr_b200.models import CaSPR                          # noqa: E402
-from caspr_b200.sharding import reconstruct_sharded          # noqa: E402
+from caspr_b200.sharding import reconstruct_sharded, lockstep          # noqa: E402
 from caspr_b200.synth import synthetic_state_dict, synthetic_sequences   # noqa: E402
 
 
@@ -36,6 +36,18 @@ def main():
         print('world %d: sharded vs unsharded rec_x max rel %.3e, tnocs identical %s, nfe full %s shard(rank0) %s'
               % (world, err_x, same_tnocs, nfe_full, nfe_shard))
         assert err_x < 1e-4 and same_tnocs
+    # lock-step mode: shared step decisions -> the step sequence (NFE) of the unsharded batch on every rank
+    with lockstep(model):
+        shard_ls = reconstruct_sharded(model, x, num_points=P, y=y, e=e)
+    nfe_ls = model.get_nfe()
+    err_ls = float((full[2] - shard_ls[2]).abs().max() / full[2].abs().max())
+    nfe_all = [None] * world
+    dist.all_gather_object(nfe_all, [int(v) for v in nfe_ls])
+    if rank == 0:
+        print('lock-step: sharded vs unsharded rec_x max rel %.3e, nfe per rank %s (unsharded %s)'
+              % (err_ls, nfe_all, [int(v) for v in nfe_full]))
+        assert all(v == [int(q) for q in nfe_full] for v in nfe_all)
+        assert err_ls < 2e-5
     dist.destroy_process_group()
 
 
