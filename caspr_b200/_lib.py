@@ -115,6 +115,8 @@ SIGNATURES = {
     'caspr_three_interp_bwd': (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, _P]),
     'caspr_rows_update': (c_int, [_P, c_int, c_longlong, c_int, c_int, _P, c_int, _P, c_int, _P]),
     'caspr_transpose': (c_int, [_P, c_int, c_int, _P, _P]),
+    'caspr_assemble_batch': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int, c_double, c_int,
+                                     _P, _P, _P]),
     'caspr_chamfer': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P]),
 }
 

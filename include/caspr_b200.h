@@ -346,6 +346,21 @@ int caspr_rows_update(const float* src, int ld_src, long long rows, int C, int a
 /* dst (cols,rows) = src (rows,cols)^T, contiguous. */
 int caspr_transpose(const float* src, int rows, int cols, float* dst, void* stream);
 
+/* ------------------------------------------------------------ input pipeline -> device (next row)
+ * Batch assembly of data/caspr_dataset.py:148-208 (load_seq_path) and :288-325 (DynamicPCLDataset.__getitem__) for
+ * frames the host has already decoded: nocs / depth are the raw float64 points of all frames of all B sequences
+ * back to back ((total,3) each; depth = nocs where a frame has no depth data, :174-176), frame_off (B*Tfull+1) the
+ * point offsets of the frames, n_valid[b] the number of frames before the first blank one (:183-186; later frames
+ * stay zero).  steps (B,T): chosen time steps (sorted, as :296); pts (B,Tp,N), Tp = 1 or T: chosen point indices into
+ * the frame padded to expected_num_pts by cycling its points (:188-195).  Outputs (B,T,N,4) float32:
+ * input_out = [depth xyz | max_timestamp*step/(Tfull-1)], output_out = [nocs xyz | step/(Tfull-1)], time stamps formed
+ * in float64 like numpy, optionally shifted so each item starts at 0 (:319-322). */
+int caspr_assemble_batch(const double* nocs, const double* depth, const long long* frame_off,
+                         const int32_t* n_valid, int B, int Tfull, int expected_num_pts,
+                         const int32_t* steps, int T, const int32_t* pts, int Tp, int N,
+                         double max_timestamp, int shift_time_to_zero, float* input_out,
+                         float* output_out, void* stream);
+
 /* -------------------------------------------------------------------- metric
  * Symmetric squared-NN Chamfer distance (reference utils/evaluations.py:40-43 via
  * tk3dv ChamferDistance): a (B,P,3), b (B,Q,3) -> d_ab (B,P) min sq dist a->b, d_ba (B,Q). */
