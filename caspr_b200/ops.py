@@ -511,3 +511,17 @@ def chamfer(a, b):
     _count('chamfer')
     check(lib.caspr_chamfer(_p(a), _p(b), B, P, Q, _p(d_ab), _p(d_ba), _stream()), 'caspr_chamfer')
     return d_ab, d_ba
+
+
+def emd(a, b):
+    """Approximate earth mover's distance (utils/emd.py earth_mover_distance with transpose=False): a (B,n,3),
+    b (B,m,3) -> cost (B,); evaluations.py:45-46 divides it by the number of points."""
+    a, b = _f32(a, 'a').contiguous(), _f32(b, 'b').contiguous()
+    B, n, _ = a.shape
+    m = b.shape[1]
+    cost = torch.empty(B, dtype=torch.float32, device=a.device)
+    nb = lib.caspr_emd_workspace_bytes(B, n, m)
+    ws = torch.empty(nb, dtype=torch.uint8, device=a.device)
+    _count('emd')
+    check(lib.caspr_emd(_p(a), _p(b), B, n, m, _p(cost), _p(ws), nb, _stream()), 'caspr_emd')
+    return cost

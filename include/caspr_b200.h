@@ -367,6 +367,13 @@ int caspr_assemble_batch(const double* nocs, const double* depth, const long lon
 int caspr_chamfer(const float* a, const float* b, int B, int P, int Q,
                   float* d_ab, float* d_ba, void* stream);
 
+/* Approximate earth mover's distance (reference utils/emd.py:11-12 -> emd_cuda approxmatch_forward + matchcost_forward,
+ * evaluations.py:45-46): xyz1 (B,n,3), xyz2 (B,m,3) -> cost (B) = sum of match(k,l) |p_k - q_l| after the ten
+ * annealing levels of the published approxmatch algorithm (oracle/emd_oracle.py).  The match matrix is never stored. */
+size_t caspr_emd_workspace_bytes(int B, int n, int m);
+int caspr_emd(const float* xyz1, const float* xyz2, int B, int n, int m, float* cost, void* workspace,
+              size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -104,3 +104,23 @@ def test_oracle_matches_live_reference_modules():
         z0_ref, tn_ref = ref.encode(x)
     z0, tn = CasprOracle(sd).encode(x)
     assert _rel(z0, z0_ref) < 1e-5 and _rel(tn, tn_ref) < 1e-5
+
+
+def test_emd_oracle_properties():
+    """The approximate-EMD restatement (third-party algorithm, parity unpinned): exact on a permuted copy, the
+    translation cost of a rigid shift, and agreement with the exact assignment on a small well-separated set."""
+    from oracle.emd_oracle import approx_emd
+    rng = np.random.default_rng(0)
+    a = rng.random((2, 256, 3)) - 0.5
+    perm = rng.permutation(256)
+    assert approx_emd(a, a[:, perm]).max() / 256 < 1e-4
+    shift = np.array([0.003, -0.002, 0.001])
+    c = approx_emd(a, a[:, perm] + shift) / 256
+    assert np.allclose(c, np.linalg.norm(shift), rtol=0.02)
+    from scipy.optimize import linear_sum_assignment
+    p, q = rng.random((1, 64, 3)), rng.random((1, 64, 3))
+    d = np.linalg.norm(p[0][:, None] - q[0][None], axis=-1)
+    r, cidx = linear_sum_assignment(d)
+    exact = d[r, cidx].sum()
+    approx = approx_emd(p, q)[0]
+    assert exact <= approx * 1.001 and approx < 1.35 * exact

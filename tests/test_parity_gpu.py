@@ -264,6 +264,34 @@ def test_chamfer(ops):
     assert _rel(cd, chamfer_distance(a, b)) < 1e-5
 
 
+@pytest.mark.parametrize('n,m', [(512, 512), (700, 350), (300, 900), (2048, 2048)])
+def test_emd_matches_oracle(ops, n, m):
+    """Approximate EMD (evaluations.py:45-46) against the float64 restatement of the published approxmatch algorithm;
+    fp32 with fast exponentials: 2e-3 relative."""
+    from oracle.emd_oracle import approx_emd
+    g = torch.Generator().manual_seed(n + m)
+    a = torch.rand(2, n, 3, generator=g) - 0.5
+    b = a[:, torch.randperm(n, generator=g)[:m] % n] * 0.9 + 0.02 * torch.randn(2, m, 3, generator=g) \
+        if m <= n else torch.rand(2, m, 3, generator=g) - 0.5
+    cost = ops.emd(a.to(DEV), b.to(DEV)).cpu().double()
+    ref = torch.from_numpy(approx_emd(a.numpy(), b.numpy()))
+    assert _rel(cost, ref) < 2e-3
+
+
+def test_emd_properties(ops):
+    """Size-independent properties at the evaluation protocol's size (2048 points): a permuted copy costs ~0, a small
+    rigid shift of the same cloud costs ~ n * |shift| (the identity pairing is optimal), symmetry in the arguments."""
+    g = torch.Generator().manual_seed(5)
+    a = (torch.rand(3, 2048, 3, generator=g) - 0.5).to(DEV)
+    perm = torch.randperm(2048, generator=g).to(DEV)
+    assert float(ops.emd(a, a[:, perm]).max()) / 2048 < 1e-4
+    shift = torch.tensor([0.003, -0.002, 0.001], device=DEV)
+    c = ops.emd(a, a[:, perm] + shift) / 2048
+    assert torch.allclose(c, shift.norm().expand(3), rtol=0.05)
+    b = (torch.rand(3, 2048, 3, generator=g) - 0.5).to(DEV)
+    assert torch.allclose(ops.emd(a, b), ops.emd(b, a), rtol=0.05)
+
+
 # ---------------------------------------------------------------------------- model level
 @pytest.fixture(scope='module', params=['vig', 'def'])
 def case(request, golden_dir, lib_built):
