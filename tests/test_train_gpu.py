@@ -182,3 +182,39 @@ def test_training_reduces_loss(weights):
         opt.step()
         losses.append(float(loss.detach()))
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+
+
+def test_cnf_adjoint_directional_derivative_at_full_size(weights):
+    """Size-independent property at the config-5 per-GPU size (8 x 5 frames x 1024 points): the adjoint's context
+    gradient predicts the change of S = sum(x1 . gx + logp1 . gl) along a random direction (central difference of two
+    exact-fp32 forward solves).  Finite differences of an adaptive solve at rtol 1e-5: 2e-2 relative."""
+    from caspr_b200 import ops
+    from caspr_b200.models import CaSPR
+    F_, P_ = 40, 1024
+    g = torch.Generator().manual_seed(11)
+    x = (torch.randn(F_, P_, 3, generator=g) * 0.3).cuda()
+    e = torch.randn(F_, P_, 3, generator=g).cuda()
+    ctx = (torch.randn(F_, 1600, generator=g) * 0.5).cuda()
+    gx = torch.randn(F_, P_, 3, generator=g).cuda()
+    gl = torch.randn(F_, P_, generator=g).cuda()
+    d = torch.randn(F_, 1600, generator=g).cuda()
+    d = d / d.norm()
+    model = CaSPR().cuda().eval()
+    model.load_state_dict(weights)
+    cnf = model.point_cnf.chain[1]
+    pack, T = cnf.weight_pack(), cnf.end_time()
+    lp0 = torch.zeros(F_, P_, device='cuda')
+
+    def S(c):
+        x1, lp1, info, rc = ops.cnf_flow(x, lp0, e, c, pack, None, None, T, False, 1e-5, 1e-5, ops.CNF_SIMT_FP32)
+        assert rc == 0
+        return float((x1.double() * gx.double()).sum() + (lp1.double() * gl.double()).sum()), x1, lp1
+
+    s0, x1, lp1 = S(ctx)
+    eps = 0.05
+    fd = (S(ctx + eps * d)[0] - S(ctx - eps * d)[0]) / (2 * eps)
+    for engine in (ops.CNF_SIMT_FP32, ops.CNF_TC_FP16X3):
+        _, _, gctx, _, _, info, rc = ops.cnf_adjoint(x1, lp1, gx, gl, e, ctx, pack, T, engine=engine)
+        assert rc == 0
+        pred = float((gctx.double() * d.double()).sum())
+        assert abs(pred - fd) < 2e-2 * abs(fd), (engine, pred, fd)
