@@ -108,7 +108,7 @@ SIGNATURES = {
     'caspr_linear_wgrad_workspace_bytes': (c_size_t, [c_longlong, c_int, c_int]),
     'caspr_linear_wgrad': (c_int, [_P, c_int, _P, c_int, c_longlong, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     'caspr_linear_wgrad_tc_workspace_bytes': (c_size_t, [c_longlong, c_int, c_int]),
-    'caspr_linear_wgrad_tc': (c_int, [_P, c_int, _P, c_int, c_longlong, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
+    'caspr_linear_wgrad_tc': (c_int, [_P, c_int, _P, c_int, c_longlong, c_int, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
     'caspr_colsum_workspace_bytes': (c_size_t, [c_longlong, c_int]),
     'caspr_colsum': (c_int, [_P, c_int, c_longlong, c_int, _P, c_int, _P, c_size_t, _P]),
     'caspr_group_points_bwd': (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P]),

@@ -97,9 +97,13 @@ __device__ __forceinline__ void through_activation(float hb, float hdb, float a,
 __global__ void __launch_bounds__(256)
 adj_act_kernel(const float* __restrict__ A, const float* __restrict__ Ad, const float* __restrict__ gate,
                const float* __restrict__ biasf, int ld, int H, int P, long long total4,
-               const CnfState* __restrict__ st, float* __restrict__ Hn, float* __restrict__ Vn) {
+               const CnfState* __restrict__ st, float* __restrict__ Hn, float* __restrict__ Vn,
+               unsigned* __restrict__ colmax) {
   if (st->done) return;
   const int h4 = H / 4;
+  // the grid stride (gridDim.x * 256) is a multiple of H/4, so a thread always works on the same four channels
+  float cmx[4] = {0.f, 0.f, 0.f, 0.f};
+  int cch = -1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
     const long long pt = i / h4;
     const int c = (int)(i - pt * h4) * 4;
@@ -117,9 +121,16 @@ adj_act_kernel(const float* __restrict__ A, const float* __restrict__ Ad, const 
       softplus_and_grad(fmaf(a[j], g[j], b[j]), sp, dsp);
       ho[j] = sp;
       vo[j] = dsp * g[j] * d[j];
+      cmx[j] = fmaxf(cmx[j], fmaxf(fabsf(ho[j]), fabsf(vo[j])));
     }
+    cch = c;
     *reinterpret_cast<float4*>(Hn + pt * H + c) = make_float4(ho[0], ho[1], ho[2], ho[3]);
     *reinterpret_cast<float4*>(Vn + pt * H + c) = make_float4(vo[0], vo[1], vo[2], vo[3]);
+  }
+  if (colmax && cch >= 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      atomic_max_nonneg(colmax + cch + j, cmx[j]);
   }
 }
 
@@ -134,7 +145,7 @@ adj_bwd_last_kernel(const float4* __restrict__ adj0, const float4* __restrict__ 
                     const float* __restrict__ H3, const float* __restrict__ V3, const float* __restrict__ gate,
                     const float* __restrict__ biasf, const float* __restrict__ lbias, int ld, int H, int P, int L,
                     float* __restrict__ Ab, float* __restrict__ Av, float* __restrict__ gpart,
-                    float* __restrict__ bpart, float* __restrict__ w3part) {
+                    float* __restrict__ bpart, float* __restrict__ w3part, unsigned* __restrict__ colmax) {
   if (st->done) return;
   __shared__ float s_ab[kChunkMax][8];      // g3*ubar3 [0..2], g3*vbar3 [4..6]
   __shared__ float s_g3[kChunkMax][8];      // gate cotangent terms [0..2], ubar3 [4..6]
@@ -162,7 +173,7 @@ adj_bwd_last_kernel(const float4* __restrict__ adj0, const float4* __restrict__ 
   __syncthreads();
   const float w0 = W3[j], w1 = W3[H + j], w2 = W3[2 * H + j];
   const float gj = g[2 * H + j], bfj = bf[2 * H + j], bl = lbias[2 * H + j];
-  float gsum = 0.f, bsum = 0.f, wa0 = 0.f, wa1 = 0.f, wa2 = 0.f;
+  float gsum = 0.f, bsum = 0.f, wa0 = 0.f, wa1 = 0.f, wa2 = 0.f, cmx = 0.f;
   for (int q = 0; q < npts; ++q) {
     const size_t row = (size_t)(f * P + q0 + q) * H + j;
     const float ab0 = s_ab[q][0], ab1 = s_ab[q][1], ab2 = s_ab[q][2];
@@ -173,6 +184,7 @@ adj_bwd_last_kernel(const float4* __restrict__ adj0, const float4* __restrict__ 
     through_activation(hb, hdb, A2[row], Ad2[row], gj, bfj, bl, ubar, vbar, gsum, bsum);
     Ab[row] = gj * ubar;
     Av[row] = gj * vbar;
+    cmx = fmaxf(cmx, fmaxf(fabsf(gj * ubar), fabsf(gj * vbar)));
     const float h3 = H3[row], v3 = V3[row];
     wa0 = fmaf(ab0, h3, fmaf(av0, v3, wa0));
     wa1 = fmaf(ab1, h3, fmaf(av1, v3, wa1));
@@ -184,6 +196,7 @@ adj_bwd_last_kernel(const float4* __restrict__ adj0, const float4* __restrict__ 
   w3part[part * 3 * H + j] = wa0;
   w3part[part * 3 * H + H + j] = wa1;
   w3part[part * 3 * H + 2 * H + j] = wa2;
+  if (colmax) atomic_max_nonneg(colmax + j, cmx);
   if (j < 3) {
     float sg = 0.f, sb = 0.f;
     for (int q = 0; q < npts; ++q) { sg += s_g3[q][j]; sb += s_g3[q][4 + j]; }
@@ -198,7 +211,7 @@ adj_bwd_mid_kernel(const float* __restrict__ Gh, const float* __restrict__ Gv, c
                    const float* __restrict__ Ad, const float* __restrict__ gate, const float* __restrict__ biasf,
                    const float* __restrict__ lbias, int ld, int H, int P, int L, int lp,
                    const CnfState* __restrict__ st, float* __restrict__ Ab, float* __restrict__ Av,
-                   float* __restrict__ gpart, float* __restrict__ bpart) {
+                   float* __restrict__ gpart, float* __restrict__ bpart, unsigned* __restrict__ colmax) {
   if (st->done) return;
   const int f = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
   const int q0 = chunk * L;
@@ -206,17 +219,19 @@ adj_bwd_mid_kernel(const float* __restrict__ Gh, const float* __restrict__ Gv, c
   const int j = threadIdx.x;
   const float gj = gate[(size_t)f * ld + lp * H + j], bfj = biasf[(size_t)f * ld + lp * H + j];
   const float bl = lbias[lp * H + j];
-  float gsum = 0.f, bsum = 0.f;
+  float gsum = 0.f, bsum = 0.f, cmx = 0.f;
   for (int q = 0; q < npts; ++q) {
     const size_t row = (size_t)(f * P + q0 + q) * H + j;
     float ubar, vbar;
     through_activation(Gh[row], Gv[row], A[row], Ad[row], gj, bfj, bl, ubar, vbar, gsum, bsum);
     Ab[row] = gj * ubar;
     Av[row] = gj * vbar;
+    cmx = fmaxf(cmx, fmaxf(fabsf(gj * ubar), fabsf(gj * vbar)));
   }
   const size_t part = (size_t)f * nchunk + chunk;
   gpart[part * ld + lp * H + j] = gsum;
   bpart[part * ld + lp * H + j] = bsum;
+  if (colmax) atomic_max_nonneg(colmax + j, cmx);
 }
 
 // Layer 0 backward: (Gh, Gv) = cotangents of h1, hd1 -> gradient wrt the stage input (k of adj_x), W0 gradient
@@ -622,6 +637,7 @@ struct AdjWorkspace {
   char* prep[4];                     // fp16 hi/lo planes of W1, W2, W1^T, W2^T
   char* wg_ws;                       // caspr_linear_wgrad_tc workspace
   size_t wg_ws_bytes;
+  unsigned* cm;                      // 4 x H column maxima (bit patterns): [h1;v1], [h2;v2], cotangents of layer 2 / 1
   float *gpart, *bpart, *w0part, *w3part, *wpart, *Ghat, *Bhat, *cpart;
   double* sums;
   float* scratch_x;                  // x(t0), logp(t0) written by the state finalize (not returned)
@@ -687,6 +703,7 @@ AdjWorkspace adj_carve(void* base, int frames, int pts, int H, int C) {
   for (int i = 0; i < 4; ++i) w.prep[i] = take1k(w.prep_bytes);
   w.wg_ws_bytes = caspr_linear_wgrad_tc_workspace_bytes((long long)(2 * n), H, H);
   w.wg_ws = take1k(w.wg_ws_bytes);
+  w.cm = (unsigned*)take((size_t)4 * H * 4);
   w.raw8 = (float*)take(n * 8 * 4);
   w.W1t = (float*)take((size_t)H * H * 4);
   w.W2t = (float*)take((size_t)H * H * 4);
@@ -723,10 +740,15 @@ int enqueue_aug_eval(const AdjWorkspace& w, const caspr_cnf_weights* cw, const f
   float* kU = w.kU + (size_t)stage * w.nu;
   float* kpar = kU + w.par_off;
   // ---- forward, keeping what the backward sweep needs
-  CASPR_COUNT(); cnf_layer0_kernel<<<blocks_for(n, 8, 148 * 16), 256, 0, s>>>(
-      b.y0, b.kbuf, (size_t)n, e, cw->W[0], H, n, pts, stage, gate, biasf, ctot, b.st, b.Ha, b.Va);
-  const dim3 ggrid(ceil_div(n, kMidBM), H / kMidBN);
   const bool tc = engine == CASPR_CNF_TC_FP16X3;
+  unsigned *cm_hv1 = nullptr, *cm_hv2 = nullptr, *cm_ab2 = nullptr, *cm_ab1 = nullptr;
+  if (tc) {
+    if (cudaMemsetAsync(w.cm, 0, (size_t)4 * H * 4, s) != cudaSuccess) return CASPR_ELAUNCH;
+    cm_hv1 = w.cm; cm_hv2 = w.cm + H; cm_ab2 = w.cm + 2 * H; cm_ab1 = w.cm + 3 * H;
+  }
+  CASPR_COUNT(); cnf_layer0_kernel<<<blocks_for(n, 8, 148 * 16), 256, 0, s>>>(
+      b.y0, b.kbuf, (size_t)n, e, cw->W[0], H, n, pts, stage, gate, biasf, ctot, b.st, b.Ha, b.Va, cm_hv1);
+  const dim3 ggrid(ceil_div(n, kMidBM), H / kMidBN);
   const long long total4 = (long long)n * H / 4;
   const int agrid = blocks_for(total4, 256 * 2, 148 * 16);
   // (2n x H) . W^T on the tcgen05 fp16x3 GEMM: rows [0,n) = activations, rows [n,2n) = tangents
@@ -737,10 +759,10 @@ int enqueue_aug_eval(const AdjWorkspace& w, const caspr_cnf_weights* cw, const f
   if (tc) {
     int rc = tc_product(b.Ha, 0, w.A1);
     if (rc) return rc;
-    CASPR_COUNT(); adj_act_kernel<<<agrid, 256, 0, s>>>(w.A1, w.Ad1, gate + H, biasf + H, ctot, H, pts, total4, b.st, w.H2, w.V2);
+    CASPR_COUNT(); adj_act_kernel<<<agrid, 256, 0, s>>>(w.A1, w.Ad1, gate + H, biasf + H, ctot, H, pts, total4, b.st, w.H2, w.V2, cm_hv2);
     rc = tc_product(w.H2, 1, w.A2);
     if (rc) return rc;
-    CASPR_COUNT(); adj_act_kernel<<<agrid, 256, 0, s>>>(w.A2, w.Ad2, gate + 2 * H, biasf + 2 * H, ctot, H, pts, total4, b.st, w.H3, w.V3);
+    CASPR_COUNT(); adj_act_kernel<<<agrid, 256, 0, s>>>(w.A2, w.Ad2, gate + 2 * H, biasf + 2 * H, ctot, H, pts, total4, b.st, w.H3, w.V3, nullptr);
   } else {
     CASPR_COUNT(); cnf_mid_layer_kernel<kMidForwardKeepRaw><<<ggrid, 256, 0, s>>>(
         b.Ha, b.Va, cw->W[1], H, n, pts, gate + H, biasf + H, ctot, b.st, w.H2, w.V2, w.A1, w.Ad1);
@@ -757,17 +779,17 @@ int enqueue_aug_eval(const AdjWorkspace& w, const caspr_cnf_weights* cw, const f
   const size_t hh = (size_t)H * H;
   CASPR_COUNT(); adj_bwd_last_kernel<<<egrid, H, 0, s>>>(
       w.adj0, w.kadj, (size_t)n, stage, b.st, e, cw->W[3], w.raw8, w.A2, w.Ad2, w.H3, w.V3, gate, biasf, b.lbias,
-      ctot, H, pts, w.L, w.Ab, w.Av, w.gpart, w.bpart, w.w3part);
+      ctot, H, pts, w.L, w.Ab, w.Av, w.gpart, w.bpart, w.w3part, cm_ab2);
   // weight gradient of an H x H layer: [Ab ; Av]^T . [h ; v] over the 2n stacked rows
-  auto wgrad = [&](const float* Hin, const float* Vin, float* dst) {
+  auto wgrad = [&](const float* Hin, const float* Vin, float* dst, const unsigned* cm_dy, const unsigned* cm_x) {
     if (tc)
-      return caspr_linear_wgrad_tc(w.Ab, H, Hin, H, 2ll * n, H, H, 0, dst, w.wg_ws, w.wg_ws_bytes, s);
+      return caspr_linear_wgrad_tc(w.Ab, H, Hin, H, 2ll * n, H, H, 0, dst, cm_dy, cm_x, w.wg_ws, w.wg_ws_bytes, s);
     CASPR_COUNT(); adj_wgrad_kernel<<<wgrid, 256, 0, s>>>(w.Ab, w.Av, Hin, Vin, H, n, w.pts_per_split, b.st, w.wpart);
     CASPR_COUNT(); adj_reduce_parts_kernel<<<(unsigned)((hh + 255) / 256), 256, 0, s>>>(w.wpart, w.nsplit, hh, b.st, dst);
     return (int)CASPR_OK;
   };
   {
-    const int rc = wgrad(w.H2, w.V2, kpar + pl.W[2]);
+    const int rc = wgrad(w.H2, w.V2, kpar + pl.W[2], cm_ab2, cm_hv2);
     if (rc) return rc;
   }
   if (tc) {
@@ -778,9 +800,9 @@ int enqueue_aug_eval(const AdjWorkspace& w, const caspr_cnf_weights* cw, const f
         w.Ab, w.Av, w.W2t, H, n, pts, nullptr, nullptr, ctot, b.st, w.Gh, w.Gv, nullptr, nullptr);
   }
   CASPR_COUNT(); adj_bwd_mid_kernel<<<egrid, H, 0, s>>>(w.Gh, w.Gv, w.A1, w.Ad1, gate, biasf, b.lbias, ctot, H, pts,
-                                                        w.L, 1, b.st, w.Ab, w.Av, w.gpart, w.bpart);
+                                                        w.L, 1, b.st, w.Ab, w.Av, w.gpart, w.bpart, cm_ab1);
   {
-    const int rc = wgrad(b.Ha, b.Va, kpar + pl.W[1]);
+    const int rc = wgrad(b.Ha, b.Va, kpar + pl.W[1], cm_ab1, cm_hv1);
     if (rc) return rc;
   }
   if (tc) {

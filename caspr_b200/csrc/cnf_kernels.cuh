@@ -114,7 +114,7 @@ cnf_layer0_kernel(const float4* __restrict__ y0, const float4* __restrict__ kbuf
                   const float* __restrict__ e, const float* __restrict__ W0, int H, int n, int P,
                   int stage, const float* __restrict__ gate, const float* __restrict__ biasf,
                   int ld_hyper, const CnfState* __restrict__ st, float* __restrict__ Hout,
-                  float* __restrict__ Vout) {
+                  float* __restrict__ Vout, unsigned* __restrict__ colmax = nullptr) {
   if (st->done) return;
   __shared__ float sW[kMaxHidden * 3];
   for (int i = threadIdx.x; i < H * 3; i += blockDim.x) sW[i] = W0[i];
@@ -122,6 +122,10 @@ cnf_layer0_kernel(const float4* __restrict__ y0, const float4* __restrict__ kbuf
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const float dt = (float)st->dt;
+  // optional per-channel max |h|, |v| over all points (operand scales of the tensor-core weight gradient)
+  float cmx[kMaxHidden / 32];
+#pragma unroll
+  for (int i = 0; i < kMaxHidden / 32; ++i) cmx[i] = 0.f;
   for (int pt = blockIdx.x * wpb + (threadIdx.x >> 5); pt < n; pt += gridDim.x * wpb) {
     float4 y = y0[pt];
     float ys[3] = {y.x, y.y, y.z};
@@ -146,7 +150,10 @@ cnf_layer0_kernel(const float4* __restrict__ y0, const float4* __restrict__ kbuf
     const float* bf = biasf + (size_t)f * ld_hyper;
     float* ho = Hout + (size_t)pt * H;
     float* vo = Vout + (size_t)pt * H;
-    for (int j = lane; j < H; j += 32) {
+#pragma unroll
+    for (int i = 0; i < kMaxHidden / 32; ++i) {
+      const int j = lane + 32 * i;
+      if (j >= H) break;
       const float w0 = sW[3 * j], w1 = sW[3 * j + 1], w2 = sW[3 * j + 2];
       const float a = fmaf(w2, ys[2], fmaf(w1, ys[1], w0 * ys[0]));
       const float ta = fmaf(w2, e2, fmaf(w1, e1, w0 * e0));
@@ -154,8 +161,17 @@ cnf_layer0_kernel(const float4* __restrict__ y0, const float4* __restrict__ kbuf
       const float pre = fmaf(a, gj, bf[j]);
       float sp, dsp;
       softplus_and_grad(pre, sp, dsp);
+      const float tv = dsp * gj * ta;
       ho[j] = sp;
-      vo[j] = dsp * gj * ta;
+      vo[j] = tv;
+      cmx[i] = fmaxf(cmx[i], fmaxf(fabsf(sp), fabsf(tv)));
+    }
+  }
+  if (colmax) {
+#pragma unroll
+    for (int i = 0; i < kMaxHidden / 32; ++i) {
+      const int j = lane + 32 * i;
+      if (j < H) atomic_max_nonneg(colmax + j, cmx[i]);
     }
   }
 }

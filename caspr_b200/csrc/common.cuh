@@ -51,6 +51,13 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Running maximum of non-negative floats kept as their bit patterns (unsigned order == float order).  The value only
+// grows, so a plain read that already shows a larger maximum makes the atomic unnecessary: almost all of them are.
+__device__ __forceinline__ void atomic_max_nonneg(unsigned* p, float v) {
+  const unsigned b = __float_as_uint(v);
+  if (v > 0.f && b > __ldcg(p)) atomicMax(p, b);
+}
+
 // Order-preserving float <-> uint mapping for atomicMax on floats.
 __device__ __forceinline__ unsigned float_to_ordered(float f) {
   unsigned u = __float_as_uint(f);

@@ -257,9 +257,23 @@ bool g_wgrad_attr_set = false;
 // ------------------------------------------------------------------ weight gradient (split-K, transposed operands)
 // dW[o][i] = sum_r dY[r][o] X[r][i]: both operands are needed with the ROW index as the contraction (K) dimension, i.e.
 // transposed.  colmax -> per-column power-of-two scale; transpose_split writes the fp16 hi/lo planes [C_pad][R_pad].
+// Column maxima are kept as the bit patterns of non-negative floats (their unsigned order is the float order), so
+// every producer can fold its part in with atomicMax; power-of-two scale 2^(14-e) for max|column| < 2^e.
+__device__ __forceinline__ void scale_from_max_bits(unsigned bits, float& scale, float& inv) {
+  const float m = __uint_as_float(bits);
+  scale = 1.f;
+  inv = 1.f;
+  if (m > 0.f && m < 3.0e38f) {
+    int e;
+    frexpf(m, &e);
+    scale = ldexpf(1.f, 14 - e);
+    inv = ldexpf(1.f, e - 14);
+  }
+}
+
 __global__ void __launch_bounds__(128)
-colmax_partial_kernel(const float* __restrict__ X, int ldx, long long rows, int C, long long rows_per_split, int relu,
-                      float* __restrict__ partial) {
+colmax_kernel(const float* __restrict__ X, int ldx, long long rows, int C, long long rows_per_split, int relu,
+              unsigned* __restrict__ cmax) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const long long r0 = blockIdx.y * rows_per_split;
@@ -280,30 +294,13 @@ colmax_partial_kernel(const float* __restrict__ X, int ldx, long long rows, int 
     const float v = X[r * ldx + c];
     m[0] = fmaxf(m[0], relu ? v : fabsf(v));
   }
-  partial[(size_t)blockIdx.y * C + c] = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
-}
-// scale[c] = 2^(14-e), inv[c] = 2^(e-14) with max|column| < 2^e; padded channels get 0
-__global__ void colscale_kernel(const float* __restrict__ partial, int nsplit, int C, int C_pad, float* __restrict__ scale,
-                                float* __restrict__ inv) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C_pad) return;
-  float m = 0.f;
-  if (c < C)
-    for (int p = 0; p < nsplit; ++p) m = fmaxf(m, partial[(size_t)p * C + c]);
-  float s = 1.f, iv = c < C ? 1.f : 0.f;
-  if (m > 0.f && m < 3.0e38f) {
-    int e;
-    frexpf(m, &e);
-    s = ldexpf(1.f, 14 - e);
-    iv = ldexpf(1.f, e - 14);
-  }
-  scale[c] = s;
-  inv[c] = iv;
+  const float mm = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
+  atomic_max_nonneg(cmax + c, mm);
 }
 // planes[c][r] = split(X[r][c] * scale[c]) for a 64 (rows) x 64 (channels) tile through shared memory; zero padding
 __global__ void __launch_bounds__(256)
 transpose_split_kernel(const float* __restrict__ X, int ldx, long long rows, int C, long long rows_pad, int relu,
-                       const float* __restrict__ scale, __half* __restrict__ hi, __half* __restrict__ lo) {
+                       const unsigned* __restrict__ cmax, __half* __restrict__ hi, __half* __restrict__ lo) {
   __shared__ float tile[64][65];
   const long long r0 = (long long)blockIdx.x * 64;
   const int c0 = blockIdx.y * 64;
@@ -320,7 +317,8 @@ transpose_split_kernel(const float* __restrict__ X, int ldx, long long rows, int
   for (int i = threadIdx.x; i < 64 * 32; i += 256) {
     const int cc = i >> 5, rp = i & 31;
     const int c = c0 + cc;
-    const float s = scale[c];
+    float s, inv_unused;
+    scale_from_max_bits(c < C ? cmax[c] : 0u, s, inv_unused);
     const float a = tile[2 * rp][cc] * s, b = tile[2 * rp + 1][cc] * s;
     const __half2 hh = __floats2half2_rn(a, b);
     const float2 hf = __half22float2(hh);
@@ -332,8 +330,8 @@ transpose_split_kernel(const float* __restrict__ X, int ldx, long long rows, int
 
 // partial[split][o][i] = acc * inv_dy[o] * inv_x[i]
 struct WgradEpilogue {
-  const float* a_inv;     // per output channel o (rows of the A operand)
-  const float* w_inv;     // per input channel i
+  const unsigned* a_max;  // column maxima (bit patterns) of dY: per output channel o (rows of the A operand)
+  const unsigned* w_max;  // column maxima of X: per input channel i
   float* part;            // [k_splits][cout][cin]
   int cout, cin, m_tiles;
   long long row;
@@ -344,7 +342,8 @@ struct WgradEpilogue {
     split = m_tile_epi / m_tiles;
     row = (long long)(m_tile_epi - split * m_tiles) * kBM + q * 32 + lane;
     col0 = n_tile * kBN;
-    inv = a_inv[row];
+    float s_unused;
+    scale_from_max_bits(row < cout ? a_max[row] : 0u, s_unused, inv);
   }
   __device__ __forceinline__ void chunk(int chunk, uint32_t (&r)[32]) {
     const int c = col0 + chunk * 32;
@@ -352,7 +351,11 @@ struct WgradEpilogue {
     float* y = part + ((size_t)split * cout + row) * cin + c;
 #pragma unroll
     for (int j = 0; j < 32; ++j)
-      if (c + j < cin) y[j] = __uint_as_float(r[j]) * (inv * w_inv[c + j]);
+      if (c + j < cin) {
+        float s_unused, winv;
+        scale_from_max_bits(w_max[c + j], s_unused, winv);
+        y[j] = __uint_as_float(r[j]) * (inv * winv);
+      }
   }
   __device__ __forceinline__ void finish() {}
 };
@@ -360,7 +363,7 @@ struct WgradEpilogue {
 struct WgradLayout {
   long long r_pad;          // contraction length padded to k_splits * k_chunks * 64
   int k_splits, k_chunks, cout_pad, cin_pad, colmax_splits;
-  size_t off_cmax, off_ascale, off_ainv, off_wscale, off_winv, off_ahi, off_alo, off_whi, off_wlo, off_part, total;
+  size_t off_amax, off_wmax, off_ahi, off_alo, off_whi, off_wlo, off_part, total;
 };
 WgradLayout make_wgrad_layout(long long rows, int cout, int cin) {
   WgradLayout l;
@@ -389,12 +392,8 @@ WgradLayout make_wgrad_layout(long long rows, int cout, int cin) {
   l.colmax_splits = (int)cs;
   size_t p = 0;
   auto take = [&](size_t bytes) { size_t r = p; p += align_up(bytes, 1024); return r; };
-  const int cmax = l.cout_pad > l.cin_pad ? l.cout_pad : l.cin_pad;
-  l.off_cmax = take((size_t)l.colmax_splits * cmax * 4);
-  l.off_ascale = take((size_t)l.cout_pad * 4);
-  l.off_ainv = take((size_t)l.cout_pad * 4);
-  l.off_wscale = take((size_t)l.cin_pad * 4);
-  l.off_winv = take((size_t)l.cin_pad * 4);
+  l.off_amax = take((size_t)l.cout_pad * 4);
+  l.off_wmax = take((size_t)l.cin_pad * 4);
   l.off_ahi = take((size_t)l.cout_pad * l.r_pad * 2);
   l.off_alo = take((size_t)l.cout_pad * l.r_pad * 2);
   l.off_whi = take((size_t)l.cin_pad * l.r_pad * 2);
@@ -421,7 +420,8 @@ extern "C" size_t caspr_linear_wgrad_tc_workspace_bytes(long long rows, int Cout
 }
 
 extern "C" int caspr_linear_wgrad_tc(const float* dY, int lddy, const float* X, int ldx, long long rows, int Cout,
-                                     int Cin, int relu_x, float* dW, void* workspace, size_t workspace_bytes,
+                                     int Cin, int relu_x, float* dW, const uint32_t* dy_colmax,
+                                     const uint32_t* x_colmax, void* workspace, size_t workspace_bytes,
                                      void* stream) {
   CASPR_REQUIRE(dY && X && dW && workspace && rows > 0 && Cout > 0 && Cin > 0 && lddy >= Cout && ldx >= Cin);
   CASPR_REQUIRE(((uintptr_t)workspace & 1023) == 0);
@@ -429,11 +429,8 @@ extern "C" int caspr_linear_wgrad_tc(const float* dY, int lddy, const float* X, 
   if (workspace_bytes < l.total) return CASPR_EWORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
   char* base = (char*)workspace;
-  float* cmax = (float*)(base + l.off_cmax);
-  float* ascale = (float*)(base + l.off_ascale);
-  float* ainv = (float*)(base + l.off_ainv);
-  float* wscale = (float*)(base + l.off_wscale);
-  float* winv = (float*)(base + l.off_winv);
+  unsigned* amax = (unsigned*)(base + l.off_amax);
+  unsigned* wmax = (unsigned*)(base + l.off_wmax);
   __half* ahi = (__half*)(base + l.off_ahi);
   __half* alo = (__half*)(base + l.off_alo);
   __half* whi = (__half*)(base + l.off_whi);
@@ -441,16 +438,22 @@ extern "C" int caspr_linear_wgrad_tc(const float* dY, int lddy, const float* X, 
   float* part = (float*)(base + l.off_part);
   const long long rps = (rows + l.colmax_splits - 1) / l.colmax_splits;
   CASPR_REQUIRE(l.r_pad / 64 < (1ll << 31));
-  // operand A = dY^T
-  CASPR_COUNT(); colmax_partial_kernel<<<dim3(ceil_div(Cout, 128), l.colmax_splits), 128, 0, s>>>(dY, lddy, rows, Cout, rps, 0, cmax);
-  CASPR_COUNT(); colscale_kernel<<<ceil_div(l.cout_pad, 128), 128, 0, s>>>(cmax, l.colmax_splits, Cout, l.cout_pad, ascale, ainv);
+  // column maxima: supplied by the producers of the operands, or one pass here
+  if (!dy_colmax) {
+    if (cudaMemsetAsync(amax, 0, (size_t)l.cout_pad * 4, s) != cudaSuccess) return CASPR_ELAUNCH;
+    CASPR_COUNT(); colmax_kernel<<<dim3(ceil_div(Cout, 128), l.colmax_splits), 128, 0, s>>>(dY, lddy, rows, Cout, rps, 0, amax);
+    dy_colmax = amax;
+  }
+  if (!x_colmax) {
+    if (cudaMemsetAsync(wmax, 0, (size_t)l.cin_pad * 4, s) != cudaSuccess) return CASPR_ELAUNCH;
+    CASPR_COUNT(); colmax_kernel<<<dim3(ceil_div(Cin, 128), l.colmax_splits), 128, 0, s>>>(X, ldx, rows, Cin, rps, relu_x, wmax);
+    x_colmax = wmax;
+  }
+  // operand A = dY^T, operand W = X^T
   CASPR_COUNT(); transpose_split_kernel<<<dim3((unsigned)(l.r_pad / 64), l.cout_pad / 64), 256, 0, s>>>(
-      dY, lddy, rows, Cout, l.r_pad, 0, ascale, ahi, alo);
-  // operand W = X^T
-  CASPR_COUNT(); colmax_partial_kernel<<<dim3(ceil_div(Cin, 128), l.colmax_splits), 128, 0, s>>>(X, ldx, rows, Cin, rps, relu_x, cmax);
-  CASPR_COUNT(); colscale_kernel<<<ceil_div(l.cin_pad, 128), 128, 0, s>>>(cmax, l.colmax_splits, Cin, l.cin_pad, wscale, winv);
+      dY, lddy, rows, Cout, l.r_pad, 0, dy_colmax, ahi, alo);
   CASPR_COUNT(); transpose_split_kernel<<<dim3((unsigned)(l.r_pad / 64), l.cin_pad / 64), 256, 0, s>>>(
-      X, ldx, rows, Cin, l.r_pad, relu_x, wscale, whi, wlo);
+      X, ldx, rows, Cin, l.r_pad, relu_x, x_colmax, whi, wlo);
   CASPR_CHECK_LAUNCH();
   CUtensorMap tm_ahi, tm_alo, tm_whi, tm_wlo;
   bool ok = true;
@@ -471,7 +474,7 @@ extern "C" int caspr_linear_wgrad_tc(const float* dY, int lddy, const float* X, 
     return CASPR_ELAUNCH;
   const int m_tiles = l.cout_pad / kBM, n_tiles = l.cin_pad / kBN;
   WgradEpilogue epi{};
-  epi.a_inv = ainv; epi.w_inv = winv; epi.part = part; epi.cout = Cout; epi.cin = Cin; epi.m_tiles = m_tiles;
+  epi.a_max = dy_colmax; epi.w_max = x_colmax; epi.part = part; epi.cout = Cout; epi.cin = Cin; epi.m_tiles = m_tiles;
   long long grid = (long long)m_tiles * n_tiles * l.k_splits;
   if (grid > num_sms) grid = num_sms;
   CASPR_COUNT(); tcg::gemm_fp16x3_kernel<WgradEpilogue><<<(int)grid, tcg::kThreads, tcg::kSmemBytes, s>>>(

@@ -33,6 +33,7 @@ lat_linear_kernel(const float* __restrict__ x, int ldx, const float* __restrict_
     float acc[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+#pragma unroll 4
     for (int k = lane; k < K; k += 32) {
       const float wv = w[k];
 #pragma unroll

@@ -100,7 +100,7 @@ def linear_wgrad(d_y, x, relu_x=False, want_bias=True, engine=None):
         buf = torch.empty(nb + 1024, dtype=torch.uint8, device=x.device)
         ptr = (buf.data_ptr() + 1023) // 1024 * 1024
         _count('linear_wgrad_tc')
-        check(lib.caspr_linear_wgrad_tc(_p(d_y), lddy, _p(x), ldx, rows, cout, cin, int(relu_x), _p(dW),
+        check(lib.caspr_linear_wgrad_tc(_p(d_y), lddy, _p(x), ldx, rows, cout, cin, int(relu_x), _p(dW), None, None,
                                         ctypes.c_void_p(ptr), nb, _stream()), 'caspr_linear_wgrad_tc')
         if want_bias:
             colsum(d_y, db)

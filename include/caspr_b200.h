@@ -326,10 +326,13 @@ int caspr_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, long 
                        int relu_x, float* dW, float* db, void* workspace, size_t workspace_bytes, void* stream);
 /* The same dW on the tensor cores: both operands are transposed into fp16 hi/lo planes with the ROW index as the
  * contraction dimension (per-channel power-of-two scales), split-K tcgen05 fp16x3 GEMM (at most 4096 rows per
- * split), ordered reduction of the partials.  Meant for Cout, Cin >= 64; workspace 1024-byte aligned. */
+ * split), ordered reduction of the partials.  Meant for Cout, Cin >= 64; workspace 1024-byte aligned.
+ * dy_colmax / x_colmax: optional per-channel max |.| of the operands as float bit patterns (a producer kernel can
+ * maintain them with atomicMax); NULL = computed here with one extra pass over the operand. */
 size_t caspr_linear_wgrad_tc_workspace_bytes(long long rows, int Cout, int Cin);
 int caspr_linear_wgrad_tc(const float* dY, int lddy, const float* X, int ldx, long long rows, int Cout, int Cin,
-                          int relu_x, float* dW, void* workspace, size_t workspace_bytes, void* stream);
+                          int relu_x, float* dW, const uint32_t* dy_colmax, const uint32_t* x_colmax,
+                          void* workspace, size_t workspace_bytes, void* stream);
 /* out[c] (+)= sum_r X[r][c] (backward of the repeat at pointnet.py:44). */
 size_t caspr_colsum_workspace_bytes(long long rows, int C);
 int caspr_colsum(const float* X, int ldx, long long rows, int C, float* out, int accumulate, void* workspace,
