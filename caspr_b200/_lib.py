@@ -65,6 +65,10 @@ SIGNATURES = {
     'caspr_linear': (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     'caspr_linear_gn_ball': (c_int, [_P, c_int, _P, c_int, _P, _P, _P, c_float, c_int, c_int, c_int, c_int, c_int,
                                      _P, c_int, _P, c_int, _P]),
+    'caspr_sa_fused_supported': (c_int, [c_int, c_int, c_int, c_int, c_int]),
+    'caspr_sa_fused': (c_int, [_P, _P, _P, c_int, c_int, _P, c_int, c_int, c_int, c_int,
+                               _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_int,
+                               c_float, _P, c_int, _P]),
     'caspr_linear_tc_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'caspr_linear_tc_weight_bytes': (c_size_t, [c_int, c_int]),
     'caspr_linear_tc_prepare_weights': (c_int, [_P, c_int, c_int, c_int, _P, c_size_t, _P]),

@@ -107,8 +107,14 @@ class PointNet2SetAbstraction(nn.Module):
         out = torch.empty(Bp * M, self.get_num_features_out(), dtype=torch.float32, device=xyz.device)
         off = 0
         for s, (grouper, pointnet) in enumerate(zip(self.grouper_modules, self.pointnet_modules)):
-            rows = ops.group_points(xyz, new_xyz, features, bq[s])
-            pointnet.forward_rows(rows, Bp * M, grouper.num_samples, out[:, off:off + pointnet.feat_size])
+            widths = [c.weight.shape[0] for c in pointnet.conv_layers]
+            if ops.sa_fused_supported(grouper.num_samples, self.pointnet_in_channels, widths):
+                # levels 1-2: gather + three per-ball layers + max in ONE kernel, activations stay in registers
+                ops.sa_fused(xyz, new_xyz, features, bq[s], pointnet.conv_layers, pointnet.bn_layers,
+                             out[:, off:off + pointnet.feat_size])
+            else:
+                rows = ops.group_points(xyz, new_xyz, features, bq[s])
+                pointnet.forward_rows(rows, Bp * M, grouper.num_samples, out[:, off:off + pointnet.feat_size])
             off += pointnet.feat_size
         return new_xyz, out.view(Bp, M, -1)
 

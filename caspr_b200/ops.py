@@ -279,6 +279,35 @@ def linear_gn_ball(x, weight, bias, gamma, beta, ns, relu, want_rows=True, maxou
     return y
 
 
+SA_FUSED = True                 # module-wide switch (accuracy / timing studies): fused set-abstraction scale kernel
+
+
+def sa_fused_supported(ns, cin, widths):
+    return SA_FUSED and len(widths) == 3 and bool(lib.caspr_sa_fused_supported(ns, cin, *widths))
+
+
+def sa_fused(xyz, new_xyz, feat, idx, convs, norms, out):
+    """One scale of a set-abstraction level in one kernel: gather -> 3 x [conv, per-ball GroupNorm(16), ReLU (not
+    after the last)] -> max over the ball.  xyz (B,N,3), new_xyz (B,M,3), feat (B,N,C) view or None, idx (B,M,ns),
+    out (B*M, C3) view (may be a column slice)."""
+    B, N, _ = xyz.shape
+    M, ns = idx.shape[1], idx.shape[2]
+    C, ld_feat = 0, 0
+    if feat is not None:
+        assert feat.dim() == 3 and feat.stride(2) == 1 and feat.stride(0) == N * feat.stride(1)
+        C, ld_feat = feat.shape[2], feat.stride(1)
+    out, ld_out = _rows2d(out, 'out')
+    args = []
+    for conv, gn in zip(convs, norms):
+        w = conv.weight.reshape(conv.weight.shape[0], conv.weight.shape[1])
+        assert w.is_contiguous() and w.dtype == torch.float32
+        args += [_p(w), _p(conv.bias), _p(gn.weight), _p(gn.bias), w.shape[0]]
+    _count('sa_fused')
+    check(lib.caspr_sa_fused(_p(xyz), _p(new_xyz), _p(feat), ld_feat, C, _p(idx), B, N, M, ns, *args,
+                             float(norms[0].eps), _p(out), ld_out, _stream()), 'caspr_sa_fused')
+    return out
+
+
 def groupnorm(x, samples, rows_per_sample, groups, gamma, beta, eps=1e-5, relu=False, write_back=True,
               maxout=None, stats=None):
     """In-place GroupNorm(groups, C) over `samples` blocks of consecutive rows, fused ReLU / max-pool.

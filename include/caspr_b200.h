@@ -111,6 +111,20 @@ int caspr_linear_gn_ball(const float* X, int ldx, const float* W, int ldw, const
                          const float* gamma, const float* beta, float eps, int rows, int Cin, int Cout,
                          int ns, int relu, float* Y, int ldy, float* maxout, int ld_max, void* stream);
 
+/* One whole scale of a set-abstraction level in a single kernel (pointnet2.py:391-401,649-708): group gather
+ * ([xyz[idx]-centre | feat[idx]], caspr_group_points) -> three layers Conv1d(k=1) + GroupNorm(16) (+ReLU after the
+ * first two, pointnet2.py:693) with per-ball statistics -> max over the ball's ns rows.  Activations never leave
+ * registers.  Supported shapes (caspr_sa_fused_supported): ns 16 or 32, layer widths (16,16,32), (32,32,64), at most
+ * 136 input channels - the four scales of SA levels 1-2.  feat (B,N,C) channels-last with row stride ld_feat (C may be
+ * 0), idx (B,M,ns) from caspr_ball_query2, weights row-major (Cout,Cin), out (B*M, C3) with row stride ld_out. */
+int caspr_sa_fused_supported(int ns, int Cin, int C1, int C2, int C3);
+int caspr_sa_fused(const float* xyz, const float* new_xyz, const float* feat, int ld_feat, int C,
+                   const int32_t* idx, int B, int N, int M, int ns,
+                   const float* W1, const float* b1, const float* g1, const float* e1, int C1,
+                   const float* W2, const float* b2, const float* g2, const float* e2, int C2,
+                   const float* W3, const float* b3, const float* g3, const float* e3, int C3,
+                   float eps, float* out, int ld_out, void* stream);
+
 /* Same contract on the tcgen05 tensor cores: 3-product fp16 split ("fp16x3",
  * X_hi.W_hi + X_lo.W_hi + X_hi.W_lo, fp32 accumulate in TMEM), operands scaled per call by powers of
  * two taken from max|X| and max|W| (undone exactly in the epilogue).  Meant for the large layers
