@@ -218,3 +218,30 @@ def test_cnf_adjoint_directional_derivative_at_full_size(weights):
         assert rc == 0
         pred = float((gctx.double() * d.double()).sum())
         assert abs(pred - fd) < 2e-2 * abs(fd), (engine, pred, fd)
+
+
+@pytest.mark.parametrize('kwargs', [dict(cnf_blocks=2), dict(regress_tnocs=False), dict(pretrain_tnocs=True)])
+def test_training_step_model_variants(kwargs):
+    """Constructor variants of train.py:109-119 go through forward + backward: every trainable parameter that takes part
+    in the loss receives a finite gradient (two chained CNF blocks, no T-NOCS head, T-NOCS pre-training only)."""
+    from caspr_b200.models import CaSPR
+    from caspr_b200.synth import synthetic_sequences
+    torch.manual_seed(0)
+    model = CaSPR(**kwargs).cuda().train()
+    x, nocs = synthetic_sequences(1, 2, 1024, seed=3)
+    e = torch.randn(2, 1024, 3, generator=torch.Generator().manual_seed(1)).cuda()
+    losses = model(x.cuda(), nocs.cuda(), e=e) if not kwargs.get('pretrain_tnocs') else model(x.cuda(), nocs.cuda())
+    if kwargs.get('pretrain_tnocs'):
+        assert len(losses) == 1
+        loss = losses[0].mean()
+    else:
+        nll, tl1 = losses
+        assert (tl1 is None) == (not kwargs.get('regress_tnocs', True))
+        loss = 0.01 * nll.sum(2).mean() + (100.0 * tl1.mean() if tl1 is not None else 0.0)
+    loss.backward()
+    missing = [k for k, p in model.named_parameters() if p.grad is None]
+    # without the T-NOCS head the encoder's conv3 does not exist; everything that exists must have a gradient
+    assert not missing, missing
+    for k, p in model.named_parameters():
+        assert torch.isfinite(p.grad).all(), k
+    assert float(sum(p.grad.abs().sum() for p in model.parameters())) > 0
