@@ -1,6 +1,6 @@
 """Development check: training-mode encoder forward/backward against the CPU oracle's autograd."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from caspr_b200.models import CaSPR
 from caspr_b200.models.encoder_train import EncoderTrainer

@@ -1,6 +1,6 @@
 """Development check: caspr_latent_ode_adjoint against the CPU training oracle."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from caspr_b200 import ops
 from caspr_b200.synth import synthetic_state_dict

@@ -1,6 +1,6 @@
 """Development check: one full training step (forward + backward) against the CPU training oracle."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from caspr_b200.models import CaSPR
 from caspr_b200.synth import synthetic_state_dict, synthetic_sequences

@@ -3,7 +3,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from caspr_b200.models import CaSPR
 from caspr_b200.synth import synthetic_state_dict, synthetic_sequences
-from oracle.train_oracle import TrainOracle
 B, T, N = int(os.environ.get('B', 2)), int(os.environ.get('T', 2)), 1024
 sd = synthetic_state_dict(0, cnf_init='vigorous')
 x, nocs = synthetic_sequences(B, T, N, seed=9)
@@ -16,7 +15,7 @@ for it in range(int(os.environ.get('ITERS', 4))):
     opt.zero_grad()
     out = model(x, nocs, e=e)
     torch.cuda.synchronize(); t1 = time.time()
-    loss = TrainOracle.loss(*out)
+    loss = 0.01 * out[0].sum(2).mean() + 100.0 * out[1][:, :, :, :4].mean()       # train_utils.py:148-166
     loss.backward()
     torch.cuda.synchronize(); t2 = time.time()
     bad = [k for k, p in model.named_parameters() if p.grad is not None and not torch.isfinite(p.grad).all()]
