@@ -433,6 +433,7 @@ adj_hyper_small_kernel(const float* __restrict__ Ghat, const float* __restrict__
   // W0 (H,3) and W3 (3,H): 3H elements each, reduced over the (frame, chunk) partials
   if (j < 3 * H) {
     float s0 = 0.f, s3 = 0.f;
+#pragma unroll 8
     for (int p = 0; p < nparts; ++p) {
       s0 += w0part[(size_t)p * 3 * H + j];
       s3 += w3part[(size_t)p * 3 * H + j];
@@ -472,8 +473,22 @@ adj_ctx_bwd_kernel(HyperPtrs hp, const float* __restrict__ Ghat, const float* __
   float acc[kCtxFrames];
 #pragma unroll
   for (int ff = 0; ff < kCtxFrames; ++ff) acc[ff] = 0.f;
-#pragma unroll 4
-  for (int jj = 0; jj < D; ++jj) {
+  // eight weight rows (2 x 8 independent loads) in flight per thread: the loop is latency-bound otherwise
+  int jj = 0;
+  for (; jj + 7 < D; jj += 8) {
+    float a[8], b[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a[u] = __ldg(wg + (size_t)(jj + u) * (C + 1));
+      b[u] = __ldg(wb + (size_t)(jj + u) * (C + 1));
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int ff = 0; ff < kCtxFrames; ++ff)
+        acc[ff] = fmaf(a[u], sG[ff][jj + u], fmaf(b[u], sB[ff][jj + u], acc[ff]));
+  }
+  for (; jj < D; ++jj) {
     const float a = wg[(size_t)jj * (C + 1)], b = wb[(size_t)jj * (C + 1)];
 #pragma unroll
     for (int ff = 0; ff < kCtxFrames; ++ff) acc[ff] = fmaf(a, sG[ff][jj], fmaf(b, sB[ff][jj], acc[ff]));
@@ -820,8 +835,8 @@ int enqueue_aug_eval(const AdjWorkspace& w, const caspr_cnf_weights* cw, const f
   const int c3 = 3 * H + 3;
   CASPR_COUNT(); adj_hyper_reduce_kernel<<<ceil_div(frames * ctot, 256), 256, 0, s>>>(
       w.gpart, w.bpart, w.nchunk, frames, c3, ctot, gate, b.st, w.Ghat, w.Bhat);
-  const int nsmall = ceil_div(c3, 256);
-  CASPR_COUNT(); adj_hyper_small_kernel<<<nsmall, 256, 0, s>>>(
+  const int nsmall = ceil_div(c3, 64);         // small blocks: the kernel is a latency-bound column reduction
+  CASPR_COUNT(); adj_hyper_small_kernel<<<nsmall, 64, 0, s>>>(
       w.Ghat, w.Bhat, gate, frames, c3, ctot, H, C, b.st, stage, po, w.w0part, w.w3part, frames * w.nchunk, kpar);
   HyperPtrs hp;
   for (int l = 0; l < 4; ++l) { hp.Wg[l] = cw->Wgate[l]; hp.Wb[l] = cw->Wbias[l]; }

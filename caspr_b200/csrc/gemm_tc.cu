@@ -304,25 +304,29 @@ transpose_split_kernel(const float* __restrict__ X, int ldx, long long rows, int
   __shared__ float tile[64][65];
   const long long r0 = (long long)blockIdx.x * 64;
   const int c0 = blockIdx.y * 64;
-  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
-    const int rr = i >> 6, cc = i & 63;
-    const long long r = r0 + rr;
-    const int c = c0 + cc;
-    float v = (r < rows && c < C) ? X[r * ldx + c] : 0.f;
-    if (relu) v = fmaxf(v, 0.f);
-    tile[rr][cc] = v;
+  // 16 independent loads per thread in flight (rows rr0 + 4j, channel cc), then the shared-memory transpose
+  const int cc = threadIdx.x & 63, rr0 = threadIdx.x >> 6;
+  const int c = c0 + cc;
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const long long r = r0 + rr0 + 4 * j;
+    v[j] = (r < rows && c < C) ? __ldg(X + r * ldx + c) : 0.f;
   }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) tile[rr0 + 4 * j][cc] = relu ? fmaxf(v[j], 0.f) : v[j];
   __syncthreads();
-  // thread -> (channel cc, row pair rp): 64 channels x 32 pairs = 2048 half2 per plane, 8 per thread
-  for (int i = threadIdx.x; i < 64 * 32; i += 256) {
-    const int cc = i >> 5, rp = i & 31;
-    const int c = c0 + cc;
+  // thread -> (row pair rp, channels ch0 + 8q): 64 channels x 32 pairs = 2048 half2 per plane, 8 per thread
+  const int rp = threadIdx.x & 31, ch0 = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int ch = ch0 + 8 * q;
     float s, inv_unused;
-    scale_from_max_bits(c < C ? cmax[c] : 0u, s, inv_unused);
-    const float a = tile[2 * rp][cc] * s, b = tile[2 * rp + 1][cc] * s;
+    scale_from_max_bits(c0 + ch < C ? cmax[c0 + ch] : 0u, s, inv_unused);
+    const float a = tile[2 * rp][ch] * s, b = tile[2 * rp + 1][ch] * s;
     const __half2 hh = __floats2half2_rn(a, b);
     const float2 hf = __half22float2(hh);
-    const size_t off = ((size_t)c * rows_pad + r0) / 2 + rp;
+    const size_t off = ((size_t)(c0 + ch) * rows_pad + r0) / 2 + rp;
     reinterpret_cast<__half2*>(hi)[off] = hh;
     reinterpret_cast<__half2*>(lo)[off] = __floats2half2_rn(a - hf.x, b - hf.y);
   }

@@ -144,9 +144,12 @@ sa_fused_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz
     feed(2, p[2] - cpt[2]);
     const float* fr = feat + ((size_t)b * N + src) * ld_feat;
     if (vec4) {
+      // software pipeline: the next 16 bytes of the gathered row are in flight while the current ones are consumed
+      float4 f = *reinterpret_cast<const float4*>(fr);
       for (int k = 0; k < C; k += 4) {
-        const float4 f = *reinterpret_cast<const float4*>(fr + k);
+        const float4 nxt = k + 4 < C ? *reinterpret_cast<const float4*>(fr + k + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         feed(3 + k, f.x); feed(4 + k, f.y); feed(5 + k, f.z); feed(6 + k, f.w);
+        f = nxt;
       }
     } else {
       for (int k = 0; k < C; ++k) feed(3 + k, fr[k]);
