@@ -167,6 +167,27 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def cpu_training_step(T, N):
+    """CPU-baseline leg of the training benchmark (tools/bench_train.py): the reference's training step on the host cores
+    — the differentiable oracle port (oracle/train_oracle.py: reference math, torchdiffeq-0.0.1 odeint_adjoint
+    restatement) on a bounded sample, ONE sequence of the workload."""
+    from caspr_b200.synth import synthetic_state_dict, synthetic_sequences
+    from oracle.train_oracle import TrainOracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synthetic_state_dict(0, cnf_init='vigorous')
+    x, nocs = synthetic_sequences(1, T, N, seed=200)
+    e = torch.randn(T, N, 3, generator=torch.Generator().manual_seed(0))
+    orc = TrainOracle(sd)
+    t0 = time.perf_counter()
+    loss = TrainOracle.loss(*orc.forward_train(x, nocs, e))
+    loss.backward()
+    dt = time.perf_counter() - t0
+    return {'metric': 'trained_points_per_sec', 'value': T * N / dt, 'unit': 'points/s', 'cores': cores, 'kind': 'port',
+            'sample': '1 sequence (T=%d, N=%d), forward + backward, 1 run, %.1f s, nfe %s' % (T, N, dt, orc.get_nfe())}
+
+
+
 # ----------------------------------------------------------------------------------- ours
 def run_ours(args, rank, world, local_rank):
     if not torch.cuda.is_available():

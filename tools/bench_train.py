@@ -17,6 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 import torch                      # noqa: E402
+from bench import cpu_training_step          # noqa: E402  (the CPU-baseline leg lives in bench.py)
 
 
 def main():
@@ -26,8 +27,14 @@ def main():
     ap.add_argument('--batch', type=int, default=8)
     ap.add_argument('--frames', type=int, default=5)
     ap.add_argument('--points', type=int, default=1024)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
+    if args.impl == 'reference':
+        if rank == 0:
+            print(json.dumps(dict(cpu_training_step(args.frames, args.points), impl='reference', n_gpus=world)), flush=True)
+        return
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
@@ -96,6 +103,8 @@ def main():
                            'latent_adjoint_info': model.latent_ode.solver.last_adjoint_info[:4],
                            'loss': losses[-1], 'gradient_elements': sum(p.numel() for p in model.parameters())},
                 'gpu_launches': int(launches)}
+        if world == 1 and not args.no_cpu_baseline:
+            line['cpu_baseline'] = cpu_training_step(T, N)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
