@@ -104,10 +104,13 @@ adj_act_kernel(const float* __restrict__ A, const float* __restrict__ Ad, const 
   // the grid stride (gridDim.x * 256) is a multiple of H/4, so a thread always works on the same four channels
   float cmx[4] = {0.f, 0.f, 0.f, 0.f};
   int cch = -1;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
-    const long long pt = i / h4;
-    const int c = (int)(i - pt * h4) * 4;
-    const int f = (int)(pt / P);
+  // total4 = n * H/4 < 2^31 (n < 2^30 / ... checked by the caller): 32-bit index arithmetic
+  const unsigned tot = (unsigned)total4, stride = gridDim.x * blockDim.x, h4u = (unsigned)h4;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += stride) {
+    const unsigned ptu = i / h4u;
+    const long long pt = ptu;
+    const int c = (int)(i - ptu * h4u) * 4;
+    const int f = (int)(ptu / (unsigned)P);
     const float4 a4 = *reinterpret_cast<const float4*>(A + pt * H + c);
     const float4 d4 = *reinterpret_cast<const float4*>(Ad + pt * H + c);
     const float4 g4 = *reinterpret_cast<const float4*>(gate + (size_t)f * ld + c);
@@ -765,6 +768,7 @@ int enqueue_aug_eval(const AdjWorkspace& w, const caspr_cnf_weights* cw, const f
       b.y0, b.kbuf, (size_t)n, e, cw->W[0], H, n, pts, stage, gate, biasf, ctot, b.st, b.Ha, b.Va, cm_hv1);
   const dim3 ggrid(ceil_div(n, kMidBM), H / kMidBN);
   const long long total4 = (long long)n * H / 4;
+  if (tc && total4 >= (1ll << 31)) return CASPR_EINVAL;
   const int agrid = blocks_for(total4, 256 * 2, 148 * 16);
   // (2n x H) . W^T on the tcgen05 fp16x3 GEMM: rows [0,n) = activations, rows [n,2n) = tangents
   auto tc_product = [&](const float* X, int widx, float* Y) {

@@ -76,19 +76,63 @@ gn_finish_kernel(const float2* __restrict__ partial, int samples, int chunks, in
   mean_rstd[i] = make_float2((float)mean, (float)(1.0 / sqrt(m2 / m + (double)eps)));
 }
 
+// The same for samples split into many chunks (clouds): one WARP per (sample, group), lanes stride over the
+// (chunk, channel) partials - the thread-per-group loop above is a latency-bound serial walk there.
+__global__ void __launch_bounds__(256)
+gn_finish_warp_kernel(const float2* __restrict__ partial, int samples, int chunks, int C, int groups, int rps,
+                      int rows_per_chunk, float eps, float2* __restrict__ mean_rstd) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= samples * groups) return;
+  const int s = i / groups, g = i - s * groups;
+  const int cpg = C / groups;
+  const int items = chunks * cpg;
+  double wsum = 0.0;
+  for (int it = lane; it < items; it += 32) {
+    const int ch = it / cpg, c = g * cpg + (it - ch * cpg);
+    const int n = min(rps, (ch + 1) * rows_per_chunk) - ch * rows_per_chunk;
+    if (n > 0) wsum += (double)n * partial[((size_t)s * chunks + ch) * C + c].x;
+  }
+  wsum = warp_sum_d(wsum);
+  const double m = (double)rps * cpg;
+  const double mean = wsum / m;
+  double m2 = 0.0;
+  for (int it = lane; it < items; it += 32) {
+    const int ch = it / cpg, c = g * cpg + (it - ch * cpg);
+    const int n = min(rps, (ch + 1) * rows_per_chunk) - ch * rows_per_chunk;
+    if (n > 0) {
+      const float2 p = partial[((size_t)s * chunks + ch) * C + c];
+      const double d = (double)p.x - mean;
+      m2 += (double)p.y + (double)n * d * d;
+    }
+  }
+  m2 = warp_sum_d(m2);
+  if (lane == 0) mean_rstd[i] = make_float2((float)mean, (float)(1.0 / sqrt(m2 / m + (double)eps)));
+}
+
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const float* __restrict__ X, int ldx, const float2* __restrict__ mean_rstd, long long rows, int rps,
                 int C, int groups, const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
                 float* __restrict__ Y, int ldy) {
   const int cpg = C / groups;
   const long long total = rows * C;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / C;
-    const int c = (int)(i - r * C);
-    const float2 mr = mean_rstd[(r / rps) * groups + c / cpg];
-    float v = fmaf((X[r * ldx + c] - mr.x) * mr.y, gamma[c], beta[c]);
+  auto body = [&](auto r, int c) {                     // r: int (fast path) or long long
+    const float2 mr = mean_rstd[(long long)(r / rps) * groups + c / cpg];
+    float v = fmaf((X[(long long)r * ldx + c] - mr.x) * mr.y, gamma[c], beta[c]);
     if (relu) v = fmaxf(v, 0.f);
-    Y[r * ldy + c] = v;
+    Y[(long long)r * ldy + c] = v;
+  };
+  if (total < (1ll << 31)) {          // 32-bit index arithmetic: the 64-bit divisions dominate this kernel otherwise
+    const unsigned tot = (unsigned)total, stride = gridDim.x * blockDim.x, Cu = (unsigned)C;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += stride) {
+      const unsigned r = i / Cu;
+      body((int)r, (int)(i - r * Cu));
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const long long r = i / C;
+      body(r, (int)(i - r * C));
+    }
   }
 }
 
@@ -183,6 +227,28 @@ gn_bwd_group_kernel(const float2* __restrict__ partial, int samples, int chunks,
 }
 
 __global__ void __launch_bounds__(256)
+gn_bwd_group_warp_kernel(const float2* __restrict__ partial, int samples, int chunks, int C, int groups, int rps,
+                         const float* __restrict__ gamma, float2* __restrict__ gs) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= samples * groups) return;
+  const int s = i / groups, g = i - s * groups;
+  const int cpg = C / groups;
+  const int items = chunks * cpg;
+  double a = 0.0, b = 0.0;
+  for (int it = lane; it < items; it += 32) {
+    const int ch = it / cpg, c = g * cpg + (it - ch * cpg);
+    const float2 p = partial[((size_t)s * chunks + ch) * C + c];
+    a += (double)gamma[c] * p.x;
+    b += (double)gamma[c] * p.y;
+  }
+  a = warp_sum_d(a);
+  b = warp_sum_d(b);
+  const double m = (double)rps * cpg;
+  if (lane == 0) gs[i] = make_float2((float)(a / m), (float)(b / m));
+}
+
+__global__ void __launch_bounds__(256)
 gn_bwd_apply_kernel(const float* __restrict__ dY, int lddy, const float* __restrict__ dMax, int ld_dmax,
                     const int32_t* __restrict__ argmax, const float* __restrict__ X, int ldx,
                     const float2* __restrict__ mean_rstd, const float2* __restrict__ gs, long long rows, int rps, int C,
@@ -190,17 +256,27 @@ gn_bwd_apply_kernel(const float* __restrict__ dY, int lddy, const float* __restr
                     float* __restrict__ dX, int lddx) {
   const int cpg = C / groups;
   const long long total = rows * C;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / C;
-    const int c = (int)(i - r * C);
+  auto body = [&](auto r, int c) {                     // r: int (fast path) or long long
     const int s = (int)(r / rps);
     const int g = c / cpg;
     const float2 mr = mean_rstd[s * groups + g];
     const float2 sg = gs[s * groups + g];
-    const float xh = (X[r * ldx + c] - mr.x) * mr.y;
+    const float xh = (X[(long long)r * ldx + c] - mr.x) * mr.y;
     const float y = fmaf(xh, gamma[c], beta[c]);
-    const float d = gn_dy_eff(dY, lddy, dMax, ld_dmax, argmax, r, s, (int)(r - (long long)s * rps), c, C, y, relu);
-    dX[r * lddx + c] = mr.y * (d * gamma[c] - sg.x - xh * sg.y);
+    const float d = gn_dy_eff(dY, lddy, dMax, ld_dmax, argmax, (long long)r, s, (int)(r - s * rps), c, C, y, relu);
+    dX[(long long)r * lddx + c] = mr.y * (d * gamma[c] - sg.x - xh * sg.y);
+  };
+  if (total < (1ll << 31)) {
+    const unsigned tot = (unsigned)total, stride = gridDim.x * blockDim.x, Cu = (unsigned)C;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += stride) {
+      const unsigned r = i / Cu;
+      body((int)r, (int)(i - r * Cu));
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const long long r = i / C;
+      body(r, (int)(i - r * C));
+    }
   }
 }
 
@@ -427,8 +503,13 @@ extern "C" int caspr_gn_moments(const float* X, int ldx, int samples, int rows_p
   float2* partial = (float2*)workspace;
   const int threads = C >= 256 ? 256 : (C + 31) / 32 * 32;
   CASPR_COUNT(); gn_partial_kernel<<<dim3(samples, chunks), threads, 0, s>>>(X, ldx, rows_per_sample, C, rpc, partial);
-  CASPR_COUNT(); gn_finish_kernel<<<ceil_div(samples * groups, 128), 128, 0, s>>>(partial, samples, chunks, C, groups,
-                                                                                  rows_per_sample, rpc, eps, (float2*)mean_rstd);
+  if (chunks * (C / groups) >= 64) {
+    CASPR_COUNT(); gn_finish_warp_kernel<<<ceil_div(samples * groups, 8), 256, 0, s>>>(
+        partial, samples, chunks, C, groups, rows_per_sample, rpc, eps, (float2*)mean_rstd);
+  } else {
+    CASPR_COUNT(); gn_finish_kernel<<<ceil_div(samples * groups, 128), 128, 0, s>>>(
+        partial, samples, chunks, C, groups, rows_per_sample, rpc, eps, (float2*)mean_rstd);
+  }
   CASPR_CHECK_LAUNCH();
   return CASPR_OK;
 }
@@ -496,8 +577,13 @@ extern "C" int caspr_gn_backward(const float* dY, int lddy, const float* dMax, i
   CASPR_COUNT(); gn_bwd_partial_kernel<<<dim3(samples, chunks), threads, 0, s>>>(
       dY, lddy, dMax, ld_dmax, argmax, X, ldx, (const float2*)mean_rstd, rows_per_sample, C, groups, gamma, beta, relu,
       rpc, partial);
-  CASPR_COUNT(); gn_bwd_group_kernel<<<ceil_div(samples * groups, 128), 128, 0, s>>>(partial, samples, chunks, C, groups,
-                                                                                     rows_per_sample, gamma, gs);
+  if (chunks * (C / groups) >= 64) {
+    CASPR_COUNT(); gn_bwd_group_warp_kernel<<<ceil_div(samples * groups, 8), 256, 0, s>>>(partial, samples, chunks, C, groups,
+                                                                                         rows_per_sample, gamma, gs);
+  } else {
+    CASPR_COUNT(); gn_bwd_group_kernel<<<ceil_div(samples * groups, 128), 128, 0, s>>>(partial, samples, chunks, C, groups,
+                                                                                       rows_per_sample, gamma, gs);
+  }
   // parameter gradients: column sums of the partials viewed as (samples*chunks) x 2C interleaved (dbeta, dgamma)
   const long long rps_split = (prow + csplit - 1) / csplit;
   CASPR_COUNT(); colsum_partial_kernel<<<dim3(ceil_div(2 * C, 128), csplit), 128, 0, s>>>((const float*)partial, 2 * C, prow,
