@@ -113,6 +113,99 @@ split_rows_kernel(const float* __restrict__ x, int ld, long long rows, int cols,
   }
 }
 
+// Single-read variant of split_rows_kernel for rows of at most KCH*128 columns with 16-byte aligned rows: a warp keeps
+// the whole (transformed) row in registers as KCH float4 per lane, so the row is read from memory ONCE with all its
+// loads in flight together, and the planes are written as 8-byte pieces (256 contiguous bytes per warp and plane).
+template <int KCH>
+__global__ void __launch_bounds__(256)
+split_rows_reg_kernel(const float* __restrict__ x, int ld, long long rows, int cols, long long rows_pad, int k_pad,
+                      int relu, __half* __restrict__ hi, __half* __restrict__ lo, float* __restrict__ inv_scale,
+                      NormFold nf) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows_pad; r += warps) {
+    uint2* h = reinterpret_cast<uint2*>(hi + r * k_pad);
+    uint2* l = reinterpret_cast<uint2*>(lo + r * k_pad);
+    if (r >= rows) {
+#pragma unroll
+      for (int j = 0; j < KCH; ++j) {
+        const int c = 4 * (lane + 32 * j);
+        if (c < k_pad) { h[c / 4] = make_uint2(0u, 0u); l[c / 4] = make_uint2(0u, 0u); }
+      }
+      if (lane == 0) inv_scale[r] = 0.f;
+      continue;
+    }
+    const float* xr = x + r * ld;
+    const float2* tab_row = nf.tab ? nf.tab + (r / nf.rows_per_sample) * nf.C : nullptr;
+    float v[KCH][4];
+#pragma unroll
+    for (int j = 0; j < KCH; ++j) {
+      const int c = 4 * (lane + 32 * j);
+      if (c + 3 < cols) {
+        const float4 f = *reinterpret_cast<const float4*>(xr + c);
+        v[j][0] = f.x; v[j][1] = f.y; v[j][2] = f.z; v[j][3] = f.w;
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[j][u] = c + u < cols ? xr[c + u] : 0.f;
+      }
+    }
+    float m = 0.f;
+#pragma unroll
+    for (int j = 0; j < KCH; ++j) {
+      const int c = 4 * (lane + 32 * j);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float a = v[j][u];
+        if (c + u < cols) {
+          if (tab_row) a = fold_apply(nf, tab_row, a, c + u);
+          if (relu) a = fmaxf(a, 0.f);
+        } else {
+          a = 0.f;
+        }
+        v[j][u] = a;
+        m = fmaxf(m, fabsf(a));
+      }
+    }
+    m = warp_max(m);
+    float s = 1.f, inv = 1.f;
+    if (m > 0.f && m < 3.0e38f) {
+      int e;
+      frexpf(m, &e);
+      s = ldexpf(1.f, 14 - e);
+      inv = ldexpf(1.f, e - 14);
+    }
+    if (lane == 0) inv_scale[r] = inv;
+#pragma unroll
+    for (int j = 0; j < KCH; ++j) {
+      const int c = 4 * (lane + 32 * j);
+      if (c >= k_pad) continue;
+      uint32_t h0, l0, h1, l1;
+      tcg::split2(v[j][0] * s, v[j][1] * s, h0, l0);
+      tcg::split2(v[j][2] * s, v[j][3] * s, h1, l1);
+      h[c / 4] = make_uint2(h0, h1);
+      l[c / 4] = make_uint2(l0, l1);
+    }
+  }
+}
+
+// dispatch: register-resident rows when they fit and are aligned, the generic two-pass kernel otherwise
+void launch_split_rows(const float* x, int ld, long long rows, int cols, long long rows_pad, int k_pad, int relu,
+                       __half* hi, __half* lo, float* inv_scale, const NormFold& nf, int blocks, cudaStream_t s) {
+  const bool aligned = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (k_pad % 4 == 0);
+  const int kch = (cols + 127) / 128;
+#define CASPR_SPLIT_REG(K)                                                                                     \
+  split_rows_reg_kernel<K><<<blocks, 256, 0, s>>>(x, ld, rows, cols, rows_pad, k_pad, relu, hi, lo, inv_scale, nf)
+  if (aligned && kch <= 1) CASPR_SPLIT_REG(1);
+  else if (aligned && kch <= 2) CASPR_SPLIT_REG(2);
+  else if (aligned && kch <= 4) CASPR_SPLIT_REG(4);
+  else if (aligned && kch <= 8) CASPR_SPLIT_REG(8);
+  else if (aligned && kch <= 13) CASPR_SPLIT_REG(13);
+  else
+    split_rows_kernel<<<blocks, 256, 0, s>>>(x, ld, rows, cols, rows_pad, k_pad, relu, (__half2*)hi, (__half2*)lo,
+                                             inv_scale, nf);
+#undef CASPR_SPLIT_REG
+}
+
 struct LinearEpilogue {
   const float* bias;
   const float* x_inv;     // per-row 1/scale of X
@@ -565,8 +658,7 @@ extern "C" int caspr_linear_tc(const float* X, int ldx, const float* W, int ldw,
     nf.tab = (const float2*)in_norm->table; nf.rows_per_sample = in_norm->rows_per_sample; nf.C = Cin;
     nf.relu = in_norm->relu;
   }
-  CASPR_COUNT(); split_rows_kernel<<<nb, 256, 0, s>>>(X, ldx, rows, Cin, l.rows_pad, l.k_pad, act_in == CASPR_ACT_RELU,
-                                       (__half2*)xhi, (__half2*)xlo, xinv, nf);
+  CASPR_COUNT(); launch_split_rows(X, ldx, rows, Cin, l.rows_pad, l.k_pad, act_in == CASPR_ACT_RELU, xhi, xlo, xinv, nf, nb, s);
   CASPR_CHECK_LAUNCH();
   if (out_stats) {
     const size_t n_stats = (size_t)(rows / out_stats->rows_per_sample) * out_stats->groups * 2;
