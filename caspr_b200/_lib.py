@@ -122,6 +122,7 @@ SIGNATURES = {
     'caspr_assemble_batch': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int, c_double, c_int,
                                      _P, _P, _P]),
     'caspr_chamfer': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P]),
+    'caspr_tnocs_error': (c_int, [_P, _P, c_int, c_int, _P, _P, _P]),
     'caspr_emd_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'caspr_emd': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
 }

@@ -121,3 +121,41 @@ extern "C" int caspr_chamfer(const float* a, const float* b, int B, int P, int Q
   CASPR_CHECK_LAUNCH();
   return CASPR_OK;
 }
+
+// ------------------------------------------------------------------ T-NOCS regression error (next row 8f.4, first half)
+// utils/evaluations.py:243-254 (test_tnocs_regression): per frame, mean over the points of the L2 distance between the
+// predicted and the ground-truth NOCS position, and of the absolute time difference.  One CTA per frame.
+namespace {
+__global__ void __launch_bounds__(256)
+tnocs_error_kernel(const float4* __restrict__ pred, const float4* __restrict__ gt, int N, float* __restrict__ space,
+                   float* __restrict__ time_err) {
+  __shared__ float s_a[8], s_b[8];
+  const size_t base = (size_t)blockIdx.x * N;
+  float a = 0.f, b = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float4 p = pred[base + i], g = gt[base + i];
+    const float dx = p.x - g.x, dy = p.y - g.y, dz = p.z - g.z;
+    a += sqrtf(dx * dx + dy * dy + dz * dz);
+    b += fabsf(p.w - g.w);
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = a; s_b[threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ta = 0.f, tb = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { ta += s_a[w]; tb += s_b[w]; }
+    space[blockIdx.x] = ta / (float)N;
+    time_err[blockIdx.x] = tb / (float)N;
+  }
+}
+}  // namespace
+
+extern "C" int caspr_tnocs_error(const float* pred, const float* gt, int frames, int N, float* space, float* time_err,
+                                 void* stream) {
+  CASPR_REQUIRE(pred && gt && space && time_err && frames > 0 && N > 0);
+  CASPR_REQUIRE((((uintptr_t)pred | (uintptr_t)gt) & 15) == 0);
+  CASPR_COUNT(); tnocs_error_kernel<<<frames, 256, 0, (cudaStream_t)stream>>>((const float4*)pred, (const float4*)gt, N, space, time_err);
+  CASPR_CHECK_LAUNCH();
+  return CASPR_OK;
+}

@@ -554,3 +554,16 @@ def emd(a, b):
     _count('emd')
     check(lib.caspr_emd(_p(a), _p(b), B, n, m, _p(cost), _p(ws), nb, _stream()), 'caspr_emd')
     return cost
+
+
+def tnocs_error(pred, gt):
+    """evaluations.py:243-254: pred, gt (B,T,N,4) -> (space (B,T), time (B,T)): per-frame mean L2 position error and
+    mean absolute time error of the T-NOCS regression."""
+    pred, gt = _f32(pred, 'pred').contiguous(), _f32(gt, 'gt').contiguous()
+    B, T, N, four = pred.shape
+    assert four == 4 and gt.shape == pred.shape
+    space = torch.empty(B, T, dtype=torch.float32, device=pred.device)
+    terr = torch.empty(B, T, dtype=torch.float32, device=pred.device)
+    _count('tnocs_error')
+    check(lib.caspr_tnocs_error(_p(pred), _p(gt), B * T, N, _p(space), _p(terr), _stream()), 'caspr_tnocs_error')
+    return space, terr

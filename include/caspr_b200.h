@@ -384,6 +384,11 @@ int caspr_assemble_batch(const double* nocs, const double* depth, const long lon
 int caspr_chamfer(const float* a, const float* b, int B, int P, int Q,
                   float* d_ab, float* d_ba, void* stream);
 
+/* T-NOCS regression error (utils/evaluations.py:243-254, test_tnocs_regression): pred, gt (frames,N,4) rows [x,y,z,t]
+ * -> space[frame] = mean_i |pred_xyz - gt_xyz|_2, time_err[frame] = mean_i |pred_t - gt_t|. */
+int caspr_tnocs_error(const float* pred, const float* gt, int frames, int N, float* space, float* time_err,
+                      void* stream);
+
 /* Approximate earth mover's distance (reference utils/emd.py:11-12 -> emd_cuda approxmatch_forward + matchcost_forward,
  * evaluations.py:45-46): xyz1 (B,n,3), xyz2 (B,m,3) -> cost (B) = sum of match(k,l) |p_k - q_l| after the ten
  * annealing levels of the published approxmatch algorithm (oracle/emd_oracle.py).  The match matrix is never stored. */

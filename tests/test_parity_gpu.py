@@ -292,6 +292,17 @@ def test_emd_properties(ops):
     assert torch.allclose(ops.emd(a, b), ops.emd(b, a), rtol=0.05)
 
 
+def test_tnocs_error_matches_reference_formula(ops):
+    """T-NOCS regression error exactly as utils/evaluations.py:243-254 computes it (torch on the same tensors)."""
+    g = torch.Generator().manual_seed(3)
+    pred = torch.rand(3, 10, 2048, 4, generator=g).to(DEV)
+    gt = torch.rand(3, 10, 2048, 4, generator=g).to(DEV)
+    space, terr = ops.tnocs_error(pred, gt)
+    diff = pred[:, :, :, :3] - gt[:, :, :, :3]
+    assert _rel(space, torch.mean(torch.norm(diff, dim=3), dim=2)) < 1e-5
+    assert _rel(terr, torch.mean(torch.abs(pred[:, :, :, 3] - gt[:, :, :, 3]), dim=2)) < 1e-5
+
+
 # ---------------------------------------------------------------------------- model level
 @pytest.fixture(scope='module', params=['vig', 'def'])
 def case(request, golden_dir, lib_built):
