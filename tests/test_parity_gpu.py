@@ -303,6 +303,18 @@ def test_tnocs_error_matches_reference_formula(ops):
     assert _rel(terr, torch.mean(torch.abs(pred[:, :, :, 3] - gt[:, :, :, 3]), dim=2)) < 1e-5
 
 
+def test_eval_reconstr_frames_protocol(ops):
+    """The reference's per-frame reconstruction metrics (evaluations.py:36-49) at the protocol size, against the oracles."""
+    from caspr_b200.metrics import eval_reconstr_frames
+    from oracle.emd_oracle import approx_emd
+    g = torch.Generator().manual_seed(9)
+    gt = torch.rand(2, 2048, 3, generator=g) - 0.5
+    pred = gt[:, torch.randperm(2048, generator=g)] + 0.01 * torch.randn(2, 2048, 3, generator=g)
+    cd, emd = eval_reconstr_frames(pred.to(DEV), gt.to(DEV))
+    assert np.abs(cd - chamfer_distance(pred, gt).numpy()).max() < 1e-5 * np.abs(cd).max() + 1e-9
+    assert np.abs(emd - approx_emd(pred.numpy(), gt.numpy()) / 2048).max() < 2e-3 * np.abs(emd).max()
+
+
 # ---------------------------------------------------------------------------- model level
 @pytest.fixture(scope='module', params=['vig', 'def'])
 def case(request, golden_dir, lib_built):
