@@ -53,6 +53,24 @@ def test_get_item_oracle_matches_reference(gold, case):
     assert np.array_equal(inp, gold[case + '_input']) and np.array_equal(out, gold[case + '_output'])
 
 
+def test_read_sequence_host_decoding(gold, tmp_path):
+    """caspr_b200.data.read_sequence (host side of the loader, no GPU): depth falls back to the NOCS cloud for a frame
+    without depth data (caspr_dataset.py:174-176) and the first blank NOCS frame ends the valid range (:183-186)."""
+    data = pytest.importorskip('caspr_b200.data')
+    for tag, expect_valid in (('plain', 5), ('blank', 3), ('nodepth', 5)):
+        nocs, depth = _frames(gold, tag)
+        paths = []
+        for i, (a, b) in enumerate(zip(nocs, depth)):
+            p = tmp_path / ('%s_%d.npz' % (tag, i))
+            np.savez(p, nocs_data=a, depth_data=b, obj_T=np.eye(4))
+            paths.append(str(p))
+        rn, rd, n_valid = data.read_sequence(paths)
+        assert n_valid == expect_valid
+        for i in range(COUNTS):
+            assert np.array_equal(rn[i], nocs[i])
+            assert np.array_equal(rd[i], nocs[i] if depth[i].size == 0 else depth[i])
+
+
 @pytest.mark.gpu
 def test_device_assembly_bit_exact(gold, tmp_path):
     """Two-sequence batches through read_sequence -> DeviceSequences.assemble, every case of the fixture."""

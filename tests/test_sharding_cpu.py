@@ -9,7 +9,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from caspr_b200.sharding import (shard_range, gather_batch, reconstruct_sharded, max_over_ranks,
-                                 allreduce_gradients, train_step_sharded)
+                                 allreduce_gradients, train_step_sharded, gather_rows, lockstep)
 
 
 def test_shard_range_partitions():
@@ -153,6 +153,46 @@ def test_gradient_allreduce_world_size_2_gloo():
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]
+
+
+def _rows_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        # lock-step latent solve: every rank gathers the z0 rows of all ranks (uneven shards) and keeps its own slice
+        n_local = 3 if rank == 0 else 1
+        local = torch.arange(n_local * 4, dtype=torch.float32).view(n_local, 4) + 100 * rank
+        full, lo, hi = gather_rows(local)
+        ok = full.shape == (4, 4) and (lo, hi) == ((0, 3) if rank == 0 else (3, 4)) and torch.equal(full[lo:hi], local)
+        ok = ok and torch.equal(full[3], torch.arange(4, dtype=torch.float32) + 100)
+
+        class _M(object):
+            lockstep_group = False
+
+            def __init__(self):
+                self.point_cnf = type('F', (), {'lockstep_group': False})()
+        m = _M()
+        with lockstep(m, group=None):
+            ok = ok and m.lockstep_group is None and m.point_cnf.lockstep_group is None
+        ok = ok and m.lockstep_group is False and m.point_cnf.lockstep_group is False
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_rows_and_lockstep_switch_world_size_2_gloo():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rows_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
