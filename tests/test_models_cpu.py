@@ -59,3 +59,23 @@ def test_synthetic_generators_are_deterministic():
     x2, n2 = synthetic_sequences(2, 3, 128, seed=4)
     assert torch.equal(x1, x2) and torch.equal(n1, n2)
     assert x1.shape == (2, 3, 128, 4) and float(x1[..., 2].min()) > 0.5
+
+
+def test_training_gradient_layouts_match_parameter_order():
+    """The flat gradient buffers the adjoint entry points fill (caspr_cnf_adjoint / caspr_latent_ode_adjoint) are cut
+    into per-parameter views in ``parameters()`` order: sizes and order must match the modules (no GPU needed: the
+    *_param_count queries are host functions)."""
+    from caspr_b200._lib import lib
+    from caspr_b200.models import CaSPR
+    model = CaSPR()
+    cnf = model.point_cnf.chain[1]
+    names = [n for n, _ in cnf.odefunc.named_parameters()]
+    per_layer = ['_layer.weight', '_layer.bias', '_hyper_bias.weight', '_hyper_gate.weight', '_hyper_gate.bias']
+    assert names == ['diffeq.layers.%d.%s' % (l, s) for l in range(4) for s in per_layer]
+    assert lib.caspr_cnf_param_count(512, 1600) == sum(p.numel() for p in cnf.odefunc.parameters())
+    net = model.latent_ode.ode_func.dynamics_net
+    lat = [p for l in (net[0], net[2], net[4], net[6]) for p in (l.weight, l.bias)]
+    assert [tuple(p.shape) for p in lat] == [(512, 64), (512,), (512, 512), (512,), (512, 512), (512,), (64, 512), (64,)]
+    assert lib.caspr_latent_ode_param_count(64, 512) == sum(p.numel() for p in lat)
+    # shared module registered twice (latent_ode.ode_func / latent_ode.solver.ode_func): one set of Parameters
+    assert len(list(model.latent_ode.parameters())) == 8
