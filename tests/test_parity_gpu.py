@@ -243,6 +243,49 @@ def test_linear_gn_ball_fused(ops, balls, ns, cin, cout, relu):
     assert float(mx[:, :4].abs().sum()) == 0 and float(mx[:, 4 + cout:].abs().sum()) == 0
 
 
+@pytest.mark.parametrize('ns,widths,C', [(16, (16, 16, 32), 6), (32, (32, 32, 64), 6), (16, (32, 32, 64), 96),
+                                        (32, (32, 32, 64), 96), (32, (32, 32, 64), 0)])
+def test_sa_fused_matches_unfused_reference(ops, ns, widths, C):
+    """One scale of a set-abstraction level in one kernel (gather + 3 x [linear, per-ball GroupNorm, ReLU] + max) against
+    the same chain in fp64 torch on the SAME ball-query indices; ragged sizes, strided feature view (the level-1 input
+    is a column slice of the 9-channel point buffer), padded balls (radius small enough that many balls hold copies of one
+    point) and an output written into a column slice."""
+    g = torch.Generator().manual_seed(ns + C)
+    B, N, M = 3, 333, 77
+    xyz = torch.rand(B, N, 3, generator=g).to(DEV)
+    _, new_xyz = ops.fps(xyz, M)
+    idx, _ = ops.ball_query2(xyz, new_xyz, 0.12, ns, 0.5, 32)                       # many under-filled balls at r = .12
+    feat = None
+    if C:
+        wide = torch.randn(B, N, C + 3, generator=g).to(DEV)
+        feat = wide[:, :, 3:]
+    cin = 3 + C
+    convs, norms = [], []
+    dims = [cin] + list(widths)
+    for i in range(3):
+        conv = torch.nn.Conv1d(dims[i], dims[i + 1], 1)
+        gn = torch.nn.GroupNorm(16, dims[i + 1])
+        with torch.no_grad():
+            gn.weight.copy_(torch.rand(dims[i + 1], generator=g) + 0.5)
+            gn.bias.copy_(0.2 * torch.randn(dims[i + 1], generator=g))
+        convs.append(conv.to(DEV))
+        norms.append(gn.to(DEV))
+    assert ops.sa_fused_supported(ns, cin, list(widths))
+    out = torch.zeros(B * M, widths[2] + 10, device=DEV)
+    ops.sa_fused(xyz, new_xyz, feat, idx, convs, norms, out[:, 5:5 + widths[2]])
+    rows = ops.group_points(xyz, new_xyz, feat, idx).double()                         # (B*M*ns, cin)
+    h = rows.view(B * M, ns, cin).transpose(1, 2)
+    for i in range(3):
+        h = torch.nn.functional.conv1d(h, convs[i].weight.double(), convs[i].bias.double())
+        h = torch.nn.functional.group_norm(h, 16, norms[i].weight.double(), norms[i].bias.double(), eps=1e-5)
+        if i < 2:
+            h = h.relu()
+    ref = h.max(2)[0]
+    # padded balls divide rounding noise by sqrt(eps) = 316 in BOTH implementations: 2e-4 instead of 2e-5
+    assert _rel(out[:, 5:5 + widths[2]], ref) < 2e-4
+    assert float(out[:, :5].abs().sum()) == 0 and float(out[:, 5 + widths[2]:].abs().sum()) == 0
+
+
 def test_augment_and_broadcast(ops):
     x, _ = synthetic_sequences(1, 2, 100, seed=0)
     x4 = x.view(-1, 4)
@@ -546,6 +589,20 @@ def test_flow_round_trip(case, engine):
     _, _, model, _, _, _ = case
     g = torch.Generator().manual_seed(8)
     F, P = 4, 512
+    ctx = (0.5 * torch.randn(F, 1600, generator=g)).to(DEV)
+    y = torch.randn(F, P, 3, generator=g).to(DEV)
+    e = torch.randn(F, P, 3, generator=g).to(DEV)
+    x = model.point_cnf(y, ctx, reverse=True, e=e)
+    y2, dlogp = model.point_cnf(x, ctx, torch.zeros(F, P, 1, device=DEV), e=e)
+    assert _rel(y2, y) < 2e-3
+    assert torch.isfinite(dlogp).all()
+
+
+def test_flow_round_trip_at_full_size(case):
+    """The same property at BASELINE config 2's full size (80 frames x 2048 points) on the tensor-core engine."""
+    _, _, model, _, _, _ = case
+    g = torch.Generator().manual_seed(18)
+    F, P = 80, 2048
     ctx = (0.5 * torch.randn(F, 1600, generator=g)).to(DEV)
     y = torch.randn(F, P, 3, generator=g).to(DEV)
     e = torch.randn(F, P, 3, generator=g).to(DEV)
