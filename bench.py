@@ -51,6 +51,12 @@ def parse_args():
     ap.add_argument('--cnf-init', default='vigorous', choices=['vigorous', 'default'])
     ap.add_argument('--engine', default='auto', choices=['auto', 'simt', 'tc'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-clock-sampler', action='store_true',
+                    help='do not spawn the nvidia-smi sampler (it hangs under ncu): lets bench.py itself be profiled')
+    ap.add_argument('--no-extra-configs', action='store_true',
+                    help='skip the "configs" block (BASELINE configs[2..4] per-GPU shards)')
+    ap.add_argument('--ref-budget-s', type=float, default=240.0,
+                    help='--impl reference: wall-clock budget for the timed steps (each step is the full batch)')
     return ap.parse_args()
 
 
@@ -137,31 +143,70 @@ def cpu_reference_step(oracle, x1, y1, e1, kwargs):
     return time.perf_counter() - t0
 
 
+def workload_config(workload, world, cnf_init, nfe):
+    """The `config` object both arms print (identical keys and values for the same workload)."""
+    B, T, N, P, S, _ = WORKLOADS[workload]
+    return {'workload': workload, 'batch_per_gpu': B, 'global_batch': B * world, 'frames': T, 'input_points': N,
+            'sampled_points': P, 'query_steps': S if S is not None else T, 'cnf_init': cnf_init,
+            'nfe_latent_cnf': [int(v) for v in nfe], 'parallelism': 'batch-shard x%d' % world}
+
+
+class ReferenceModules(object):
+    """The reference's own `models.caspr.CaSPR` (unmodified, imported from /root/reference over the oracle shims for its
+    absent dependencies) behind the oracle's reconstruct signature; only where /root/reference exists."""
+
+    def __init__(self, sd):
+        from oracle.reference_loader import build_reference_caspr
+        self.model = build_reference_caspr()
+        self.model.load_state_dict(sd)
+        self.model.eval()
+
+    def reconstruct(self, x, y=None, e=None, **kwargs):
+        # the unmodified modules draw y and e themselves (CPU generator): same cost, different values
+        with torch.no_grad():
+            return self.model.reconstruct(x, **kwargs)
+
+    def get_nfe(self):
+        return [int(v) for v in self.model.get_nfe()]
+
+
 def run_reference(args, rank, world):
-    """The reference's own CPU path (PyTorch + torchdiffeq-0.0.1 semantics) on the host cores.  The
-    reference's dependencies cannot be installed here, so this is the oracle port of the same math
-    (kind "port"); each step is a bounded sample: ONE sequence of the workload."""
+    """The reference's own CPU path (PyTorch + torchdiffeq-0.0.1 semantics) on all host cores: the unmodified reference
+    modules over the oracle shims when /root/reference is present (kind "reference"), else the oracle port of the same
+    math (kind "port").  Every step is ONE `reconstruct` call over the FULL per-GPU batch of the workload — the same
+    batch-global step controllers as the GPU arm.  A full step costs about a minute of CPU, so the number of timed steps
+    is capped by --ref-budget-s and warm-up by one step; the line reports the steps actually run."""
     if rank != 0:
         return
-    from oracle.caspr_oracle import CasprOracle
+    from oracle.reference_loader import reference_available
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd, x, y, e, kwargs, (B, T, N, P, Tq) = make_inputs(args.workload, 0, args.cnf_init)
-    per_seq_y = y.shape[0] // B
-    x1, y1, e1 = x[:1], y[:per_seq_y], e[:Tq]
-    oracle = CasprOracle(sd)
-    for _ in range(args.warmup):
-        cpu_reference_step(oracle, x1, y1, e1, kwargs)
-    times = [cpu_reference_step(oracle, x1, y1, e1, kwargs) for _ in range(args.steps)]
+    if reference_available():
+        impl, kind = ReferenceModules(sd), 'reference'
+    else:
+        from oracle.caspr_oracle import CasprOracle
+        impl, kind = CasprOracle(sd), 'port'
+    t_first = cpu_reference_step(impl, x, y, e, kwargs)               # warm-up (page-in, thread pools)
+    n_warm = 1
+    while n_warm < args.warmup and t_first * (n_warm + 2) < 0.25 * args.ref_budget_s:
+        cpu_reference_step(impl, x, y, e, kwargs)
+        n_warm += 1
+    times = []
+    while len(times) < args.steps and (not times or sum(times) + times[-1] < args.ref_budget_s):
+        times.append(cpu_reference_step(impl, x, y, e, kwargs))
     total = sum(times)
-    pts = Tq * P * args.steps
-    value = pts / total
-    sample = '1 of %d sequences per step (B=1,T=%d,N=%d,P=%d), oracle port, %d threads' % (B, T, N, P, cores)
+    value = B * Tq * P * len(times) / total
+    sample = ('full per-GPU batch per step (B=%d,T=%d,N=%d,P=%d), %s, %d threads; %d of %d requested steps timed '
+              '(%.0f s budget), %d warm-up' % (B, T, N, P, 'unmodified reference modules over shims' if kind ==
+                                              'reference' else 'oracle port', cores, len(times), args.steps,
+                                              args.ref_budget_s, n_warm))
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
-            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps,
+            'steps': len(times), 'steps_requested': args.steps, 'warmup': n_warm,
+            'ms_per_step': 1e3 * total / len(times),
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': args.workload, 'cnf_init': args.cnf_init, 'nfe': oracle.get_nfe()},
-            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'config': workload_config(args.workload, max(args.gpus, 1), args.cnf_init, impl.get_nfe()),
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': sample},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line), flush=True)
@@ -186,6 +231,130 @@ def cpu_training_step(T, N):
     return {'metric': 'trained_points_per_sec', 'value': T * N / dt, 'unit': 'points/s', 'cores': cores, 'kind': 'port',
             'sample': '1 sequence (T=%d, N=%d), forward + backward, 1 run, %.1f s, nfe %s' % (T, N, dt, orc.get_nfe())}
 
+
+
+
+def lookup_traffic(engine, n_pts):
+    """profiles/traffic.json: {"<engine>:<points per launch>": {"bytes_per_launch": ..., "source": "<ncu summary>"}}."""
+    path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    try:
+        with open(path) as f:
+            entry = json.load(f).get('%s:%d' % (engine, n_pts))
+    except (OSError, ValueError):
+        entry = None
+    if not entry:
+        return None, 'no ncu capture for %s at %d points per launch under profiles/' % (engine, n_pts)
+    return float(entry['bytes_per_launch']), entry.get('source')
+
+
+def guarded(fn):
+    """The extra configs must never take the headline line down with them."""
+    try:
+        return fn()
+    except Exception as exc:                                   # noqa: BLE001
+        return {'error': '%s: %s' % (type(exc).__name__, str(exc)[:300])}
+
+
+def _max_over_ranks(values, dev, world):
+    t = torch.tensor(values, dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def time_reconstruct_config(model, workload, rank, world, dev, cnf_init, steps=3, warmup=3):
+    """Device-resident `reconstruct` over this rank's shard of another BASELINE workload (3 warm-up + 3 timed steps,
+    barrier + CUDA events, max over ranks)."""
+    _, x, y, e, kwargs, (B, T, N, P, Tq) = make_inputs(workload, rank, cnf_init)
+    x, y, e = x.to(dev), y.to(dev), e.to(dev)
+    kw = dict(kwargs)
+    if 'timestamps' in kw:
+        kw['timestamps'] = kw['timestamps'].to(dev)
+    for _ in range(warmup):
+        model.reconstruct(x, y=y, e=e, **kw)
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        model.reconstruct(x, y=y, e=e, **kw)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = _max_over_ranks([ev0.elapsed_time(ev1)], dev, world)[0] / steps
+    return {'ms_per_step': round(ms, 3), 'value': world * B * Tq * P / (ms * 1e-3), 'unit': UNIT, 'steps': steps,
+            'warmup': warmup, 'config': workload_config(workload, world, cnf_init, model.get_nfe())}
+
+
+def time_training_config(rank, world, dev, steps=3, warmup=3, B=8, T=5, N=1024):
+    """BASELINE configs[4] per-GPU shape: one training step = CaSPR.forward (train mode) -> loss (train_utils.py:148-166)
+    -> loss.backward() (hand-written encoder backward, CUDA adjoint solves) -> ONE flat NCCL all-reduce of the 16.26 M
+    gradient elements (no pack / unpack: `.grad`s are views of the flat buffer) -> Adam (train.py:135) -> broadcast of
+    rank 0's MovingBatchNorm statistics.  Weights are re-loaded before every step so the solvers see the same dynamics."""
+    from caspr_b200 import _lib
+    from caspr_b200.models import CaSPR
+    from caspr_b200.sharding import FlatGradients, broadcast_moving_batchnorm
+    from caspr_b200.synth import synthetic_state_dict, synthetic_sequences
+    sd = synthetic_state_dict(0, cnf_init='vigorous')
+    x, nocs = synthetic_sequences(B, T, N, seed=200 + rank)
+    x, nocs = x.to(dev), nocs.to(dev)
+    e = torch.randn(B * T, N, 3, generator=torch.Generator().manual_seed(rank)).to(dev)
+    model = CaSPR().to(dev).train()
+    flat = FlatGradients(model.parameters())
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+    phase = [0.0] * 5
+
+    def loss_fn(nll, tl1):
+        return 0.01 * nll.sum(2).mean() + 100.0 * tl1[:, :, :, :4].mean()
+
+    def step(timed):
+        model.load_state_dict(sd)
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        ev[0].record()
+        flat.zero()
+        loss = loss_fn(*model(x, nocs, e=e))
+        ev[1].record()
+        loss.backward()
+        ev[2].record()
+        if world > 1:
+            flat.allreduce(average=True)
+        ev[3].record()
+        opt.step()
+        ev[4].record()
+        if world > 1:
+            broadcast_moving_batchnorm(model)
+        ev[5].record()
+        torch.cuda.synchronize()
+        if timed:
+            for i in range(5):
+                phase[i] += ev[i].elapsed_time(ev[i + 1])
+        return float(loss.detach())
+
+    for _ in range(warmup):
+        step(False)
+    n0 = _lib.lib.caspr_launch_count()
+    losses = [step(True) for _ in range(steps)]
+    launches = _lib.lib.caspr_launch_count() - n0
+    tot, ar = _max_over_ranks([sum(phase), phase[2]], dev, world)
+    ms, ar_ms = tot / steps, ar / steps
+    nbytes = flat.flat.numel() * 4
+    out = {'ms_per_step': round(ms, 3), 'value': world * B * T * N / (ms * 1e-3), 'unit': 'trained points/s',
+           'steps': steps, 'warmup': warmup,
+           'config': {'workload': 'airplanes_train_T%d_N%d_B%d' % (T, N, B), 'batch_per_gpu': B, 'global_batch': B * world,
+                      'frames': T, 'input_points': N, 'nfe_latent_cnf_forward': [int(v) for v in model.get_nfe()],
+                      'optimizer': 'Adam', 'parallelism': 'batch-shard x%d + gradient all-reduce' % world},
+           'phase_ms_forward_backward_allreduce_adam_bufsync': [round(v / steps, 3) for v in phase],
+           'loss': losses[-1], 'gradient_bytes': nbytes, 'gpu_launches_per_step': int(launches // steps),
+           'allreduce_ms': round(ar_ms, 3) if world > 1 else None,
+           # NCCL bus bandwidth of a ring/tree all-reduce: 2 (n-1)/n x bytes / time; NVLink 5 offers 900 GB/s per direction
+           'allreduce_busbw_gbs': round(2.0 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9, 1) if world > 1 else None}
+    return out
 
 
 # ----------------------------------------------------------------------------------- ours
@@ -242,7 +411,7 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     barrier()
     torch.cuda.synchronize()
-    if rank == 0:
+    if rank == 0 and not args.no_clock_sampler:
         sampler.start()
     lib.caspr_profile_enable(1)
     launches0 = lib.caspr_launch_count()
@@ -296,6 +465,18 @@ def run_ours(args, rank, world, local_rank):
     phases()
     phase_ms = [round(v, 3) for v in phases()]
 
+    # ---- BASELINE configs[2..4]: per-GPU shards of the other reconstruction workloads and one training step
+    extra = None
+    if not args.no_extra_configs and args.workload == DEFAULT_WORKLOAD:
+        del x_dev, y_dev, e_dev
+        extra = {}
+        for name in sorted(WORKLOADS):
+            if name != args.workload:
+                extra[name] = guarded(lambda: time_reconstruct_config(model, name, rank, world, dev, args.cnf_init))
+        model = None
+        torch.cuda.empty_cache()
+        extra['airplanes_train_T5_N1024_B8'] = guarded(lambda: time_training_config(rank, world, dev))
+
     t = torch.tensor([ms, ms_e2e, float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         import torch.distributed as dist
@@ -330,18 +511,13 @@ def run_ours(args, rank, world, local_rank):
         avg_ms = tot_ms / cnt
         flop_per_launch = layer_flop / chunks
         achieved = flop_per_launch / (avg_ms * 1e-3) / 1e12
-        # DRAM bytes per launch from the committed ncu --set full capture of the same kernels on this workload
-        # (profiles/r1_ncu_cnf_gemm_fp16x3_tcgen05.txt: layer 1 reads 672.5 MB + writes 619.1 MB, layer 2 reads
-        # 677.8 MB + writes 7.9 MB; profiles/r1_ncu_cnf_mid_layer_simt.txt: 2686 MB + 651 MB); algorithmic bytes
-        # are 671 MB per plane pass, i.e. 1342 MB (layer 1) and 671 MB (layer 2)
-        traffic = None
-        if B * Tq * P == 163840:
-            traffic = (672.53e6 + 619.10e6 + 677.78e6 + 7.89e6) / 2 if 'tcgen05' in kname else 2686.1e6 + 650.7e6
-            traffic *= flop_per_launch / layer_flop            # the capture covered all points in one launch
+        # DRAM bytes per launch: read from the committed summary of the ncu --set full capture of this kernel on this
+        # shape (profiles/traffic.json, written by tools/ncu_summary.py --traffic); None when no capture matches
+        traffic, traffic_src = lookup_traffic('tc' if 'tcgen05' in kname else 'simt', n_pts // chunks)
         roofline = {'bound': 'tensor', 'kernel': kname, 'achieved': achieved, 'peak': peaks['tf_sustained'],
                     'unit': 'TFLOP/s', 'frac': achieved / peaks['tf_sustained'], 'traffic': traffic,
                     'traffic_unit': 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, average of '
-                                    'the two H x H layers)',
+                                    'the two H x H layers)', 'traffic_source': traffic_src,
                     'peak_source': peaks['source'] + ' bf16 dense sustained', 'launches': cnt,
                     'avg_launch_ms': avg_ms, 'share_of_step': tot_ms / (ms / args.steps) / args.steps,
                     'flop_per_launch': flop_per_launch,
@@ -364,13 +540,13 @@ def run_ours(args, rank, world, local_rank):
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': args.workload, 'batch_per_gpu': B, 'global_batch': B * world, 'frames': T,
-                       'input_points': N, 'sampled_points': P, 'query_steps': Tq, 'cnf_init': args.cnf_init,
-                       'nfe_latent_cnf': nfe, 'engine': engine_name, 'phase_ms_encode_latent_decode': phase_ms, 'parallelism': 'batch-shard x%d' % world,
+            'config': workload_config(args.workload, world, args.cnf_init, nfe),
+            'detail': {'engine': engine_name, 'phase_ms_encode_latent_decode': phase_ms,
                        'l2': 'working set per dynamics evaluation (>1 GB of activations) exceeds the 126 MB L2; no flush'},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(x.numel() * 4 + y.numel() * 4),
                     'd2h_bytes_per_step': int(B * Tq * P * 3 * 4), 'ms_per_step': ms_e2e / args.steps},
-            'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline}
+            'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
+            'configs': extra}
     print(json.dumps(line), flush=True)
 
 

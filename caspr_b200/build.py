@@ -21,6 +21,7 @@ LIB_DIR = os.path.join(HERE, 'lib')
 OBJ_DIR = os.path.join(HERE, 'build')
 LIB_PATH = os.path.join(LIB_DIR, 'libcaspr_b200.so')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
+EXPORTS = os.path.join(CSRC, 'exports.map')      # only the caspr_* C entry points leave the library
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-I', INCLUDE,
@@ -42,7 +43,7 @@ def _digest():
     h = hashlib.sha256()
     for root in (CSRC, INCLUDE):
         for f in sorted(os.listdir(root)):
-            if f.endswith(('.cu', '.cuh', '.h')):
+            if f.endswith(('.cu', '.cuh', '.h', '.map')):
                 with open(os.path.join(root, f), 'rb') as fh:
                     h.update(f.encode())
                     h.update(fh.read())
@@ -72,7 +73,8 @@ def build_library(force=False, verbose=False):
     srcs = _sources()
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(_compile, srcs))
-    cmd = [_nvcc(), '-shared', '-o', LIB_PATH] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
+    cmd = [_nvcc(), '-shared', '-o', LIB_PATH] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a',
+                                                         '-Xlinker', '--version-script=' + EXPORTS]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))

@@ -138,15 +138,90 @@ def allreduce_gradients(parameters, group=None, average=True):
     return flat.numel()
 
 
-def train_step_sharded(model, optimizer, x, sample_points, loss_fn, group=None, **forward_kwargs):
+class FlatGradients(object):
+    """Gradients of a model kept as views into ONE persistent flat fp32 buffer, so the per-step all-reduce needs no
+    pack / unpack copies (round 1 issued ~440 small copy kernels per step for them).
+
+    ``p.grad`` of every trainable parameter is a view of ``self.flat``; autograd accumulates into the views in place.
+    Use ``zero()`` instead of ``optimizer.zero_grad()`` (whose default ``set_to_none=True`` would drop the views —
+    ``attach()`` re-establishes them if that happened)."""
+
+    def __init__(self, parameters):
+        self.params = [p for p in parameters if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device if self.params else 'cpu'
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.views = []
+        off = 0
+        for p in self.params:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        self.attach()
+
+    def attach(self):
+        for p, v in zip(self.params, self.views):
+            if p.grad is not v:
+                if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                    v.copy_(p.grad)
+                p.grad = v
+
+    def zero(self):
+        self.attach()
+        self.flat.zero_()
+
+    def allreduce(self, group=None, average=True):
+        """ONE sum all-reduce of the flat buffer (16.26 M floats = 65 MB for CaSPR).  Returns the element count."""
+        self.attach()
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            self.flat /= dist.get_world_size(group)
+        return self.flat.numel()
+
+
+def moving_batchnorm_buffers(model):
+    """The running statistics that feed the NEXT forward pass (normalization.py:60-64): ``running_mean``,
+    ``running_var`` and ``step`` of every MovingBatchNorm layer, in module order."""
+    bufs = []
+    for m in model.modules():
+        if hasattr(m, 'running_mean') and hasattr(m, 'running_var') and hasattr(m, 'step'):
+            bufs += [m.running_mean, m.running_var, m.step]
+    return bufs
+
+
+def broadcast_moving_batchnorm(model, src=0, group=None):
+    """DataParallel semantics for the MovingBatchNorm statistics: the reference's ``nn.DataParallel`` (train.py:131-132)
+    re-broadcasts replica 0's buffers before every forward, so all replicas normalise with ONE set of statistics
+    (those updated from replica 0's shard, normalization.py:43-64).  Here every rank updates its own copy during the
+    step; this sends rank ``src``'s copy to everyone (one broadcast of 14 floats for CaSPR) so the next forward and
+    any rank's checkpoint see identical buffers.  Returns the number of elements sent."""
+    bufs = moving_batchnorm_buffers(model)
+    if not bufs:
+        return 0
+    flat = torch.cat([b.detach().reshape(-1).to(torch.float32) for b in bufs])
+    dist.broadcast(flat, src=src if group is None else dist.get_global_rank(group, src), group=group)
+    off = 0
+    with torch.no_grad():
+        for b in bufs:
+            b.copy_(flat[off:off + b.numel()].view_as(b))
+            off += b.numel()
+    return off
+
+
+def train_step_sharded(model, optimizer, x, sample_points, loss_fn, group=None, flat_grads=None, **forward_kwargs):
     """One data-parallel training step (train_utils.py:118-175 under ``--parallel``): rank r runs forward + backward on
-    its slice of the batch, gradients are averaged with one all-reduce, every rank applies the same optimizer step.
+    its slice of the batch, gradients are averaged with one all-reduce, every rank applies the same optimizer step,
+    and rank 0's MovingBatchNorm statistics are broadcast (``broadcast_moving_batchnorm``).
 
     ``loss_fn(nll, tnocs_l1) -> scalar`` must be a MEAN over the sequences it is given; shards of equal size then
-    reproduce the single-process gradient.  Returns this rank's loss (python float; nan for an empty shard)."""
+    reproduce the single-process gradient.  ``flat_grads``: a ``FlatGradients`` over ``model.parameters()`` (kept by
+    the caller across steps) makes the reduction copy-free; without it the gradients are packed per step.
+    Returns this rank's loss (python float; nan for an empty shard)."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     lo, hi = shard_range(x.shape[0], rank, world)
-    optimizer.zero_grad()
+    if flat_grads is not None:
+        flat_grads.zero()
+    else:
+        optimizer.zero_grad()
     loss_value = float('nan')
     if hi > lo:
         kw = dict(forward_kwargs)
@@ -157,6 +232,10 @@ def train_step_sharded(model, optimizer, x, sample_points, loss_fn, group=None, 
         loss = loss_fn(*losses)
         loss.backward()
         loss_value = float(loss.detach())
-    allreduce_gradients(model.parameters(), group=group, average=True)
+    if flat_grads is not None:
+        flat_grads.allreduce(group=group, average=True)
+    else:
+        allreduce_gradients(model.parameters(), group=group, average=True)
     optimizer.step()
+    broadcast_moving_batchnorm(model, src=0, group=group)
     return loss_value

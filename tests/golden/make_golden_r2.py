@@ -1,0 +1,119 @@
+"""Freeze round-2 golden vectors from the UNMODIFIED reference modules (dev container only).
+
+    python tests/golden/make_golden_r2.py
+
+Same mechanism as make_golden.py (reference `models.caspr.CaSPR` imported over the oracle shims, seeded synthetic
+'vigorous' weights), for the call shapes the single-sequence fixtures of round 1 do not reach:
+
+  b2_*      two DIFFERENT sequences in one batch (B=2, T=10, N=1024, P=512): per-sequence head GroupNorm / max-pool,
+            the `torch.unique` / `batch_inds` scatter of caspr.py:166-177 and the batch-global step controllers
+  eval_*    the evaluation call of utils/evaluations.py:105-114: observed steps [0,5,9] of a 10-step sequence as input,
+            all 10 NOCS time stamps as query times, constant_in_time=False
+  demo_*    two REAL demo sequences (/root/reference/data/demo, decoded by the reference's own `load_seq_path`,
+            first 5 frames, first 1024 of the 4096 padded points): the inputs are stored because the GPU box has no
+            /root/reference
+  cont_*    decode(sample_contours=[0.5, 1.0]) through the interpolated-reconstruction call of utils/viz_utils.py:142-148
+            (numpy RNG stream of utils/transform_utils.py:80-85)
+  trunc_*   reconstruct(truncate_std=1.5): models/utils.py:15-22 on the CPU generator (the reference on a GPU draws the
+            candidates with the CUDA generator, so only `truncated_normal` itself is pinned, on CPU)
+
+The Hutchinson noise the reference drew (`torch.randn_like` inside ODEfunc, right after the base samples) is recovered by
+replaying the CPU generator and stored next to the outputs.
+"""
+import glob
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+REF = '/root/reference'
+
+from oracle.reference_loader import build_reference_caspr          # noqa: E402
+from caspr_b200.synth import synthetic_state_dict, synthetic_sequences   # noqa: E402
+
+
+def demo_sequences(n_seq=2, T=5, N=1024):
+    sys.modules.setdefault('torchvision', types.ModuleType('torchvision'))
+    sys.modules['torchvision'].transforms = types.ModuleType('transforms')
+    sys.modules['torchvision'].utils = types.ModuleType('utils')
+    from data import caspr_dataset as cd                # reference module (its caspr/ dir is on sys.path by now)
+    xs, ns = [], []
+    for d in sorted(glob.glob(os.path.join(REF, 'data/demo/*/seq_00000000')))[:n_seq]:
+        frames = sorted(glob.glob(os.path.join(d, 'frame_*.npz')))
+        nocs_seq, depth_seq, _ = cd.load_seq_path(frames, max_timestamp=5.0, expected_num_pts=4096)
+        xs.append(depth_seq[:T, :N].astype(np.float32))        # __getitem__: first steps, first points, float32
+        ns.append(nocs_seq[:T, :N].astype(np.float32))
+    return torch.from_numpy(np.stack(xs)), torch.from_numpy(np.stack(ns))
+
+
+def main():
+    torch.set_num_threads(8)
+    sd = synthetic_state_dict(0, cnf_init='vigorous')
+    model = build_reference_caspr()
+    model.load_state_dict(sd)
+    model.eval()
+    out = {}
+    with torch.no_grad():
+        # ---- b2: two sequences, full 10 frames
+        x, _ = synthetic_sequences(2, 10, 1024, seed=31)
+        torch.manual_seed(15)
+        y, logp, xr, tn = model.reconstruct(x, num_points=512)
+        z0, _ = model.encode(x)
+        out['b2_x_rec'] = xr.numpy()
+        out['b2_logp_y'] = logp.numpy()
+        out['b2_z0'] = z0.numpy()
+        out['b2_tnocs_frame'] = tn[:, ::3, ::8].numpy()          # a strided sample of the (2,10,1024,4) regression
+        out['b2_nfe'] = np.asarray(model.get_nfe())
+        torch.manual_seed(15)
+        assert torch.equal(torch.randn(20, 512, 3), y.view(20, 512, 3))
+        # ---- eval protocol call shape
+        x, nocs = synthetic_sequences(2, 10, 1024, seed=32)
+        torch.manual_seed(16)
+        y, _, xr, _ = model.reconstruct(x[:, [0, 5, 9]], num_points=256, timestamps=nocs[0, :, 0, 3],
+                                        constant_in_time=False)
+        out['eval_x_rec'] = xr.numpy()
+        out['eval_nfe'] = np.asarray(model.get_nfe())
+        # ---- real demo sequences
+        x, nocs = demo_sequences()
+        torch.manual_seed(17)
+        y, _, xr, tn = model.reconstruct(x, num_points=256)
+        z0, _ = model.encode(x)
+        out['demo_x'] = x.numpy()
+        out['demo_nocs'] = nocs.numpy()
+        out['demo_x_rec'] = xr.numpy()
+        out['demo_z0'] = z0.numpy()
+        out['demo_tnocs'] = tn[:, :, ::4].numpy()
+        out['demo_nfe'] = np.asarray(model.get_nfe())
+        # ---- Gaussian contours through the interpolated call (viz_utils.py:142-148)
+        x, _ = synthetic_sequences(1, 3, 1024, seed=1)
+        np.random.seed(3)
+        torch.manual_seed(8)
+        y, logp, xr, _ = model.reconstruct(x, num_points=128, timestamps=torch.linspace(0, 1, 4),
+                                           constant_in_time=True, sample_contours=[0.5, 1.0])
+        out['cont_y'] = y.numpy()
+        out['cont_logp_y'] = logp.numpy()
+        out['cont_x_rec'] = xr.numpy()
+        out['cont_nfe'] = np.asarray(model.get_nfe())
+        torch.manual_seed(8)
+        out['cont_e'] = torch.randn(4, 128, 3).numpy()
+        # ---- truncated base samples
+        torch.manual_seed(9)
+        y, logp, xr, _ = model.reconstruct(x, num_points=128, truncate_std=1.5)
+        out['trunc_y'] = y.numpy()
+        out['trunc_x_rec'] = xr.numpy()
+        out['trunc_nfe'] = np.asarray(model.get_nfe())
+        torch.manual_seed(9)
+        _ = torch.randn(3, 128, 3)
+        _ = torch.empty(3, 128, 3, 4).normal_()
+        out['trunc_e'] = torch.randn(3, 128, 3).numpy()
+    path = os.path.join(HERE, 'caspr_r2.npz')
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path) // 1024, 'KiB', {k: v.shape for k, v in out.items()})
+
+
+if __name__ == '__main__':
+    main()

@@ -23,6 +23,9 @@ def test_header_symbols_exported(lib_built):
     out = subprocess.run(['nm', '-D', '--defined-only', lib_built], capture_output=True, text=True).stdout
     exported = sorted(set(re.findall(r' T (caspr_[a-z0-9_]+)', out)))
     assert exported == names, 'exports not declared in the header: %s' % (set(exported) ^ set(names))
+    # nothing else leaves the library: no C++-mangled internals, no data symbols (csrc/exports.map)
+    others = [l for l in out.splitlines() if l.strip() and not re.search(r' T caspr_[a-z0-9_]+$', l)]
+    assert others == [], others
 
 
 def test_ctypes_signatures_cover_header(lib_built):

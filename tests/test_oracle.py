@@ -124,3 +124,64 @@ def test_emd_oracle_properties():
     exact = d[r, cidx].sum()
     approx = approx_emd(p, q)[0]
     assert exact <= approx * 1.001 and approx < 1.35 * exact
+
+
+# ------------------------------------------------------------------ round-2 fixtures (tests/golden/make_golden_r2.py)
+@pytest.fixture(scope='module')
+def r2(golden_dir):
+    torch.set_num_threads(8)
+    return dict(np.load(os.path.join(golden_dir, 'caspr_r2.npz'))), CasprOracle(synthetic_state_dict(0, 'vigorous'))
+
+
+def _seeded_y_e(seed, shape):
+    torch.manual_seed(seed)
+    return torch.randn(*shape), torch.randn(*shape)
+
+
+def test_two_sequences_match_reference_fixture(r2):
+    """B=2 with two different sequences: per-sequence head statistics, the unique / batch_inds scatter of
+    caspr.py:166-177 and the batch-global controllers, against the unmodified reference modules."""
+    gold, oracle = r2
+    x, _ = synthetic_sequences(2, 10, 1024, seed=31)
+    y, e = _seeded_y_e(15, (20, 512, 3))
+    _, logp, xr, tn = oracle.reconstruct(x, num_points=512, y=y, e=e)
+    assert list(oracle.get_nfe()) == list(gold['b2_nfe'])
+    assert _rel(xr, gold['b2_x_rec']) < 1e-5
+    assert _rel(logp, gold['b2_logp_y']) < 1e-6
+    assert _rel(tn[:, ::3, ::8], gold['b2_tnocs_frame']) < 1e-5
+
+
+def test_evaluation_call_and_demo_sequences_match_reference_fixture(r2):
+    """utils/evaluations.py:105-114 (3 observed steps in, 10 query times) and two real demo sequences."""
+    gold, oracle = r2
+    x, nocs = synthetic_sequences(2, 10, 1024, seed=32)
+    y, e = _seeded_y_e(16, (20, 256, 3))
+    _, _, xr, _ = oracle.reconstruct(x[:, [0, 5, 9]], num_points=256, timestamps=nocs[0, :, 0, 3], y=y, e=e)
+    assert list(oracle.get_nfe()) == list(gold['eval_nfe'])
+    assert _rel(xr, gold['eval_x_rec']) < 1e-5
+    y, e = _seeded_y_e(17, (10, 256, 3))
+    _, _, xr, tn = oracle.reconstruct(torch.from_numpy(gold['demo_x']), num_points=256, y=y, e=e)
+    assert list(oracle.get_nfe()) == list(gold['demo_nfe'])
+    assert _rel(xr, gold['demo_x_rec']) < 1e-5
+    assert _rel(tn[:, :, ::4], gold['demo_tnocs']) < 1e-5
+
+
+def test_contour_and_truncated_samples_match_reference_fixture(r2):
+    """The base-sample variants of decode (caspr.py:236-252): the fixture's contour / truncated points decode to the
+    fixture's clouds, and the host-side samplers of the product reproduce the reference's RNG streams."""
+    from caspr_b200.models.utils import sample_gaussian, sphere_surface_points
+    gold, oracle = r2
+    x, _ = synthetic_sequences(1, 3, 1024, seed=1)
+    _, _, xr, _ = oracle.reconstruct(x, num_points=128, timestamps=torch.linspace(0, 1, 4), constant_in_time=True,
+                                     y=torch.from_numpy(gold['cont_y'])[:, 0], e=torch.from_numpy(gold['cont_e']))
+    assert list(oracle.get_nfe()) == list(gold['cont_nfe'])
+    assert _rel(xr, gold['cont_x_rec']) < 1e-5
+    _, _, xr, _ = oracle.reconstruct(x, num_points=128, y=torch.from_numpy(gold['trunc_y']).view(3, 128, 3),
+                                     e=torch.from_numpy(gold['trunc_e']))
+    assert list(oracle.get_nfe()) == list(gold['trunc_nfe'])
+    assert _rel(xr, gold['trunc_x_rec']) < 1e-5
+    torch.manual_seed(9)
+    assert np.array_equal(sample_gaussian((3, 128, 3), 1.5).numpy(), gold['trunc_y'].reshape(3, 128, 3))
+    np.random.seed(3)
+    c = np.concatenate([sphere_surface_points(64, r).reshape(1, 64, 3) for r in (0.5, 1.0)], axis=1)
+    assert np.array_equal(c[0].astype(np.float32), gold['cont_y'][0, 0])

@@ -9,7 +9,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from caspr_b200.sharding import (shard_range, gather_batch, reconstruct_sharded, max_over_ranks,
-                                 allreduce_gradients, train_step_sharded, gather_rows, lockstep)
+                                 allreduce_gradients, train_step_sharded, gather_rows, lockstep, FlatGradients,
+                                 broadcast_moving_batchnorm, moving_batchnorm_buffers)
 
 
 def test_shard_range_partitions():
@@ -193,6 +194,92 @@ def test_gather_rows_and_lockstep_switch_world_size_2_gloo():
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_rows_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]
+
+
+class _TinyFlowModel(torch.nn.Module):
+    """A trainable map followed by the product's MovingBatchNorm1d (pure torch in training mode): its running statistics
+    are updated from the local shard and are the ones USED by the next forward (normalization.py:60-64)."""
+
+    def __init__(self):
+        super().__init__()
+        from caspr_b200.models.cnf import MovingBatchNorm1d
+        torch.manual_seed(0)
+        self.lin = torch.nn.Linear(4, 3)
+        self.mbn = MovingBatchNorm1d(3)
+
+    def forward(self, x, sample_points, e=None):
+        B, T, N, _ = x.shape
+        y = self.mbn(self.lin(x).view(B * T, N, 3)).view(B, T, N, 3)
+        return (y ** 2).sum(-1), (y - sample_points[..., :3]).abs()
+
+
+def _mbn_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(2)
+        B, T, N = 4, 2, 6
+        model = _TinyFlowModel().train()
+        flat = FlatGradients(model.parameters())
+        opt = torch.optim.SGD(model.parameters(), lr=0.05)
+        ok = len(moving_batchnorm_buffers(model)) == 3
+        for step in range(3):
+            x = torch.randn(B, T, N, 4, generator=g) + 0.5 * step
+            nocs = torch.randn(B, T, N, 4, generator=g)
+            train_step_sharded(model, opt, x, nocs, _loss, flat_grads=flat)
+            # gradients are still views of the one flat buffer after backward + optimizer step
+            ok = ok and all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(flat.params, flat.views))
+            state = torch.cat([b.reshape(-1) for b in moving_batchnorm_buffers(model)] +
+                              [p.detach().reshape(-1) for p in model.parameters()])
+            both = [torch.empty_like(state) for _ in range(world)]
+            dist.all_gather(both, state)
+            ok = ok and torch.equal(both[0], both[1])          # buffers AND parameters identical on every rank
+            ok = ok and float(model.mbn.step) == step + 1
+        # DataParallel semantics: the statistics are those of rank 0's shard (sequences [0, 2))
+        ref = _TinyFlowModel().train()
+        g = torch.Generator().manual_seed(2)
+        x = torch.randn(B, T, N, 4, generator=g)
+        ref(x[:2], None if False else torch.zeros(2, T, N, 4))
+        first = _TinyFlowModel().train()
+        g = torch.Generator().manual_seed(2)
+        x = torch.randn(B, T, N, 4, generator=g)
+        nocs = torch.randn(B, T, N, 4, generator=g)
+        train_step_sharded(first, torch.optim.SGD(first.parameters(), lr=0.0), x, nocs, _loss)
+        ok = ok and torch.allclose(first.mbn.running_mean, ref.mbn.running_mean, atol=1e-7)
+        ok = ok and torch.allclose(first.mbn.running_var, ref.mbn.running_var, atol=1e-7)
+        # without the broadcast the ranks would have drifted apart
+        drift = _TinyFlowModel().train()
+        lo = 2 * rank
+        drift(x[lo:lo + 2], torch.zeros(2, T, N, 4))
+        state = drift.mbn.running_mean.clone()
+        both = [torch.empty_like(state) for _ in range(world)]
+        dist.all_gather(both, state)
+        ok = ok and not torch.equal(both[0], both[1])
+        n = broadcast_moving_batchnorm(drift)
+        ok = ok and n == 7
+        state = drift.mbn.running_mean.clone()
+        dist.all_gather(both, state)
+        ok = ok and torch.equal(both[0], both[1])
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_moving_batchnorm_buffers_stay_identical_across_ranks_gloo():
+    """Three sharded steps: after every step all ranks hold identical MovingBatchNorm statistics (rank 0's, as
+    nn.DataParallel's replica 0 does in the reference) and identical parameters; gradients live in one flat buffer."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_mbn_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
