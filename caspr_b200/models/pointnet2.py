@@ -116,6 +116,8 @@ class PointNet2SetAbstraction(nn.Module):
                 rows = ops.group_points(xyz, new_xyz, features, bq[s])
                 pointnet.forward_rows(rows, Bp * M, grouper.num_samples, out[:, off:off + pointnet.feat_size])
             off += pointnet.feat_size
+        if trace is not None:
+            trace.setdefault('sa_out', []).append(out.view(Bp, M, -1))
         return new_xyz, out.view(Bp, M, -1)
 
 
