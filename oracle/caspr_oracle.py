@@ -26,8 +26,12 @@ SA_SAMPLES = [16, 32]
 
 class CasprOracle(object):
     def __init__(self, state_dict, radii_list=(0.02, 0.05, 0.1, 0.2, 0.4, 0.8),
-                 motion_feat_size=64, regress_tnocs=True, augment_quad=True, augment_pairs=True):
-        self.sd = {k: v.detach().to(torch.float32).cpu() if v.is_floating_point() else v.cpu()
+                 motion_feat_size=64, regress_tnocs=True, augment_quad=True, augment_pairs=True,
+                 dtype=torch.float32):
+        # dtype=torch.float64 evaluates the same network in double precision (geometry indices are still taken in the
+        # declared fp32 arithmetic): the yardstick for how well-conditioned an fp32 result is on a given input
+        self.dtype = dtype
+        self.sd = {k: v.detach().to(dtype).cpu() if v.is_floating_point() else v.cpu()
                    for k, v in state_dict.items()}
         self.radii = list(radii_list)
         self.motion = motion_feat_size
@@ -129,7 +133,7 @@ class CasprOracle(object):
 
     def encode(self, x):
         """tpointnet2.py:70-115 (via caspr.py:148-155).  x (B,T,N,4) -> z0 (B,1600), tnocs."""
-        x = x.to(torch.float32)
+        x = x.to(self.dtype)
         B, T, N, _ = x.shape
         g_in = x.view(B, T * N, 4).transpose(2, 1).contiguous()                     # :75
         g = self.pointnet_global(g_in)                                              # :76

@@ -11,7 +11,7 @@ Same mechanism as make_golden.py (reference `models.caspr.CaSPR` imported over t
             all 10 NOCS time stamps as query times, constant_in_time=False
   demo_*    two REAL demo sequences (/root/reference/data/demo, decoded by the reference's own `load_seq_path`,
             first 5 frames, first 1024 of the 4096 padded points): the inputs are stored because the GPU box has no
-            /root/reference
+            /root/reference; `*_f64` = the oracle restatement evaluated in float64 on the same inputs
   cont_*    decode(sample_contours=[0.5, 1.0]) through the interpolated-reconstruction call of utils/viz_utils.py:142-148
             (numpy RNG stream of utils/transform_utils.py:80-85)
   trunc_*   reconstruct(truncate_std=1.5): models/utils.py:15-22 on the CPU generator (the reference on a GPU draws the
@@ -83,11 +83,21 @@ def main():
         y, _, xr, tn = model.reconstruct(x, num_points=256)
         z0, _ = model.encode(x)
         out['demo_x'] = x.numpy()
-        out['demo_nocs'] = nocs.numpy()
         out['demo_x_rec'] = xr.numpy()
         out['demo_z0'] = z0.numpy()
         out['demo_tnocs'] = tn[:, :, ::4].numpy()
         out['demo_nfe'] = np.asarray(model.get_nfe())
+        # The same network in float64 (oracle restatement, identical geometry indices): real depth data is quantised,
+        # per-ball GroupNorm statistics cancel catastrophically on it, and the reference's own fp32 result is only
+        # reproducible to ~1e-3 (z0) / 2e-4 (reconstruction) -- the yardstick the GPU test uses for this input
+        from oracle.caspr_oracle import CasprOracle
+        o64 = CasprOracle(sd, dtype=torch.float64)
+        torch.manual_seed(17)
+        y64, e64 = torch.randn(10, 256, 3).double(), torch.randn(10, 256, 3).double()
+        _, _, xr64, tn64 = o64.reconstruct(x, num_points=256, y=y64, e=e64)
+        out['demo_z0_f64'] = o64.encode(x)[0].numpy().astype(np.float32)      # float64 results, stored rounded
+        out['demo_x_rec_f64'] = xr64.numpy().astype(np.float32)
+        out['demo_tnocs_f64'] = tn64[:, :, ::4].numpy().astype(np.float32)
         # ---- Gaussian contours through the interpolated call (viz_utils.py:142-148)
         x, _ = synthetic_sequences(1, 3, 1024, seed=1)
         np.random.seed(3)

@@ -22,6 +22,18 @@ for eng in ('auto', 'simt'):
     z0, tn = m.encode(x.cuda())
     tr = m.encoder.trace
     print('engine', eng, 'z0 rel err', float((z0.cpu() - z_ref).abs().max() / z_ref.abs().max()))
+    z64 = torch.from_numpy(g['demo_z0_f64'])
+    print('   vs f64: gpu %.3g   ref32 %.3g' % (float((z0.cpu() - z64).abs().max() / z64.abs().max()),
+                                               float((z_ref - z64).abs().max() / z64.abs().max())))
+    if eng == 'auto':
+        torch.manual_seed(17); y = torch.randn(10, 256, 3); e = torch.randn(10, 256, 3)
+        _, _, xr, tn2 = m.reconstruct(x.cuda(), num_points=256, y=y, e=e.cuda())
+        x64 = torch.from_numpy(g['demo_x_rec_f64']); x32 = torch.from_numpy(g['demo_x_rec'])
+        print('   x_rec vs f64: gpu %.3g  ref32 %.3g   gpu vs ref32 %.3g  nfe %s' % (
+            float((xr.cpu() - x64).abs().max() / x64.abs().max()), float((x32 - x64).abs().max() / x64.abs().max()),
+            float((xr.cpu() - x32).abs().max() / x32.abs().max()), m.get_nfe()))
+        t64 = torch.from_numpy(g['demo_tnocs_f64']); t32 = torch.from_numpy(g['demo_tnocs'])
+        print('   tnocs vs f64: gpu %.3g  ref32 %.3g' % (float((tn2[:, :, ::4].cpu() - t64).abs().max()), float((t32 - t64).abs().max())))
     for l in range(5):
         fe = torch.equal(tr['fps_idx'][l].cpu(), o.trace['fps_idx_%d' % l])
         be = [torch.equal(tr['ball_idx'][l][s].cpu(), o.trace['ball_idx_%d_%d' % (l, s)]) for s in range(2)]
