@@ -384,8 +384,6 @@ cnf_tc_last_finish_kernel(float* __restrict__ acc6, const float* __restrict__ e,
   kout[pt] = reverse ? make_float4(-dy0, -dy1, -dy2, div) : make_float4(dy0, dy1, dy2, -div);
 }
 
-bool g_attr_set = false;
-
 }  // namespace
 
 size_t weights_workspace_bytes() {
@@ -423,19 +421,11 @@ int make_plan(Plan& plan, const Weights& w, __half* a_hi, __half* a_lo, __half* 
   ok &= caspr_make_tmap_f16(&plan.tm_act[1][0], b_hi, rows, 512, kBM);
   ok &= caspr_make_tmap_f16(&plan.tm_act[1][1], b_lo, rows, 512, kBM);
   for (int l = 0; l < 2; ++l) {
-    ok &= caspr_make_tmap_f16(&plan.tm_w[l][0], w.hi[l], 512, 512, kBN);
-    ok &= caspr_make_tmap_f16(&plan.tm_w[l][1], w.lo[l], 512, 512, kBN);
+    ok &= caspr_make_tmap_f16(&plan.tm_w[l][0], w.hi[l], 512, 512, tcg::w_box_rows());
+    ok &= caspr_make_tmap_f16(&plan.tm_w[l][1], w.lo[l], 512, 512, tcg::w_box_rows());
   }
   plan.a_hi = a_hi; plan.a_lo = a_lo; plan.b_hi = b_hi; plan.b_lo = b_lo;
   if (!ok) return CASPR_ELAUNCH;
-  if (!g_attr_set) {
-    if (cudaFuncSetAttribute(tcg::gemm_fp16x3_kernel<CnfEpilogue<false>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             tcg::kSmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(tcg::gemm_fp16x3_kernel<CnfEpilogue<true>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             tcg::kSmemBytes) != cudaSuccess)
-      return CASPR_ELAUNCH;
-    g_attr_set = true;
-  }
   return CASPR_OK;
 }
 
@@ -453,26 +443,24 @@ int enqueue_layer0(const Plan& plan, const float4* y0, const float4* kbuf, size_
 int enqueue_mid(const Plan& plan, int layer, int m_tile0, int m_tiles, const float* gate, const float* biasf,
                 int ld_hyper, int n, int P, const CnfState* st, const float* W3, float* acc6, int* range_flag,
                 int num_sms, cudaStream_t s) {
-  int grid = m_tiles * 2;
-  if (grid > num_sms) grid = num_sms;
   const int* skip = &st->done;
   caspr_prof_begin(CASPR_PROF_CNF_FUSED_TC, s);
   CASPR_COUNT();
+  cudaError_t err;
   if (layer == 0) {
     CnfEpilogue<false> epi{};
     epi.gate = gate; epi.biasf = biasf; epi.ld_hyper = ld_hyper; epi.n = n; epi.P = P;
     epi.out_hi = plan.b_hi; epi.out_lo = plan.b_lo; epi.range_flag = range_flag;
-    tcg::gemm_fp16x3_kernel<CnfEpilogue<false>><<<grid, tcg::kThreads, tcg::kSmemBytes, s>>>(
-        plan.tm_act[0][0], plan.tm_act[0][1], plan.tm_w[0][0], plan.tm_w[0][1], plan.tm_act[1][0], plan.tm_act[1][1],
-        m_tile0, m_tiles, 2, 512 / tcg::kBK, skip, epi);
+    err = tcg::launch_gemm(plan.tm_act[0][0], plan.tm_act[0][1], plan.tm_w[0][0], plan.tm_w[0][1], plan.tm_act[1][0],
+                           plan.tm_act[1][1], m_tile0, m_tiles, 2, 512 / tcg::kBK, skip, epi, 1, num_sms, s);
   } else {
     CnfEpilogue<true> epi{};
     epi.gate = gate; epi.biasf = biasf; epi.ld_hyper = ld_hyper; epi.n = n; epi.P = P;
     epi.W3 = W3; epi.acc6 = acc6; epi.range_flag = range_flag; epi.pending = false;
-    tcg::gemm_fp16x3_kernel<CnfEpilogue<true>><<<grid, tcg::kThreads, tcg::kSmemBytes, s>>>(
-        plan.tm_act[1][0], plan.tm_act[1][1], plan.tm_w[1][0], plan.tm_w[1][1], plan.tm_act[1][0], plan.tm_act[1][1],
-        m_tile0, m_tiles, 2, 512 / tcg::kBK, skip, epi);
+    err = tcg::launch_gemm(plan.tm_act[1][0], plan.tm_act[1][1], plan.tm_w[1][0], plan.tm_w[1][1], plan.tm_act[1][0],
+                           plan.tm_act[1][1], m_tile0, m_tiles, 2, 512 / tcg::kBK, skip, epi, 1, num_sms, s);
   }
+  if (err != cudaSuccess) return CASPR_ELAUNCH;
   caspr_prof_end(CASPR_PROF_CNF_FUSED_TC, s);
   CASPR_CHECK_LAUNCH();
   return CASPR_OK;

@@ -344,8 +344,6 @@ Layout make_layout(long long rows, int cin, int cout) {
   return l;
 }
 
-bool g_linear_attr_set = false;
-bool g_wgrad_attr_set = false;
 
 // ------------------------------------------------------------------ weight gradient (split-K, transposed operands)
 // dW[o][i] = sum_r dY[r][o] X[r][i]: both operands are needed with the ROW index as the contraction (K) dimension, i.e.
@@ -556,15 +554,9 @@ extern "C" int caspr_linear_wgrad_tc(const float* dY, int lddy, const float* X, 
   bool ok = true;
   ok &= caspr_make_tmap_f16(&tm_ahi, ahi, (uint64_t)l.cout_pad, (uint64_t)l.r_pad, kBM);
   ok &= caspr_make_tmap_f16(&tm_alo, alo, (uint64_t)l.cout_pad, (uint64_t)l.r_pad, kBM);
-  ok &= caspr_make_tmap_f16(&tm_whi, whi, (uint64_t)l.cin_pad, (uint64_t)l.r_pad, kBN);
-  ok &= caspr_make_tmap_f16(&tm_wlo, wlo, (uint64_t)l.cin_pad, (uint64_t)l.r_pad, kBN);
+  ok &= caspr_make_tmap_f16(&tm_whi, whi, (uint64_t)l.cin_pad, (uint64_t)l.r_pad, tcg::w_box_rows());
+  ok &= caspr_make_tmap_f16(&tm_wlo, wlo, (uint64_t)l.cin_pad, (uint64_t)l.r_pad, tcg::w_box_rows());
   if (!ok) return CASPR_ELAUNCH;
-  if (!g_wgrad_attr_set) {
-    if (cudaFuncSetAttribute(tcg::gemm_fp16x3_kernel<WgradEpilogue>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             tcg::kSmemBytes) != cudaSuccess)
-      return CASPR_ELAUNCH;
-    g_wgrad_attr_set = true;
-  }
   int dev = 0, num_sms = 148;
   if (cudaGetDevice(&dev) != cudaSuccess ||
       cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
@@ -572,10 +564,10 @@ extern "C" int caspr_linear_wgrad_tc(const float* dY, int lddy, const float* X, 
   const int m_tiles = l.cout_pad / kBM, n_tiles = l.cin_pad / kBN;
   WgradEpilogue epi{};
   epi.a_max = dy_colmax; epi.w_max = x_colmax; epi.part = part; epi.cout = Cout; epi.cin = Cin; epi.m_tiles = m_tiles;
-  long long grid = (long long)m_tiles * n_tiles * l.k_splits;
-  if (grid > num_sms) grid = num_sms;
-  CASPR_COUNT(); tcg::gemm_fp16x3_kernel<WgradEpilogue><<<(int)grid, tcg::kThreads, tcg::kSmemBytes, s>>>(
-      tm_ahi, tm_alo, tm_whi, tm_wlo, tm_ahi, tm_alo, 0, m_tiles, n_tiles, l.k_chunks, nullptr, epi, l.k_splits);
+  CASPR_COUNT();
+  if (tcg::launch_gemm(tm_ahi, tm_alo, tm_whi, tm_wlo, tm_ahi, tm_alo, 0, m_tiles, n_tiles, l.k_chunks, nullptr, epi,
+                       l.k_splits, num_sms, s) != cudaSuccess)
+    return CASPR_ELAUNCH;
   const size_t nelem = (size_t)Cout * Cin;
   CASPR_COUNT(); wgrad_sum_parts_kernel<<<(unsigned)((nelem + 255) / 256), 256, 0, s>>>(part, l.k_splits, nelem, dW);
   CASPR_CHECK_LAUNCH();
@@ -669,15 +661,9 @@ extern "C" int caspr_linear_tc(const float* X, int ldx, const float* W, int ldw,
   bool ok = true;
   ok &= caspr_make_tmap_f16(&tm_xhi, xhi, (uint64_t)l.rows_pad, (uint64_t)l.k_pad, kBM);
   ok &= caspr_make_tmap_f16(&tm_xlo, xlo, (uint64_t)l.rows_pad, (uint64_t)l.k_pad, kBM);
-  ok &= caspr_make_tmap_f16(&tm_whi, whi, (uint64_t)l.cout_pad, (uint64_t)l.k_pad, kBN);
-  ok &= caspr_make_tmap_f16(&tm_wlo, wlo, (uint64_t)l.cout_pad, (uint64_t)l.k_pad, kBN);
+  ok &= caspr_make_tmap_f16(&tm_whi, whi, (uint64_t)l.cout_pad, (uint64_t)l.k_pad, tcg::w_box_rows());
+  ok &= caspr_make_tmap_f16(&tm_wlo, wlo, (uint64_t)l.cout_pad, (uint64_t)l.k_pad, tcg::w_box_rows());
   if (!ok) return CASPR_ELAUNCH;
-  if (!g_linear_attr_set) {
-    if (cudaFuncSetAttribute(tcg::gemm_fp16x3_kernel<LinearEpilogue>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             tcg::kSmemBytes) != cudaSuccess)
-      return CASPR_ELAUNCH;
-    g_linear_attr_set = true;
-  }
   int dev = 0, num_sms = 148;
   if (cudaGetDevice(&dev) != cudaSuccess ||
       cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
@@ -691,12 +677,12 @@ extern "C" int caspr_linear_tc(const float* X, int ldx, const float* W, int ldw,
   }
   epi.vec_ok = (ldy % 4 == 0) && (((uintptr_t)Y & 15) == 0) && (!bias || ((uintptr_t)bias & 15) == 0);
   const int m_tiles = (int)(l.rows_pad / kBM), n_tiles = l.cout_pad / kBN;
-  int grid = m_tiles * n_tiles;
-  if (grid > num_sms) grid = num_sms;
   caspr_prof_begin(CASPR_PROF_LINEAR, s);
-  CASPR_COUNT(); tcg::gemm_fp16x3_kernel<LinearEpilogue><<<grid, tcg::kThreads, tcg::kSmemBytes, s>>>(
-      tm_xhi, tm_xlo, tm_whi, tm_wlo, tm_xhi, tm_xlo, 0, m_tiles, n_tiles, l.k_pad / kBK, nullptr, epi);
+  CASPR_COUNT();
+  const cudaError_t lerr = tcg::launch_gemm(tm_xhi, tm_xlo, tm_whi, tm_wlo, tm_xhi, tm_xlo, 0, m_tiles, n_tiles,
+                                            l.k_pad / kBK, nullptr, epi, 1, num_sms, s);
   caspr_prof_end(CASPR_PROF_LINEAR, s);
+  if (lerr != cudaSuccess) return CASPR_ELAUNCH;
   CASPR_CHECK_LAUNCH();
   return CASPR_OK;
 }

@@ -24,6 +24,7 @@
 //   void chunk(int chunk_idx, uint32_t (&acc)[32]);   // fp32 bits of columns chunk*32 .. +31 of this thread's row
 //   void finish();                                     // once, after the last tile
 #pragma once
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace tcg {
@@ -167,6 +168,209 @@ gemm_fp16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem_base, 512);
   }
+}
+
+// ------------------------------------------------------------------------------------------------- CTA-pair variant
+// Same GEMM with `tcgen05.mma.cta_group::2` (M = 256 over the two SMs of a TPC): a cluster of two CTAs works on the row
+// tiles (2p, 2p+1) of one column tile.  Every CTA loads its own A tile and only HALF of the W tile (128 of the 256
+// output channels), so the bytes an SM pulls from L2 per k-chunk drop from 96 KB to 64 KB — the single-CTA kernel
+// runs at the L2 -> SM delivery limit (148 x 96 KB per 0.83 us), not at the tensor-core limit — and the smaller stage
+// leaves room for a 3-deep ring.  Roles per CTA as above; only the leader's warp 1 issues MMAs; smem stages and
+// accumulators are released / published to both CTAs with multicast commits; the leader's `full` barrier collects
+// the TMA bytes of both CTAs; both CTAs' epilogue threads arrive on the leader's `tempty`.
+constexpr int kPairStages = 3;
+constexpr int kPairWTile = (kBN / 2) * kBK * 2;                      // 16 KB: this CTA's half of the W tile
+constexpr int kPairStageBytes = 2 * kATile + 2 * kPairWTile;        // 64 KB
+constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + kStagingBytes + 1024 + 256;
+
+template <class Epilogue>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_fp16x3_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                        const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                        const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
+                        int m_tile0, int m_tiles, int n_tiles, int k_chunks, const int* __restrict__ skip_flag,
+                        Epilogue epi, int k_splits = 1) {
+  if (skip_flag && *skip_flag) return;       // uniform over the grid: both CTAs of a pair leave together
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* staging = smem + kPairStages * kPairStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
+  uint64_t* full = bars;                     // [kPairStages]  (leader's copy is the live one)
+  uint64_t* empty = bars + kPairStages;      // [kPairStages]
+  uint64_t* tfull = bars + 2 * kPairStages;  // [2]
+  uint64_t* tempty = tfull + 2;              // [2]           (leader's copy is the live one)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = tc::cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int m_pairs = (m_tiles + 1) >> 1;
+  const int mn_items = m_pairs * n_tiles;
+  const int total_items = mn_items * k_splits;
+
+  if (threadIdx.x == 0) {
+    tc::prefetch_tmap(&tm_a_hi);
+    tc::prefetch_tmap(&tm_a_lo);
+    tc::prefetch_tmap(&tm_w_hi);
+    tc::prefetch_tmap(&tm_w_lo);
+    for (int s = 0; s < kPairStages; ++s) {
+      tc::mbar_init(&full[s], 2);            // leader's arrive.expect_tx + the peer producer's remote arrive
+      tc::mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(&tfull[b], 1);
+      tc::mbar_init(&tempty[b], 256);        // the epilogue threads of both CTAs
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc_pair(tmem_slot, 512);
+  tc::fence_before_sync();
+  tc::cluster_sync_all();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = cluster_id; item < total_items; item += n_clusters) {
+        const int split = item / mn_items, mn = item - split * mn_items;
+        const int m_pair = mn / n_tiles, n_tile = mn - m_pair * n_tiles;
+        int m_local = 2 * m_pair + (int)rank;
+        if (m_local >= m_tiles) m_local = m_tiles - 1;            // odd tail: load a valid tile, result is discarded
+        const int m_tile = m_tile0 + m_local;
+        const int kc0 = split * k_chunks;
+        for (int kc = 0; kc < k_chunks; ++kc) {
+          tc::mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sb = smem + stage * kPairStageBytes;
+          const uint32_t lead_full = tc::mapa_shared(&full[stage], 0);
+          if (rank == 0) tc::mbar_arrive_expect_tx(&full[stage], 2 * kPairStageBytes);
+          else tc::mbar_arrive_cluster(lead_full);
+          tc::tma_load_2d_pair(sb, &tm_a_hi, lead_full, (kc0 + kc) * kBK, m_tile * kBM);
+          tc::tma_load_2d_pair(sb + kATile, &tm_a_lo, lead_full, (kc0 + kc) * kBK, m_tile * kBM);
+          tc::tma_load_2d_pair(sb + 2 * kATile, &tm_w_hi, lead_full, (kc0 + kc) * kBK,
+                               n_tile * kBN + (int)rank * (kBN / 2));
+          tc::tma_load_2d_pair(sb + 2 * kATile + kPairWTile, &tm_w_lo, lead_full, (kc0 + kc) * kBK,
+                               n_tile * kBN + (int)rank * (kBN / 2));
+          if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_f16(2 * kBM, kBN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int item = cluster_id; item < total_items; item += n_clusters, ++it) {
+        const int buf = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        tc::mbar_wait(&tempty[buf], acc_phase ^ 1);
+        tc::fence_after_sync();
+        const uint32_t d_tmem = tmem_base + buf * kBN;
+        for (int kc = 0; kc < k_chunks; ++kc) {
+          tc::mbar_wait(&full[stage], phase);
+          tc::fence_after_sync();
+          const uint32_t sb = tc::smem_u32(smem + stage * kPairStageBytes);
+          const uint64_t a_hi = tc::make_desc_k128(sb);
+          const uint64_t a_lo = tc::make_desc_k128(sb + kATile);
+          const uint64_t w_hi = tc::make_desc_k128(sb + 2 * kATile);
+          const uint64_t w_lo = tc::make_desc_k128(sb + 2 * kATile + kPairWTile);
+#pragma unroll
+          for (int ks = 0; ks < kBK / 16; ++ks) {
+            const uint64_t adv = (uint64_t)(ks * 2);              // 32 bytes per UMMA_K
+            tc::umma_f16_ss_pair(d_tmem, a_hi + adv, w_hi + adv, idesc, (kc | ks) != 0);
+            tc::umma_f16_ss_pair(d_tmem, a_lo + adv, w_hi + adv, idesc, 1);
+            tc::umma_f16_ss_pair(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+          }
+          tc::umma_commit_pair(&empty[stage], 3);
+          if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+        }
+        tc::umma_commit_pair(&tfull[buf], 3);
+      }
+    }
+  } else {
+    const int q = warp & 3;                                       // TMEM lane quadrant of this warp
+    epi.setup(staging, &tm_o_hi, &tm_o_lo, (int)threadIdx.x - 64);
+    int it = 0;
+    for (int item = cluster_id; item < total_items; item += n_clusters, ++it) {
+      const int split = item / mn_items, mn = item - split * mn_items;
+      const int m_pair = mn / n_tiles, n_tile = mn - m_pair * n_tiles;
+      const int m_local = 2 * m_pair + (int)rank;
+      const bool valid = m_local < m_tiles;                       // warp-uniform
+      const int m_tile = m_tile0 + m_local + split * m_tiles;
+      const int buf = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      if (valid) epi.tile_begin(m_tile, n_tile, q, lane);
+      tc::mbar_wait(&tfull[buf], acc_phase);
+      tc::fence_after_sync();
+      if (valid) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * kBN;
+#pragma unroll 1
+        for (int chunk = 0; chunk < kBN / 32; ++chunk) {
+          uint32_t r[32];
+          tc::tmem_ld_32x32(taddr + chunk * 32, r);
+          tc::tmem_ld_wait();
+          epi.chunk(chunk, r);
+        }
+      }
+      tc::fence_before_sync();
+      tc::mbar_arrive_cluster(tc::mapa_shared(&tempty[buf], 0));
+    }
+    epi.finish();
+  }
+  tc::fence_before_sync();
+  tc::cluster_sync_all();                    // the leader's MMAs read the peer's smem and write its TMEM until here
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- host launcher
+// CASPR_TC_PAIR=0 selects the single-CTA kernel (kept for comparison); default is the CTA-pair kernel.
+inline bool use_pair() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("CASPR_TC_PAIR");
+    mode = (e && e[0] == '0') ? 0 : 1;
+  }
+  return mode == 1;
+}
+// rows of the W box the tensor maps of the W planes must be built with
+inline uint32_t w_box_rows() { return use_pair() ? kBN / 2 : kBN; }
+
+template <class Epilogue>
+inline cudaError_t launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
+                               const CUtensorMap& w_lo, const CUtensorMap& o_hi, const CUtensorMap& o_lo, int m_tile0,
+                               int m_tiles, int n_tiles, int k_chunks, const int* skip_flag, const Epilogue& epi,
+                               int k_splits, int num_sms, cudaStream_t s) {
+  static bool attr_set = false;           // per Epilogue instantiation
+  if (use_pair()) {
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(gemm_fp16x3_pair_kernel<Epilogue>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kPairSmemBytes);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    long long clusters = (long long)((m_tiles + 1) / 2) * n_tiles * k_splits;
+    if (clusters > num_sms / 2) clusters = num_sms / 2;
+    gemm_fp16x3_pair_kernel<Epilogue><<<(int)(2 * clusters), kThreads, kPairSmemBytes, s>>>(
+        a_hi, a_lo, w_hi, w_lo, o_hi, o_lo, m_tile0, m_tiles, n_tiles, k_chunks, skip_flag, epi, k_splits);
+  } else {
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(gemm_fp16x3_kernel<Epilogue>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kSmemBytes);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    long long grid = (long long)m_tiles * n_tiles * k_splits;
+    if (grid > num_sms) grid = num_sms;
+    gemm_fp16x3_kernel<Epilogue><<<(int)grid, kThreads, kSmemBytes, s>>>(a_hi, a_lo, w_hi, w_lo, o_hi, o_lo, m_tile0,
+                                                                        m_tiles, n_tiles, k_chunks, skip_flag, epi,
+                                                                        k_splits);
+  }
+  return cudaGetLastError();
 }
 
 // x -> fp16 hi and fp16 lo with hi + lo ~= x to ~22 bits (two values at a time)
