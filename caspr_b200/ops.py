@@ -567,3 +567,31 @@ def tnocs_error(pred, gt):
     _count('tnocs_error')
     check(lib.caspr_tnocs_error(_p(pred), _p(gt), B * T, N, _p(space), _p(terr), _stream()), 'caspr_tnocs_error')
     return space, terr
+
+
+def ransac_pose(src, dst, samples, max_distance=0.015, refine=False, want_counts=False):
+    """Correspondence-RANSAC rigid pose (evaluations.py:360-380): src, dst (F,N,3) corresponding points, samples
+    (F,H,4) int32 correspondences of the H hypotheses -> dict with R (F,3,3), t (F,3), best (F,) int32, fitness (F,),
+    inlier_rmse (F,) and, on request, counts (F,H)."""
+    src, dst = _f32(src, 'src').contiguous(), _f32(dst, 'dst').contiguous()
+    F, N, _ = src.shape
+    assert dst.shape == src.shape and samples.dim() == 3 and samples.shape[0] == F and samples.shape[2] == 4
+    samples = samples.to(device=src.device, dtype=torch.int32).contiguous()
+    H = samples.shape[1]
+    dev = src.device
+    R = torch.empty(F, 3, 3, dtype=torch.float32, device=dev)
+    t = torch.empty(F, 3, dtype=torch.float32, device=dev)
+    best = torch.empty(F, dtype=torch.int32, device=dev)
+    fit = torch.empty(F, dtype=torch.float32, device=dev)
+    rmse = torch.empty(F, dtype=torch.float32, device=dev)
+    counts = torch.empty(F, H, dtype=torch.int32, device=dev) if want_counts else None
+    nb = lib.caspr_ransac_pose_workspace_bytes(F, H)
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+    _count('ransac_pose')
+    check(lib.caspr_ransac_pose(_p(src), _p(dst), _p(samples), F, N, H, float(max_distance), int(bool(refine)), _p(R),
+                                _p(t), _p(best), _p(fit), _p(rmse), _p(counts) if want_counts else None, _p(ws), nb,
+                                _stream()), 'caspr_ransac_pose')
+    out = {'R': R, 't': t, 'best': best, 'fitness': fit, 'inlier_rmse': rmse}
+    if want_counts:
+        out['counts'] = counts
+    return out

@@ -396,6 +396,23 @@ size_t caspr_emd_workspace_bytes(int B, int n, int m);
 int caspr_emd(const float* xyz1, const float* xyz2, int B, int n, int m, float* cost, void* workspace,
               size_t workspace_bytes, void* stream);
 
+/* Correspondence-RANSAC rigid pose (reference utils/evaluations.py:360-380: open3d
+ * registration_ransac_based_on_correspondence with identity correspondences, ransac_n = 4, threshold 0.015,
+ * RANSACConvergenceCriteria(50000, 5000), TransformationEstimationPointToPoint(False)).  open3d is absent from the
+ * reference tree and unpinned: this restates its published algorithm (oracle/ransac_oracle.py).
+ * src, dst (frames,N,3): corresponding points (src = predicted NOCS - 0.5, dst = observed points); samples
+ * (frames,H,4) int32: the four correspondences of every hypothesis (open3d draws them with C rand(); here the caller
+ * supplies them).  Per frame: every hypothesis is fitted (least-squares rigid transform dst ~ R src + t) and scored
+ * (inliers = correspondences with |R src + t - dst| < max_distance); the best one (most inliers, then lowest inlier
+ * RMSE, then lowest index) is returned: R_out (frames,9) row-major, t_out (frames,3), best_out (frames) hypothesis
+ * index, fitness_out = inliers / N, rmse_out; counts_out (frames,H) inlier counts of all hypotheses or NULL.
+ * refine != 0 refits the transform on the winner's inliers (newer open3d versions). */
+size_t caspr_ransac_pose_workspace_bytes(int frames, int hypotheses);
+int caspr_ransac_pose(const float* src, const float* dst, const int32_t* samples, int frames, int N, int hypotheses,
+                      float max_distance, int refine, float* R_out, float* t_out, int32_t* best_out,
+                      float* fitness_out, float* rmse_out, int32_t* counts_out, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
