@@ -47,9 +47,11 @@ def ransac_pose_errors(R_pred, t_pred, R_gt, t_gt, gt_nocs, pcl_in):
     point_mean distance between the observed points and the ground-truth NOCS moved by the predicted pose."""
     import math
     import torch
-    g = gt_nocs[..., :3] - 0.5
+    # float64 like the reference's numpy code: arccos near 1 loses half the digits in float32
+    R_pred, t_pred, R_gt, t_gt = R_pred.double(), t_pred.double(), R_gt.double(), t_gt.double()
+    g = gt_nocs[..., :3].double() - 0.5
     moved = torch.einsum('btij,btnj->btni', R_pred, g) + t_pred.unsqueeze(2)
-    dist = (moved - pcl_in[..., :3]).norm(dim=-1)
+    dist = (moved - pcl_in[..., :3].double()).norm(dim=-1)
     tr = torch.einsum('btji,btji->bt', R_pred, R_gt)                  # trace(R_pred^T R_gt)
     cosang = ((tr - 1.0) / 2.0).clamp(-1.0, 1.0)
     return {'trans': (t_pred - t_gt).norm(dim=-1), 'rot': torch.acos(cosang) * (180.0 / math.pi),
