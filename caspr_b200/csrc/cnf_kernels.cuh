@@ -632,6 +632,8 @@ struct CnfWorkspace {
   float* acc6;                         // n x 8 partial sums of the fused output layer (tensor-core engine)
   int* range_flag;
   cnf_tc::Weights tcw;
+  void* fused_scratch;                 // per-CTA L2-resident planes of the fused evaluation kernel
+  int fused_grid;
   size_t bytes;
 };
 
@@ -666,6 +668,9 @@ CnfWorkspace carve(void* base, int frames, int pts, int H) {
   }
   w.tcw.scales = (float*)take(256);
   w.tcw.max_bits = (unsigned*)take(256);
+  // sized for the largest device this library targets (148 SMs); a smaller point set needs fewer CTAs
+  w.fused_grid = cnf_tc::fused_grid_for((int)n, 148);
+  w.fused_scratch = take(cnf_tc::fused_scratch_bytes(w.fused_grid));
   w.bytes = (size_t)(p - (char*)base);
   return w;
 }
@@ -782,6 +787,17 @@ int enqueue_stages(const CnfWorkspace& w, const caspr_cnf_weights* cw, const flo
       w.Gc, w.Bc, w.wg_t, w.wb_t, w.lbias, frames, 3 * H + 3, ctot, stage_first, reverse, w.st,
       use_tc ? w.col_scale : nullptr, w.gate, w.biasf);
   CASPR_CHECK_LAUNCH();
+  if (use_tc && plan->fused_grid > 0) {
+    // ONE launch per dynamics evaluation: layer 0, both H x H layers, the output layer and the divergence
+    for (int stage = stage_first; stage <= stage_last; ++stage) {
+      const float* gate = w.gate + (size_t)stage * frames * ctot;
+      const float* biasf = w.biasf + (size_t)stage * frames * ctot;
+      int rc = cnf_tc::enqueue_fused(*plan, w.y0, w.kbuf, (size_t)n, e, cw->W[0], cw->W[3], n, pts, stage, reverse, gate,
+                                     biasf, ctot, w.st, w.kbuf + (size_t)stage * n, w.range_flag, s);
+      if (rc) return rc;
+    }
+    return CASPR_OK;
+  }
   if (use_tc) {
     const int n_tiles = (n + 63) / 64;
     // Optional (CASPR_CNF_PIPELINE_HALVES=1): measured on B200 at 163 840 points the decode span drops from 41.1 to
@@ -849,7 +865,10 @@ int prepare_engine(const CnfWorkspace& w, const caspr_cnf_weights* cw, int n, in
   if (rc) return rc;
   rc = cnf_tc::fill_col_scale(w.tcw, hyper_ld(cw->hidden), w.col_scale, s);
   if (rc) return rc;
-  return cnf_tc::make_plan(*plan, w.tcw, (__half*)w.Ha, (__half*)w.Va, (__half*)w.Hb, (__half*)w.Vb, n);
+  int fgrid = cnf_tc::fused_grid_for(n, *num_sms);
+  if (fgrid > w.fused_grid) fgrid = w.fused_grid;
+  return cnf_tc::make_plan(*plan, w.tcw, (__half*)w.Ha, (__half*)w.Va, (__half*)w.Hb, (__half*)w.Vb, n,
+                           cnf_tc::fused_enabled() ? w.fused_scratch : nullptr, fgrid);
 }
 
 bool weights_ok(const caspr_cnf_weights* cw) {

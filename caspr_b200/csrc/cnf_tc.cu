@@ -384,6 +384,460 @@ cnf_tc_last_finish_kernel(float* __restrict__ acc6, const float* __restrict__ e,
   kout[pt] = reverse ? make_float4(-dy0, -dy1, -dy2, div) : make_float4(dy0, dy1, dy2, -div);
 }
 
+
+// ====================================================================================================================
+// Fused dynamics evaluation: ONE launch per RK stage (north_star: "a fused RK solver that evaluates the dynamics MLP and
+// accumulates the divergence trace ... in one launch per step").  Replaces the four launches
+// layer 0 -> H x H GEMM -> H x H GEMM -> output finish, whose [activation ; tangent] fp16 planes made a round trip
+// through HBM between them (2.6 GB per evaluation at config 2).
+//
+// Persistent CTA pairs (cta_group::2), one CTA per SM, 448 threads.  Every CTA streams its own 64-point tiles through
+// the whole network; the planes between the layers live in a per-CTA scratch of 768 KB that is re-used in place every
+// tile and therefore stays in the 126 MB L2 (148 x 768 KB = 114 MB address range, ~2/3 of it live at any time):
+//
+//   warps 10-13  layer 0   : RK stage input from (y0, k_j), 3 -> H layer, softplus, tangent W0 e; writes the A planes
+//                            of the tile as fp16 hi / lo rows into scratch SA, k-chunk by k-chunk (`sa_full[kc]`)
+//   warp 0       producer  : TMA loads of A (SA for layer 1, SB for layer 2) and of this CTA's half of the W tile into
+//                            a 2-stage ring (64 KB per stage)
+//   warp 1       MMA       : leader CTA only; 3 x tcgen05.mma.cta_group::2 (M 256, N 256, K 16) per k-step
+//   warps 2-5, 6-9         : two epilogue groups, group g owns TMEM accumulator g.  Layer-1 items: gate / bias /
+//                            softplus / tangent chain rule, fp16 hi / lo split, TMA store into scratch SB; layer-2
+//                            items: the same followed by the fused H -> 3 output layer; the two column halves of a
+//                            tile meet in shared memory and the second group writes k = (dy, -e.J.e) of the tile.
+//
+// Work items of one CTA pair, issued in this order (tile i = the i-th tile pair of the cluster):
+//   L1(i).n0, L1(i).n1, L2(i-1).n0, L2(i-1).n1, L1(i+1).n0, ...
+// so the layer-2 products of a tile run one iteration after its layer-1 epilogues: no tensor-pipe bubble waits for an
+// epilogue, and SB is double buffered by tile parity.
+namespace fused {
+
+constexpr int kThreads = 448;
+constexpr int kStages = 2;
+constexpr int kATile = tcg::kATile;                               // 16 KB
+constexpr int kWTile = tcg::kPairWTile;                           // 16 KB (this CTA's half of the 256-channel W tile)
+constexpr int kStageBytes = 2 * kATile + 2 * kWTile;              // 64 KB
+constexpr int kStagingBytes = 2 * kBM * 64 * 2;                   // per epilogue group: hi and lo boxes of 128 x 64 fp16
+constexpr int kSlotFloats = 64 * 8;                               // partial sums of the output layer, one tile
+constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStagingBytes + kSlotFloats * 4 + 512 + 1024;
+
+struct Params {
+  const float4* y0;
+  const float4* kbuf;
+  size_t kstride;
+  const float* e;
+  const float* W0;
+  const float* W3;
+  const float* gate;       // this stage's slot: layer l at + l*H (l = 0..2), output layer at + 3H
+  const float* biasf;
+  int ld_hyper;
+  int n, P, stage, reverse, n_tiles;
+  const CnfState* st;
+  float4* kout;
+  int* range_flag;
+  __half* sa_hi;           // scratch SA planes [gridDim.x * 128][512]
+  __half* sa_lo;
+};
+
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ void softplus_pair(float pre, float& sp, float& dsp) {
+  const float z = ex2_approx(fminf(pre, 40.f) * kLog2e);
+  const float t = 1.f + z;
+  const bool big = pre > 20.f;
+  sp = big ? pre : kLn2 * lg2_approx(t);
+  dsp = big ? 1.f : z * rcp_approx(t);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid_constant__ CUtensorMap tm_sa_lo,
+                      const __grid_constant__ CUtensorMap tm_sb_hi, const __grid_constant__ CUtensorMap tm_sb_lo,
+                      const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_constant__ CUtensorMap tm_w1_lo,
+                      const __grid_constant__ CUtensorMap tm_w2_hi, const __grid_constant__ CUtensorMap tm_w2_lo,
+                      const Params p) {
+  if (p.st->done) return;                   // uniform over the grid
+  constexpr int H = 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* staging = smem + kStages * kStageBytes;                // [2 groups][hi box | lo box]
+  float* slot = reinterpret_cast<float*>(staging + 2 * kStagingBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slot + kSlotFloats);
+  uint64_t* full = bars;                     // [2]  leader's copy is live
+  uint64_t* empty = bars + 2;                // [2]
+  uint64_t* tfull = bars + 4;                // [2]
+  uint64_t* tempty = bars + 6;               // [2]  leader's copy is live
+  uint64_t* sa_full = bars + 8;              // [8]  layer-0 warps -> producer, per k-chunk
+  uint64_t* sa_free = bars + 16;             //      MMA (commit) -> layer-0 warps
+  uint64_t* sb_full = bars + 17;             // [2]  epilogue groups -> producer, per SB buffer
+  uint64_t* out_half = bars + 19;            //      n0 epilogue group -> n1 epilogue group
+  uint64_t* out_free = bars + 20;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = tc::cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int pairs = (p.n_tiles + 1) >> 1;
+  const int n_iter = cluster_id < pairs ? (pairs - cluster_id + n_clusters - 1) / n_clusters : 0;
+  const int cta = blockIdx.x;
+
+  if (threadIdx.x == 0) {
+    tc::prefetch_tmap(&tm_sa_hi); tc::prefetch_tmap(&tm_sa_lo); tc::prefetch_tmap(&tm_sb_hi); tc::prefetch_tmap(&tm_sb_lo);
+    tc::prefetch_tmap(&tm_w1_hi); tc::prefetch_tmap(&tm_w1_lo); tc::prefetch_tmap(&tm_w2_hi); tc::prefetch_tmap(&tm_w2_lo);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&full[s], 2);
+      tc::mbar_init(&empty[s], 1);
+      tc::mbar_init(&tfull[s], 1);
+      tc::mbar_init(&tempty[s], 256);
+      tc::mbar_init(&sb_full[s], 2);         // one arrival per column half
+    }
+    for (int k = 0; k < 8; ++k) tc::mbar_init(&sa_full[k], 128);
+    tc::mbar_init(sa_free, 1);
+    tc::mbar_init(out_half, 128);
+    tc::mbar_init(out_free, 128);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc_pair(tmem_slot, 512);
+  tc::fence_before_sync();
+  tc::cluster_sync_all();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto load_item = [&](const CUtensorMap* a_hi, const CUtensorMap* a_lo, const CUtensorMap* w_hi,
+                           const CUtensorMap* w_lo, int a_row, int nh, const uint64_t* chunk_bars, uint32_t chunk_parity) {
+        for (int kc = 0; kc < 8; ++kc) {
+          tc::mbar_wait(&empty[stage], phase ^ 1);
+          if (chunk_bars) tc::mbar_wait(const_cast<uint64_t*>(&chunk_bars[kc]), chunk_parity);
+          uint8_t* sb = smem + stage * kStageBytes;
+          const uint32_t lead_full = tc::mapa_shared(&full[stage], 0);
+          if (rank == 0) tc::mbar_arrive_expect_tx(&full[stage], 2 * kStageBytes);
+          else tc::mbar_arrive_cluster(lead_full);
+          tc::tma_load_2d_pair(sb, a_hi, lead_full, kc * 64, a_row);
+          tc::tma_load_2d_pair(sb + kATile, a_lo, lead_full, kc * 64, a_row);
+          tc::tma_load_2d_pair(sb + 2 * kATile, w_hi, lead_full, kc * 64, nh * kBN + (int)rank * (kBN / 2));
+          tc::tma_load_2d_pair(sb + 2 * kATile + kWTile, w_lo, lead_full, kc * 64, nh * kBN + (int)rank * (kBN / 2));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      };
+      for (int i = 0; i <= n_iter; ++i) {
+        if (i < n_iter) {
+          load_item(&tm_sa_hi, &tm_sa_lo, &tm_w1_hi, &tm_w1_lo, cta * kBM, 0, sa_full, (uint32_t)(i & 1));
+          load_item(&tm_sa_hi, &tm_sa_lo, &tm_w1_hi, &tm_w1_lo, cta * kBM, 1, nullptr, 0);
+        }
+        if (i >= 1) {
+          const int b = (i - 1) & 1;
+          tc::mbar_wait(&sb_full[b], (uint32_t)(((i - 1) >> 1) & 1));
+          const int row = (b * (int)gridDim.x + cta) * kBM;
+          load_item(&tm_sb_hi, &tm_sb_lo, &tm_w2_hi, &tm_w2_lo, row, 0, nullptr, 0);
+          load_item(&tm_sb_hi, &tm_sb_lo, &tm_w2_hi, &tm_w2_lo, row, 1, nullptr, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------------------------------------------- MMA issuer
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_f16(2 * kBM, kBN);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      auto mma_item = [&]() {
+        const int buf = it & 1;
+        tc::mbar_wait(&tempty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
+        tc::fence_after_sync();
+        const uint32_t d_tmem = tmem_base + buf * kBN;
+        for (int kc = 0; kc < 8; ++kc) {
+          tc::mbar_wait(&full[stage], phase);
+          tc::fence_after_sync();
+          const uint32_t sb = tc::smem_u32(smem + stage * kStageBytes);
+          const uint64_t a_hi = tc::make_desc_k128(sb);
+          const uint64_t a_lo = tc::make_desc_k128(sb + kATile);
+          const uint64_t w_hi = tc::make_desc_k128(sb + 2 * kATile);
+          const uint64_t w_lo = tc::make_desc_k128(sb + 2 * kATile + kWTile);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t adv = (uint64_t)(ks * 2);
+            tc::umma_f16_ss_pair(d_tmem, a_hi + adv, w_hi + adv, idesc, (kc | ks) != 0);
+            tc::umma_f16_ss_pair(d_tmem, a_lo + adv, w_hi + adv, idesc, 1);
+            tc::umma_f16_ss_pair(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+          }
+          tc::umma_commit_pair(&empty[stage], 3);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        tc::umma_commit_pair(&tfull[buf], 3);
+        ++it;
+      };
+      for (int i = 0; i <= n_iter; ++i) {
+        if (i < n_iter) {
+          mma_item();
+          mma_item();
+          tc::umma_commit_pair(sa_free, 3);          // both layer-1 products of tile i have consumed SA
+        }
+        if (i >= 1) { mma_item(); mma_item(); }
+      }
+    }
+  } else if (warp < 10) {
+    // ---------------------------------------------------------------------------------------- epilogue groups 0 / 1
+    const int grp = (warp - 2) >> 2;                              // owns accumulator `grp`
+    const int q = warp & 3;                                       // TMEM lane quadrant
+    const int etid = (int)threadIdx.x - 64 - grp * 128;
+    const int is_v = lane >> 4;
+    const int pl = q * 16 + (lane & 15);                          // point of this lane within the tile
+    const int box_row = q * 32 + (lane & 15);
+    uint8_t* hi_box = staging + grp * kStagingBytes;
+    uint8_t* lo_box = hi_box + kBM * 128;
+    float range_max = 0.f;
+    int it = 0;                                                   // item counter (all roles count alike)
+    int uses = 0;                                                 // how often this group's accumulator was used
+    for (int i = 0; i <= n_iter; ++i) {
+      for (int sub = 0; sub < 4; ++sub) {
+        const bool layer2 = sub >= 2;
+        if (layer2 ? (i < 1) : (i >= n_iter)) continue;
+        const int my = (it & 1) == grp;
+        ++it;
+        if (!my) continue;
+        const int nh = sub & 1;
+        const int ti = layer2 ? i - 1 : i;                        // tile-pair index this item belongs to
+        const int tile = 2 * (cluster_id + ti * n_clusters) + (int)rank;
+        const int pt = tile * 64 + pl;
+        const bool live = pt < p.n;
+        const int f = (live ? pt : p.n - 1) / p.P;
+        const int col0 = nh * kBN + is_v * 16;
+        const float* gp = p.gate + (size_t)f * p.ld_hyper + (layer2 ? 2 * H : H) + col0;
+        const float* bp = p.biasf + (size_t)f * p.ld_hyper + (layer2 ? 2 * H : H) + col0;
+        tc::mbar_wait(&tfull[grp], (uint32_t)(uses & 1));
+        ++uses;
+        tc::fence_after_sync();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * kBN;
+        float pa[3] = {0.f, 0.f, 0.f}, pv[3] = {0.f, 0.f, 0.f};
+        const int sb_row = ((ti & 1) * (int)gridDim.x + cta) * kBM;
+#pragma unroll 1
+        for (int chunk = 0; chunk < 8; ++chunk) {
+          uint32_t r[32];
+          tc::tmem_ld_32x32(taddr + chunk * 32, r);
+          tc::tmem_ld_wait();
+          float ah[16], av[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t send = is_v ? r[j] : r[16 + j];
+            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 16);
+            ah[j] = __uint_as_float(is_v ? recv : r[j]);
+            av[j] = __uint_as_float(is_v ? r[16 + j] : recv);
+          }
+          float ho[16], vo[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 g4 = *reinterpret_cast<const float4*>(gp + chunk * 32 + j4 * 4);
+            const float4 b4 = *reinterpret_cast<const float4*>(bp + chunk * 32 + j4 * 4);
+            const float g[4] = {g4.x, g4.y, g4.z, g4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int j = j4 * 4 + u;
+              float sp, dsp;
+              softplus_pair(fmaf(ah[j], g[u], b[u]), sp, dsp);
+              ho[j] = sp;
+              vo[j] = dsp * g[u] * av[j];
+            }
+          }
+          if (layer2) {
+            const int col = col0 + chunk * 32;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const float4* w4 = reinterpret_cast<const float4*>(p.W3 + c * H + col);
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 w = __ldg(w4 + j4);
+                pa[c] = fmaf(w.x, ho[4 * j4], pa[c]); pv[c] = fmaf(w.x, vo[4 * j4], pv[c]);
+                pa[c] = fmaf(w.y, ho[4 * j4 + 1], pa[c]); pv[c] = fmaf(w.y, vo[4 * j4 + 1], pv[c]);
+                pa[c] = fmaf(w.z, ho[4 * j4 + 2], pa[c]); pv[c] = fmaf(w.z, vo[4 * j4 + 2], pv[c]);
+                pa[c] = fmaf(w.w, ho[4 * j4 + 3], pa[c]); pv[c] = fmaf(w.w, vo[4 * j4 + 3], pv[c]);
+              }
+            }
+          } else {
+            uint32_t hh[8], hl[8], vh[8], vl[8];
+#pragma unroll
+            for (int j2 = 0; j2 < 8; ++j2) {
+              const float h0 = ho[2 * j2] * kActScale, h1 = ho[2 * j2 + 1] * kActScale;
+              const float v0 = vo[2 * j2] * kActScale, v1 = vo[2 * j2 + 1] * kActScale;
+              if (live) range_max = fmaxf(range_max, fmaxf(fmaxf(fabsf(h0), fabsf(h1)), fmaxf(fabsf(v0), fabsf(v1))));
+              split2(h0, h1, hh[j2], hl[j2]);
+              split2(v0, v1, vh[j2], vl[j2]);
+            }
+            const int odd = chunk & 1;
+            if (!odd) {
+              if (etid == 0) tc::tma_store_wait_read();            // earlier boxes have left the staging buffer
+              tc::named_bar_sync(1 + grp, 128);
+            }
+            const int cc0 = odd * 4 + is_v * 2;
+            const int rh = box_row, rv = box_row + 16;
+            *reinterpret_cast<uint4*>(hi_box + rh * 128 + (((cc0) ^ (rh & 7)) << 4)) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+            *reinterpret_cast<uint4*>(hi_box + rh * 128 + (((cc0 + 1) ^ (rh & 7)) << 4)) = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+            *reinterpret_cast<uint4*>(lo_box + rh * 128 + (((cc0) ^ (rh & 7)) << 4)) = make_uint4(hl[0], hl[1], hl[2], hl[3]);
+            *reinterpret_cast<uint4*>(lo_box + rh * 128 + (((cc0 + 1) ^ (rh & 7)) << 4)) = make_uint4(hl[4], hl[5], hl[6], hl[7]);
+            *reinterpret_cast<uint4*>(hi_box + rv * 128 + (((cc0) ^ (rv & 7)) << 4)) = make_uint4(vh[0], vh[1], vh[2], vh[3]);
+            *reinterpret_cast<uint4*>(hi_box + rv * 128 + (((cc0 + 1) ^ (rv & 7)) << 4)) = make_uint4(vh[4], vh[5], vh[6], vh[7]);
+            *reinterpret_cast<uint4*>(lo_box + rv * 128 + (((cc0) ^ (rv & 7)) << 4)) = make_uint4(vl[0], vl[1], vl[2], vl[3]);
+            *reinterpret_cast<uint4*>(lo_box + rv * 128 + (((cc0 + 1) ^ (rv & 7)) << 4)) = make_uint4(vl[4], vl[5], vl[6], vl[7]);
+            if (odd) {
+              tc::fence_proxy_async_smem();
+              tc::named_bar_sync(1 + grp, 128);
+              if (etid == 0) {
+                const int c_out = nh * kBN + (chunk >> 1) * 64;
+                tc::tma_store_2d(&tm_sb_hi, hi_box, c_out, sb_row);
+                tc::tma_store_2d(&tm_sb_lo, lo_box, c_out, sb_row);
+                tc::tma_store_commit();
+              }
+            }
+          }
+        }
+        // the accumulator is drained: hand it back to the MMA issuer (leader's barrier, both CTAs arrive)
+        tc::fence_before_sync();
+        tc::mbar_arrive_cluster(tc::mapa_shared(&tempty[grp], 0));
+        if (!layer2) {
+          // SB(ti) is complete once the stores of BOTH column halves have landed: each half's storing thread waits
+          // for its own bulk stores and arrives (the barrier counts two arrivals per tile)
+          if (etid == 0) {
+            tc::tma_store_wait_all();
+            fence_proxy_async_all();
+            tc::mbar_arrive(&sb_full[ti & 1]);
+          }
+        } else {
+          // fused output layer: combine the two column halves of every point's lane pair, then the two n halves
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            pa[c] += __shfl_xor_sync(0xffffffffu, pa[c], 16);
+            pv[c] += __shfl_xor_sync(0xffffffffu, pv[c], 16);
+          }
+          if (nh == 0) {
+            tc::mbar_wait(out_free, (uint32_t)((ti & 1) ^ 1));
+            if (!is_v) {
+              float* sl = slot + pl * 8;
+              sl[0] = pa[0]; sl[1] = pa[1]; sl[2] = pa[2]; sl[3] = pv[0]; sl[4] = pv[1]; sl[5] = pv[2];
+            }
+            tc::mbar_arrive(out_half);
+          } else {
+            tc::mbar_wait(out_half, (uint32_t)(ti & 1));
+            if (!is_v) {
+              const float* sl = slot + pl * 8;
+              const float a0 = pa[0] + sl[0], a1 = pa[1] + sl[1], a2 = pa[2] + sl[2];
+              const float t0 = pv[0] + sl[3], t1 = pv[1] + sl[4], t2 = pv[2] + sl[5];
+              if (live) {
+                const float* g = p.gate + (size_t)f * p.ld_hyper + 3 * H;
+                const float* bf = p.biasf + (size_t)f * p.ld_hyper + 3 * H;
+                const float dy0 = fmaf(a0, g[0], bf[0]);
+                const float dy1 = fmaf(a1, g[1], bf[1]);
+                const float dy2 = fmaf(a2, g[2], bf[2]);
+                const float e0 = p.e[3 * (size_t)pt], e1 = p.e[3 * (size_t)pt + 1], e2 = p.e[3 * (size_t)pt + 2];
+                const float div = (g[0] * t0) * e0 + (g[1] * t1) * e1 + (g[2] * t2) * e2;
+                p.kout[pt] = p.reverse ? make_float4(-dy0, -dy1, -dy2, div) : make_float4(dy0, dy1, dy2, -div);
+              }
+            }
+            tc::mbar_arrive(out_free);
+          }
+        }
+      }
+    }
+    if (etid == 0) tc::tma_store_wait_all();
+    if (range_max > 65504.f) atomicOr(p.range_flag, 1);
+  } else {
+    // --------------------------------------------------------------------------------------------- layer-0 warps
+    const int wl = warp - 10;                                     // 0..3: 16 points each
+    const int cg = lane & 7;                                      // 8-channel group inside a 64-channel k-chunk
+    const float dt = (float)p.st->dt;
+    float range_max = 0.f;
+    for (int i = 0; i < n_iter; ++i) {
+      const int tile = 2 * (cluster_id + i * n_clusters) + (int)rank;
+      float ys[4][3], ev[4][3];
+      int fr[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        int pt = tile * 64 + wl * 16 + r * 4 + (lane >> 3);
+        if (pt >= p.n) pt = p.n - 1;                              // tail: recompute a valid point, nobody reads it
+        const float4 y = p.y0[pt];
+        ys[r][0] = y.x; ys[r][1] = y.y; ys[r][2] = y.z;
+        if (p.stage > 0) {
+          float kx[6], ky[6], kz[6];
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+            if (j < p.stage) {
+              const float4 kv = p.kbuf[(size_t)j * p.kstride + pt];
+              kx[j] = kv.x; ky[j] = kv.y; kz[j] = kv.z;
+            } else {
+              kx[j] = ky[j] = kz[j] = 0.f;
+            }
+          }
+          ys[r][0] = dopri5::stage_combine(y.x, dt, kx, p.stage - 1);
+          ys[r][1] = dopri5::stage_combine(y.y, dt, ky, p.stage - 1);
+          ys[r][2] = dopri5::stage_combine(y.z, dt, kz, p.stage - 1);
+        }
+        ev[r][0] = p.e[3 * (size_t)pt]; ev[r][1] = p.e[3 * (size_t)pt + 1]; ev[r][2] = p.e[3 * (size_t)pt + 2];
+        fr[r] = pt / p.P;
+      }
+      if (i > 0) tc::mbar_wait(sa_free, (uint32_t)((i - 1) & 1)); // layer-1 products of the previous tile are done
+#pragma unroll 1
+      for (int kc = 0; kc < 8; ++kc) {
+        const int j0 = kc * 64 + cg * 8;
+        float wl0[24];
+#pragma unroll
+        for (int j4 = 0; j4 < 6; ++j4) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.W0 + 3 * j0) + j4);
+          wl0[4 * j4] = w4.x; wl0[4 * j4 + 1] = w4.y; wl0[4 * j4 + 2] = w4.z; wl0[4 * j4 + 3] = w4.w;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float4* g4p = reinterpret_cast<const float4*>(p.gate + (size_t)fr[r] * p.ld_hyper + j0);
+          const float4* b4p = reinterpret_cast<const float4*>(p.biasf + (size_t)fr[r] * p.ld_hyper + j0);
+          float g[8], bf[8];
+#pragma unroll
+          for (int j4 = 0; j4 < 2; ++j4) {
+            const float4 a = g4p[j4], b = b4p[j4];
+            g[4 * j4] = a.x; g[4 * j4 + 1] = a.y; g[4 * j4 + 2] = a.z; g[4 * j4 + 3] = a.w;
+            bf[4 * j4] = b.x; bf[4 * j4 + 1] = b.y; bf[4 * j4 + 2] = b.z; bf[4 * j4 + 3] = b.w;
+          }
+          uint32_t hh[4], hl[4], vh[4], vl[4];
+#pragma unroll
+          for (int j2 = 0; j2 < 4; ++j2) {
+            float hv[2], vv[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int jj = j2 * 2 + u;
+              const float w0 = wl0[3 * jj], w1 = wl0[3 * jj + 1], w2 = wl0[3 * jj + 2];
+              const float a = fmaf(w2, ys[r][2], fmaf(w1, ys[r][1], w0 * ys[r][0]));
+              const float ta = fmaf(w2, ev[r][2], fmaf(w1, ev[r][1], w0 * ev[r][0]));
+              float sp, dsp;
+              softplus_pair(fmaf(a, g[jj], bf[jj]), sp, dsp);
+              hv[u] = sp * kActScale;
+              vv[u] = dsp * g[jj] * ta * kActScale;
+              range_max = fmaxf(range_max, fmaxf(fabsf(hv[u]), fabsf(vv[u])));
+            }
+            split2(hv[0], hv[1], hh[j2], hl[j2]);
+            split2(vv[0], vv[1], vh[j2], vl[j2]);
+          }
+          const int plr = wl * 16 + r * 4 + (lane >> 3);
+          const size_t row_h = (size_t)cta * kBM + (plr >> 4) * 32 + (plr & 15);
+          const size_t row_v = row_h + 16;
+          *reinterpret_cast<uint4*>(p.sa_hi + row_h * H + j0) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+          *reinterpret_cast<uint4*>(p.sa_lo + row_h * H + j0) = make_uint4(hl[0], hl[1], hl[2], hl[3]);
+          *reinterpret_cast<uint4*>(p.sa_hi + row_v * H + j0) = make_uint4(vh[0], vh[1], vh[2], vh[3]);
+          *reinterpret_cast<uint4*>(p.sa_lo + row_v * H + j0) = make_uint4(vl[0], vl[1], vl[2], vl[3]);
+        }
+        fence_proxy_async_all();                                  // generic-proxy stores -> visible to the TMA loads
+        tc::mbar_arrive(&sa_full[kc]);
+      }
+    }
+    if (range_max > 65504.f) atomicOr(p.range_flag, 1);
+  }
+  tc::fence_before_sync();
+  tc::cluster_sync_all();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+}  // namespace fused
+
 }  // namespace
 
 size_t weights_workspace_bytes() {
@@ -412,7 +866,8 @@ int fill_col_scale(const Weights& w, int ctot, float* col_scale, cudaStream_t s)
   return CASPR_OK;
 }
 
-int make_plan(Plan& plan, const Weights& w, __half* a_hi, __half* a_lo, __half* b_hi, __half* b_lo, int n) {
+int make_plan(Plan& plan, const Weights& w, __half* a_hi, __half* a_lo, __half* b_hi, __half* b_lo, int n,
+              void* fused_scratch, int fused_grid) {
   plan.n_tiles = (n + 63) / 64;
   const uint64_t rows = (uint64_t)plan.n_tiles * 128;
   bool ok = true;
@@ -425,7 +880,57 @@ int make_plan(Plan& plan, const Weights& w, __half* a_hi, __half* a_lo, __half* 
     ok &= caspr_make_tmap_f16(&plan.tm_w[l][1], w.lo[l], 512, 512, tcg::w_box_rows());
   }
   plan.a_hi = a_hi; plan.a_lo = a_lo; plan.b_hi = b_hi; plan.b_lo = b_lo;
+  plan.fused_grid = 0;
+  if (fused_scratch && fused_grid > 0 && tcg::use_pair()) {
+    // scratch layout: [SA hi | SA lo | SB hi (2 buffers) | SB lo (2 buffers)], tiles of [128][512] fp16 per CTA
+    const size_t tile_bytes = (size_t)128 * 512 * 2;
+    char* base = (char*)fused_scratch;
+    plan.sa_hi = (__half*)base;
+    plan.sa_lo = (__half*)(base + (size_t)fused_grid * tile_bytes);
+    __half* sb_hi = (__half*)(base + (size_t)2 * fused_grid * tile_bytes);
+    __half* sb_lo = (__half*)(base + (size_t)4 * fused_grid * tile_bytes);
+    ok &= caspr_make_tmap_f16(&plan.tm_sa[0], plan.sa_hi, (uint64_t)fused_grid * 128, 512, kBM);
+    ok &= caspr_make_tmap_f16(&plan.tm_sa[1], plan.sa_lo, (uint64_t)fused_grid * 128, 512, kBM);
+    ok &= caspr_make_tmap_f16(&plan.tm_sb[0], sb_hi, (uint64_t)2 * fused_grid * 128, 512, kBM);
+    ok &= caspr_make_tmap_f16(&plan.tm_sb[1], sb_lo, (uint64_t)2 * fused_grid * 128, 512, kBM);
+    plan.fused_grid = fused_grid;
+  }
   if (!ok) return CASPR_ELAUNCH;
+  return CASPR_OK;
+}
+
+bool fused_enabled() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("CASPR_CNF_FUSED");
+    mode = (e && e[0] == '0') ? 0 : 1;
+  }
+  return mode == 1 && tcg::use_pair();
+}
+
+int enqueue_fused(const Plan& plan, const float4* y0, const float4* kbuf, size_t kstride, const float* e,
+                  const float* W0, const float* W3, int n, int P, int stage, int reverse, const float* gate,
+                  const float* biasf, int ld_hyper, const CnfState* st, float4* kout, int* range_flag,
+                  cudaStream_t s) {
+  if (plan.fused_grid <= 0) return CASPR_EINVAL;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(fused::cnf_fused_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             fused::kSmemBytes) != cudaSuccess)
+      return CASPR_ELAUNCH;
+    attr_set = true;
+  }
+  fused::Params p;
+  p.y0 = y0; p.kbuf = kbuf; p.kstride = kstride; p.e = e; p.W0 = W0; p.W3 = W3; p.gate = gate; p.biasf = biasf;
+  p.ld_hyper = ld_hyper; p.n = n; p.P = P; p.stage = stage; p.reverse = reverse; p.n_tiles = (n + 63) / 64; p.st = st;
+  p.kout = kout; p.range_flag = range_flag; p.sa_hi = plan.sa_hi; p.sa_lo = plan.sa_lo;
+  caspr_prof_begin(CASPR_PROF_CNF_FUSED_TC, s);
+  CASPR_COUNT();
+  fused::cnf_fused_eval_kernel<<<plan.fused_grid, fused::kThreads, fused::kSmemBytes, s>>>(
+      plan.tm_sa[0], plan.tm_sa[1], plan.tm_sb[0], plan.tm_sb[1], plan.tm_w[0][0], plan.tm_w[0][1], plan.tm_w[1][0],
+      plan.tm_w[1][1], p);
+  caspr_prof_end(CASPR_PROF_CNF_FUSED_TC, s);
+  CASPR_CHECK_LAUNCH();
   return CASPR_OK;
 }
 

@@ -22,12 +22,33 @@ struct Plan {
   CUtensorMap tm_w[2][2];     // [layer][hi/lo]
   __half *a_hi, *a_lo, *b_hi, *b_lo;
   int n_tiles;
+  // fused evaluation kernel: per-CTA scratch planes (SA: one 128-row tile per CTA, SB: two) and their tensor maps
+  CUtensorMap tm_sa[2], tm_sb[2];     // [hi/lo]
+  __half *sa_hi, *sa_lo;
+  int fused_grid;                     // CTAs of the fused kernel (0: fused path not available)
 };
+
+// number of CTAs the fused kernel uses for n points on a device with num_sms SMs (even: CTA pairs)
+inline int fused_grid_for(int n, int num_sms) {
+  const int pairs = ((n + 63) / 64 + 1) / 2;
+  const int clusters = pairs < num_sms / 2 ? pairs : num_sms / 2;
+  return 2 * clusters;
+}
+// bytes of scratch the fused kernel needs for `grid` CTAs: SA (hi, lo) + SB (hi, lo) x 2 buffers, [128][512] fp16 tiles
+inline size_t fused_scratch_bytes(int grid) { return (size_t)grid * 128 * 512 * 2 * 6; }
 
 size_t weights_workspace_bytes();
 int prepare_weights(const float* W1, const float* W2, const Weights& out, cudaStream_t s);
 int fill_col_scale(const Weights& w, int ctot, float* col_scale, cudaStream_t s);
-int make_plan(Plan& plan, const Weights& w, __half* a_hi, __half* a_lo, __half* b_hi, __half* b_lo, int n);
+int make_plan(Plan& plan, const Weights& w, __half* a_hi, __half* a_lo, __half* b_hi, __half* b_lo, int n,
+              void* fused_scratch = nullptr, int fused_grid = 0);
+// whether the fused single-launch evaluation is used (CASPR_CNF_FUSED=0 selects the four-kernel path)
+bool fused_enabled();
+// One dynamics evaluation (all four layers) for ALL points into kout, one launch.
+int enqueue_fused(const Plan& plan, const float4* y0, const float4* kbuf, size_t kstride, const float* e,
+                  const float* W0, const float* W3, int n, int P, int stage, int reverse, const float* gate,
+                  const float* biasf, int ld_hyper, const CnfState* st, float4* kout, int* range_flag,
+                  cudaStream_t s);
 // The three stages below work on the point range [pt0, n_end) (tile aligned: pt0 % 64 == 0) resp. the row tiles
 // [m_tile0, m_tile0 + m_tiles), so that two halves of the point set can be pipelined on two streams.
 int enqueue_layer0(const Plan& plan, const float4* y0, const float4* kbuf, size_t kstride, const float* e,
