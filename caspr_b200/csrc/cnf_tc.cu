@@ -392,8 +392,8 @@ cnf_tc_last_finish_kernel(float* __restrict__ acc6, const float* __restrict__ e,
 // through HBM between them (2.6 GB per evaluation at config 2).
 //
 // Persistent CTA pairs (cta_group::2), one CTA per SM, 448 threads.  Every CTA streams its own 64-point tiles through
-// the whole network; the planes between the layers live in a per-CTA scratch of 768 KB that is re-used in place every
-// tile and therefore stays in the 126 MB L2 (148 x 768 KB = 114 MB address range, ~2/3 of it live at any time):
+// the whole network; the planes between the layers live in a per-CTA scratch of 512 KB that is re-used in place every
+// tile and therefore stays in the 126 MB L2 (148 x 512 KB = 76 MB):
 //
 //   warps 10-13  layer 0   : RK stage input from (y0, k_j), 3 -> H layer, softplus, tangent W0 e; writes the A planes
 //                            of the tile as fp16 hi / lo rows into scratch SA, k-chunk by k-chunk (`sa_full[kc]`)
@@ -406,9 +406,12 @@ cnf_tc_last_finish_kernel(float* __restrict__ acc6, const float* __restrict__ e,
 //                            tile meet in shared memory and the second group writes k = (dy, -e.J.e) of the tile.
 //
 // Work items of one CTA pair, issued in this order (tile i = the i-th tile pair of the cluster):
-//   L1(i).n0, L1(i).n1, L2(i-1).n0, L2(i-1).n1, L1(i+1).n0, ...
-// so the layer-2 products of a tile run one iteration after its layer-1 epilogues: no tensor-pipe bubble waits for an
-// epilogue, and SB is double buffered by tile parity.
+//   L1(i).n0, L1(i).n1, L2(i).n0, L2(i).n1, L1(i+1).n0, ...
+// The layer-2 products chase the layer-1 epilogues through per-box flags (`sb_full[kc]`: the 64-column box kc of SB
+// has landed): L2(i).n0 starts with the four k-chunks L1(i).n0 produced while the epilogue of L1(i).n1 is still
+// writing the other four.  Keeping the re-use distance of a scratch line this short (SA and SB are single buffers of
+// 256 KB per CTA, 76 MB in total) is what keeps them in L2: a first version that ran L2(i-1) one iteration behind
+// L1(i) with a double-buffered SB (114 MB) had a 60 % L2 hit rate and still moved 2.0 GB through HBM per launch.
 namespace fused {
 
 constexpr int kThreads = 448;
@@ -467,10 +470,10 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
   uint64_t* tempty = bars + 6;               // [2]  leader's copy is live
   uint64_t* sa_full = bars + 8;              // [8]  layer-0 warps -> producer, per k-chunk
   uint64_t* sa_free = bars + 16;             //      MMA (commit) -> layer-0 warps
-  uint64_t* sb_full = bars + 17;             // [2]  epilogue groups -> producer, per SB buffer
-  uint64_t* out_half = bars + 19;            //      n0 epilogue group -> n1 epilogue group
-  uint64_t* out_free = bars + 20;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  uint64_t* sb_full = bars + 17;             // [8]  epilogue groups -> producer, per 64-column box of SB
+  uint64_t* out_half = bars + 25;            //      n0 epilogue group -> n1 epilogue group
+  uint64_t* out_free = bars + 26;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = tc::cluster_ctarank();
@@ -487,9 +490,11 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
       tc::mbar_init(&empty[s], 1);
       tc::mbar_init(&tfull[s], 1);
       tc::mbar_init(&tempty[s], 256);
-      tc::mbar_init(&sb_full[s], 2);         // one arrival per column half
     }
-    for (int k = 0; k < 8; ++k) tc::mbar_init(&sa_full[k], 128);
+    for (int k = 0; k < 8; ++k) {
+      tc::mbar_init(&sa_full[k], 128);
+      tc::mbar_init(&sb_full[k], 1);
+    }
     tc::mbar_init(sa_free, 1);
     tc::mbar_init(out_half, 128);
     tc::mbar_init(out_free, 128);
@@ -522,18 +527,12 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       };
-      for (int i = 0; i <= n_iter; ++i) {
-        if (i < n_iter) {
-          load_item(&tm_sa_hi, &tm_sa_lo, &tm_w1_hi, &tm_w1_lo, cta * kBM, 0, sa_full, (uint32_t)(i & 1));
-          load_item(&tm_sa_hi, &tm_sa_lo, &tm_w1_hi, &tm_w1_lo, cta * kBM, 1, nullptr, 0);
-        }
-        if (i >= 1) {
-          const int b = (i - 1) & 1;
-          tc::mbar_wait(&sb_full[b], (uint32_t)(((i - 1) >> 1) & 1));
-          const int row = (b * (int)gridDim.x + cta) * kBM;
-          load_item(&tm_sb_hi, &tm_sb_lo, &tm_w2_hi, &tm_w2_lo, row, 0, nullptr, 0);
-          load_item(&tm_sb_hi, &tm_sb_lo, &tm_w2_hi, &tm_w2_lo, row, 1, nullptr, 0);
-        }
+      for (int i = 0; i < n_iter; ++i) {
+        const uint32_t par = (uint32_t)(i & 1);
+        load_item(&tm_sa_hi, &tm_sa_lo, &tm_w1_hi, &tm_w1_lo, cta * kBM, 0, sa_full, par);
+        load_item(&tm_sa_hi, &tm_sa_lo, &tm_w1_hi, &tm_w1_lo, cta * kBM, 1, nullptr, 0);
+        load_item(&tm_sb_hi, &tm_sb_lo, &tm_w2_hi, &tm_w2_lo, cta * kBM, 0, sb_full, par);
+        load_item(&tm_sb_hi, &tm_sb_lo, &tm_w2_hi, &tm_w2_lo, cta * kBM, 1, nullptr, 0);
       }
     }
   } else if (warp == 1) {
@@ -568,13 +567,12 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
         tc::umma_commit_pair(&tfull[buf], 3);
         ++it;
       };
-      for (int i = 0; i <= n_iter; ++i) {
-        if (i < n_iter) {
-          mma_item();
-          mma_item();
-          tc::umma_commit_pair(sa_free, 3);          // both layer-1 products of tile i have consumed SA
-        }
-        if (i >= 1) { mma_item(); mma_item(); }
+      for (int i = 0; i < n_iter; ++i) {
+        mma_item();
+        mma_item();
+        tc::umma_commit_pair(sa_free, 3);            // both layer-1 products of tile i have consumed SA
+        mma_item();
+        mma_item();
       }
     }
   } else if (warp < 10) {
@@ -590,15 +588,15 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
     float range_max = 0.f;
     int it = 0;                                                   // item counter (all roles count alike)
     int uses = 0;                                                 // how often this group's accumulator was used
-    for (int i = 0; i <= n_iter; ++i) {
+    int pending_box = -1;                                         // etid 0: box whose TMA store is still in flight
+    for (int i = 0; i < n_iter; ++i) {
       for (int sub = 0; sub < 4; ++sub) {
         const bool layer2 = sub >= 2;
-        if (layer2 ? (i < 1) : (i >= n_iter)) continue;
         const int my = (it & 1) == grp;
         ++it;
         if (!my) continue;
         const int nh = sub & 1;
-        const int ti = layer2 ? i - 1 : i;                        // tile-pair index this item belongs to
+        const int ti = i;                                         // tile-pair index this item belongs to
         const int tile = 2 * (cluster_id + ti * n_clusters) + (int)rank;
         const int pt = tile * 64 + pl;
         const bool live = pt < p.n;
@@ -611,7 +609,7 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
         tc::fence_after_sync();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * kBN;
         float pa[3] = {0.f, 0.f, 0.f}, pv[3] = {0.f, 0.f, 0.f};
-        const int sb_row = ((ti & 1) * (int)gridDim.x + cta) * kBM;
+        const int sb_row = cta * kBM;
 #pragma unroll 1
         for (int chunk = 0; chunk < 8; ++chunk) {
           uint32_t r[32];
@@ -666,7 +664,14 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
             }
             const int odd = chunk & 1;
             if (!odd) {
-              if (etid == 0) tc::tma_store_wait_read();            // earlier boxes have left the staging buffer
+              if (etid == 0 && pending_box >= 0) {
+                // the previous box was issued two chunks ago: by now its store has landed (and has long left the
+                // staging buffer) -> publish it to the producer, then the staging buffer may be refilled
+                tc::tma_store_wait_all();
+                fence_proxy_async_all();
+                tc::mbar_arrive(&sb_full[pending_box]);
+                pending_box = -1;
+              }
               tc::named_bar_sync(1 + grp, 128);
             }
             const int cc0 = odd * 4 + is_v * 2;
@@ -687,6 +692,7 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
                 tc::tma_store_2d(&tm_sb_hi, hi_box, c_out, sb_row);
                 tc::tma_store_2d(&tm_sb_lo, lo_box, c_out, sb_row);
                 tc::tma_store_commit();
+                pending_box = nh * 4 + (chunk >> 1);
               }
             }
           }
@@ -695,12 +701,12 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
         tc::fence_before_sync();
         tc::mbar_arrive_cluster(tc::mapa_shared(&tempty[grp], 0));
         if (!layer2) {
-          // SB(ti) is complete once the stores of BOTH column halves have landed: each half's storing thread waits
-          // for its own bulk stores and arrives (the barrier counts two arrivals per tile)
-          if (etid == 0) {
+          // the last box of this item: wait for it right away (the accumulator has already been handed back)
+          if (etid == 0 && pending_box >= 0) {
             tc::tma_store_wait_all();
             fence_proxy_async_all();
-            tc::mbar_arrive(&sb_full[ti & 1]);
+            tc::mbar_arrive(&sb_full[pending_box]);
+            pending_box = -1;
           }
         } else {
           // fused output layer: combine the two column halves of every point's lane pair, then the two n halves
@@ -882,17 +888,17 @@ int make_plan(Plan& plan, const Weights& w, __half* a_hi, __half* a_lo, __half* 
   plan.a_hi = a_hi; plan.a_lo = a_lo; plan.b_hi = b_hi; plan.b_lo = b_lo;
   plan.fused_grid = 0;
   if (fused_scratch && fused_grid > 0 && tcg::use_pair()) {
-    // scratch layout: [SA hi | SA lo | SB hi (2 buffers) | SB lo (2 buffers)], tiles of [128][512] fp16 per CTA
+    // scratch layout: [SA hi | SA lo | SB hi | SB lo], one [128][512] fp16 tile per CTA and plane
     const size_t tile_bytes = (size_t)128 * 512 * 2;
     char* base = (char*)fused_scratch;
     plan.sa_hi = (__half*)base;
     plan.sa_lo = (__half*)(base + (size_t)fused_grid * tile_bytes);
     __half* sb_hi = (__half*)(base + (size_t)2 * fused_grid * tile_bytes);
-    __half* sb_lo = (__half*)(base + (size_t)4 * fused_grid * tile_bytes);
+    __half* sb_lo = (__half*)(base + (size_t)3 * fused_grid * tile_bytes);
     ok &= caspr_make_tmap_f16(&plan.tm_sa[0], plan.sa_hi, (uint64_t)fused_grid * 128, 512, kBM);
     ok &= caspr_make_tmap_f16(&plan.tm_sa[1], plan.sa_lo, (uint64_t)fused_grid * 128, 512, kBM);
-    ok &= caspr_make_tmap_f16(&plan.tm_sb[0], sb_hi, (uint64_t)2 * fused_grid * 128, 512, kBM);
-    ok &= caspr_make_tmap_f16(&plan.tm_sb[1], sb_lo, (uint64_t)2 * fused_grid * 128, 512, kBM);
+    ok &= caspr_make_tmap_f16(&plan.tm_sb[0], sb_hi, (uint64_t)fused_grid * 128, 512, kBM);
+    ok &= caspr_make_tmap_f16(&plan.tm_sb[1], sb_lo, (uint64_t)fused_grid * 128, 512, kBM);
     plan.fused_grid = fused_grid;
   }
   if (!ok) return CASPR_ELAUNCH;

@@ -22,7 +22,7 @@ struct Plan {
   CUtensorMap tm_w[2][2];     // [layer][hi/lo]
   __half *a_hi, *a_lo, *b_hi, *b_lo;
   int n_tiles;
-  // fused evaluation kernel: per-CTA scratch planes (SA: one 128-row tile per CTA, SB: two) and their tensor maps
+  // fused evaluation kernel: per-CTA scratch planes (SA, SB: one 128-row tile per CTA) and their tensor maps
   CUtensorMap tm_sa[2], tm_sb[2];     // [hi/lo]
   __half *sa_hi, *sa_lo;
   int fused_grid;                     // CTAs of the fused kernel (0: fused path not available)
@@ -34,8 +34,8 @@ inline int fused_grid_for(int n, int num_sms) {
   const int clusters = pairs < num_sms / 2 ? pairs : num_sms / 2;
   return 2 * clusters;
 }
-// bytes of scratch the fused kernel needs for `grid` CTAs: SA (hi, lo) + SB (hi, lo) x 2 buffers, [128][512] fp16 tiles
-inline size_t fused_scratch_bytes(int grid) { return (size_t)grid * 128 * 512 * 2 * 6; }
+// bytes of scratch the fused kernel needs for `grid` CTAs: SA (hi, lo) + SB (hi, lo), one [128][512] fp16 tile each
+inline size_t fused_scratch_bytes(int grid) { return (size_t)grid * 128 * 512 * 2 * 4; }
 
 size_t weights_workspace_bytes();
 int prepare_weights(const float* W1, const float* W2, const Weights& out, cudaStream_t s);
