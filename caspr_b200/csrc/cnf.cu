@@ -217,3 +217,15 @@ extern "C" int caspr_cnf_feval(const float* y, const float* e, const float* ctx,
     return CASPR_ELAUNCH;
   return CASPR_OK;
 }
+
+// Profiling aid: with CASPR_CNF_FUSED_DEBUG=1 the fused evaluation kernel records, per CTA, the cycles its TMA producer
+// and MMA threads spent waiting ([0] stage free, [1] layer-0 / layer-1 output ready, [2] producer total, [4] accumulator
+// free, [5] operands landed, [6] MMA thread total) during its LAST launch.  Copies count (<= 148*8) counters to `out`.
+extern "C" int caspr_cnf_fused_debug_read(long long* out, int count) {
+  CASPR_REQUIRE(out && count > 0 && count <= 148 * 8);
+  long long* buf = cnf_tc::fused_debug_buffer();
+  if (!buf) return CASPR_EINVAL;
+  if (cudaDeviceSynchronize() != cudaSuccess) return CASPR_ELAUNCH;
+  if (cudaMemcpy(out, buf, (size_t)count * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return CASPR_ELAUNCH;
+  return CASPR_OK;
+}

@@ -400,10 +400,11 @@ cnf_tc_last_finish_kernel(float* __restrict__ acc6, const float* __restrict__ e,
 //   warp 0       producer  : TMA loads of A (SA for layer 1, SB for layer 2) and of this CTA's half of the W tile into
 //                            a 2-stage ring (64 KB per stage)
 //   warp 1       MMA       : leader CTA only; 3 x tcgen05.mma.cta_group::2 (M 256, N 256, K 16) per k-step
-//   warps 2-5, 6-9         : two epilogue groups, group g owns TMEM accumulator g.  Layer-1 items: gate / bias /
-//                            softplus / tangent chain rule, fp16 hi / lo split, TMA store into scratch SB; layer-2
-//                            items: the same followed by the fused H -> 3 output layer; the two column halves of a
-//                            tile meet in shared memory and the second group writes k = (dy, -e.J.e) of the tile.
+//   warps 2-5, 6-9         : two epilogue groups; BOTH work on every accumulator, group g on its columns 128g..128g+127
+//                            (halves the latency of an item's epilogue, which the chase below depends on).  Layer-1
+//                            items: gate / bias / softplus / tangent chain rule, fp16 hi / lo split, 16-byte stores
+//                            into scratch SB; layer-2 items: the same followed by the fused H -> 3 output layer; the
+//                            four partial sums of a tile meet in shared memory and group 1 writes k = (dy, -e.J.e).
 //
 // Work items of one CTA pair, issued in this order (tile i = the i-th tile pair of the cluster):
 //   L1(i).n0, L1(i).n1, L2(i).n0, L2(i).n1, L1(i+1).n0, ...
@@ -415,13 +416,12 @@ cnf_tc_last_finish_kernel(float* __restrict__ acc6, const float* __restrict__ e,
 namespace fused {
 
 constexpr int kThreads = 448;
-constexpr int kStages = 2;
+constexpr int kStages = 3;
 constexpr int kATile = tcg::kATile;                               // 16 KB
 constexpr int kWTile = tcg::kPairWTile;                           // 16 KB (this CTA's half of the 256-channel W tile)
 constexpr int kStageBytes = 2 * kATile + 2 * kWTile;              // 64 KB
-constexpr int kStagingBytes = 2 * kBM * 64 * 2;                   // per epilogue group: hi and lo boxes of 128 x 64 fp16
-constexpr int kSlotFloats = 64 * 8;                               // partial sums of the output layer, one tile
-constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStagingBytes + kSlotFloats * 4 + 512 + 1024;
+constexpr int kSlotFloats = 4 * 64 * 6;                           // partial sums of the output layer: [group][n half][point][6]
+constexpr int kSmemBytes = kStages * kStageBytes + kSlotFloats * 4 + 512 + 1024;
 
 struct Params {
   const float4* y0;
@@ -439,6 +439,9 @@ struct Params {
   int* range_flag;
   __half* sa_hi;           // scratch SA planes [gridDim.x * 128][512]
   __half* sa_lo;
+  __half* sb_hi;           // scratch SB planes, same shape
+  __half* sb_lo;
+  long long* debug;        // optional [gridDim.x][8] cycle counters of the producer / MMA threads (CASPR_CNF_FUSED_DEBUG)
 };
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -461,19 +464,18 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
   constexpr int H = 512;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* staging = smem + kStages * kStageBytes;                // [2 groups][hi box | lo box]
-  float* slot = reinterpret_cast<float*>(staging + 2 * kStagingBytes);
+  float* slot = reinterpret_cast<float*>(smem + kStages * kStageBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(slot + kSlotFloats);
-  uint64_t* full = bars;                     // [2]  leader's copy is live
-  uint64_t* empty = bars + 2;                // [2]
-  uint64_t* tfull = bars + 4;                // [2]
-  uint64_t* tempty = bars + 6;               // [2]  leader's copy is live
-  uint64_t* sa_full = bars + 8;              // [8]  layer-0 warps -> producer, per k-chunk
-  uint64_t* sa_free = bars + 16;             //      MMA (commit) -> layer-0 warps
-  uint64_t* sb_full = bars + 17;             // [8]  epilogue groups -> producer, per 64-column box of SB
-  uint64_t* out_half = bars + 25;            //      n0 epilogue group -> n1 epilogue group
-  uint64_t* out_free = bars + 26;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
+  uint64_t* full = bars;                     // [3]  leader's copy is live
+  uint64_t* empty = bars + 3;                // [3]
+  uint64_t* tfull = bars + 6;                // [2]
+  uint64_t* tempty = bars + 8;               // [2]  leader's copy is live
+  uint64_t* sa_full = bars + 10;             // [8]  layer-0 warps -> producer, per k-chunk
+  uint64_t* sa_free = bars + 18;             //      MMA (commit) -> layer-0 warps
+  uint64_t* sb_full = bars + 19;             // [8]  epilogue groups -> producer, per 64-column box of SB
+  uint64_t* out_half = bars + 27;            //      n0 epilogue group -> n1 epilogue group
+  uint64_t* out_free = bars + 28;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = tc::cluster_ctarank();
@@ -485,19 +487,21 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
   if (threadIdx.x == 0) {
     tc::prefetch_tmap(&tm_sa_hi); tc::prefetch_tmap(&tm_sa_lo); tc::prefetch_tmap(&tm_sb_hi); tc::prefetch_tmap(&tm_sb_lo);
     tc::prefetch_tmap(&tm_w1_hi); tc::prefetch_tmap(&tm_w1_lo); tc::prefetch_tmap(&tm_w2_hi); tc::prefetch_tmap(&tm_w2_lo);
-    for (int s = 0; s < 2; ++s) {
-      tc::mbar_init(&full[s], 2);
+    for (int s = 0; s < kStages; ++s) {
+      tc::mbar_init(&full[s], 1);            // the leader's arrive.expect_tx; the peer only contributes bytes
       tc::mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&tfull[s], 1);
-      tc::mbar_init(&tempty[s], 256);
+      tc::mbar_init(&tempty[s], 512);        // both epilogue groups of both CTAs
     }
     for (int k = 0; k < 8; ++k) {
       tc::mbar_init(&sa_full[k], 128);
-      tc::mbar_init(&sb_full[k], 1);
+      tc::mbar_init(&sb_full[k], 128);       // every thread of the storing epilogue group arrives
     }
     tc::mbar_init(sa_free, 1);
-    tc::mbar_init(out_half, 128);
-    tc::mbar_init(out_free, 128);
+    tc::mbar_init(out_half, 256);            // all partial sums of a tile are in `slot`
+    tc::mbar_init(out_free, 128);            // group 1 has consumed them
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc_pair(tmem_slot, 512);
@@ -511,15 +515,19 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      long long dbg_empty = 0, dbg_dep = 0, dbg_dep2 = 0;
+      const long long dbg_t0 = p.debug ? clock64() : 0;
       auto load_item = [&](const CUtensorMap* a_hi, const CUtensorMap* a_lo, const CUtensorMap* w_hi,
                            const CUtensorMap* w_lo, int a_row, int nh, const uint64_t* chunk_bars, uint32_t chunk_parity) {
         for (int kc = 0; kc < 8; ++kc) {
+          const long long c0 = p.debug ? clock64() : 0;
           tc::mbar_wait(&empty[stage], phase ^ 1);
+          const long long c1 = p.debug ? clock64() : 0;
           if (chunk_bars) tc::mbar_wait(const_cast<uint64_t*>(&chunk_bars[kc]), chunk_parity);
+          if (p.debug) { const long long c2 = clock64(); dbg_empty += c1 - c0; if (chunk_bars == sa_full) dbg_dep += c2 - c1; else dbg_dep2 += c2 - c1; }
           uint8_t* sb = smem + stage * kStageBytes;
           const uint32_t lead_full = tc::mapa_shared(&full[stage], 0);
-          if (rank == 0) tc::mbar_arrive_expect_tx(&full[stage], 2 * kStageBytes);
-          else tc::mbar_arrive_cluster(lead_full);
+          if (rank == 0) tc::mbar_arrive_expect_tx(&full[stage], 2 * kStageBytes);       // bytes of BOTH CTAs
           tc::tma_load_2d_pair(sb, a_hi, lead_full, kc * 64, a_row);
           tc::tma_load_2d_pair(sb + kATile, a_lo, lead_full, kc * 64, a_row);
           tc::tma_load_2d_pair(sb + 2 * kATile, w_hi, lead_full, kc * 64, nh * kBN + (int)rank * (kBN / 2));
@@ -534,6 +542,10 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
         load_item(&tm_sb_hi, &tm_sb_lo, &tm_w2_hi, &tm_w2_lo, cta * kBM, 0, sb_full, par);
         load_item(&tm_sb_hi, &tm_sb_lo, &tm_w2_hi, &tm_w2_lo, cta * kBM, 1, nullptr, 0);
       }
+      if (p.debug) {
+        p.debug[cta * 8 + 0] = dbg_empty; p.debug[cta * 8 + 1] = dbg_dep; p.debug[cta * 8 + 2] = clock64() - dbg_t0;
+        p.debug[cta * 8 + 3] = dbg_dep2;
+      }
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------------------------------------------- MMA issuer
@@ -541,13 +553,19 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
       constexpr uint32_t idesc = tc::make_idesc_f16(2 * kBM, kBN);
       int stage = 0, it = 0;
       uint32_t phase = 0;
+      long long dbg_tempty = 0, dbg_full = 0;
+      const long long dbg_t0 = p.debug ? clock64() : 0;
       auto mma_item = [&]() {
         const int buf = it & 1;
+        const long long c0 = p.debug ? clock64() : 0;
         tc::mbar_wait(&tempty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
+        if (p.debug) dbg_tempty += clock64() - c0;
         tc::fence_after_sync();
         const uint32_t d_tmem = tmem_base + buf * kBN;
         for (int kc = 0; kc < 8; ++kc) {
+          const long long c1 = p.debug ? clock64() : 0;
           tc::mbar_wait(&full[stage], phase);
+          if (p.debug) dbg_full += clock64() - c1;
           tc::fence_after_sync();
           const uint32_t sb = tc::smem_u32(smem + stage * kStageBytes);
           const uint64_t a_hi = tc::make_desc_k128(sb);
@@ -574,6 +592,9 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
         mma_item();
         mma_item();
       }
+      if (p.debug) {
+        p.debug[cta * 8 + 4] = dbg_tempty; p.debug[cta * 8 + 5] = dbg_full; p.debug[cta * 8 + 6] = clock64() - dbg_t0;
+      }
     }
   } else if (warp < 10) {
     // ---------------------------------------------------------------------------------------- epilogue groups 0 / 1
@@ -583,18 +604,14 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
     const int is_v = lane >> 4;
     const int pl = q * 16 + (lane & 15);                          // point of this lane within the tile
     const int box_row = q * 32 + (lane & 15);
-    uint8_t* hi_box = staging + grp * kStagingBytes;
-    uint8_t* lo_box = hi_box + kBM * 128;
     float range_max = 0.f;
     int it = 0;                                                   // item counter (all roles count alike)
-    int uses = 0;                                                 // how often this group's accumulator was used
-    int pending_box = -1;                                         // etid 0: box whose TMA store is still in flight
     for (int i = 0; i < n_iter; ++i) {
       for (int sub = 0; sub < 4; ++sub) {
         const bool layer2 = sub >= 2;
-        const int my = (it & 1) == grp;
+        const int buf = it & 1;
+        const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
         ++it;
-        if (!my) continue;
         const int nh = sub & 1;
         const int ti = i;                                         // tile-pair index this item belongs to
         const int tile = 2 * (cluster_id + ti * n_clusters) + (int)rank;
@@ -604,14 +621,20 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
         const int col0 = nh * kBN + is_v * 16;
         const float* gp = p.gate + (size_t)f * p.ld_hyper + (layer2 ? 2 * H : H) + col0;
         const float* bp = p.biasf + (size_t)f * p.ld_hyper + (layer2 ? 2 * H : H) + col0;
-        tc::mbar_wait(&tfull[grp], (uint32_t)(uses & 1));
-        ++uses;
+        tc::mbar_wait(&tfull[buf], acc_phase);
         tc::fence_after_sync();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * kBN;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * kBN;
         float pa[3] = {0.f, 0.f, 0.f}, pv[3] = {0.f, 0.f, 0.f};
         const int sb_row = cta * kBM;
 #pragma unroll 1
-        for (int chunk = 0; chunk < 8; ++chunk) {
+        for (int chunk = grp * 4; chunk < grp * 4 + 4; ++chunk) {
+          // gate / bias of this chunk: issued before the accumulator read so that the L2 latency overlaps it
+          float4 g4[4], b4[4];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            g4[j4] = *reinterpret_cast<const float4*>(gp + chunk * 32 + j4 * 4);
+            b4[j4] = *reinterpret_cast<const float4*>(bp + chunk * 32 + j4 * 4);
+          }
           uint32_t r[32];
           tc::tmem_ld_32x32(taddr + chunk * 32, r);
           tc::tmem_ld_wait();
@@ -626,9 +649,8 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
           float ho[16], vo[16];
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 g4 = *reinterpret_cast<const float4*>(gp + chunk * 32 + j4 * 4);
-            const float4 b4 = *reinterpret_cast<const float4*>(bp + chunk * 32 + j4 * 4);
-            const float g[4] = {g4.x, g4.y, g4.z, g4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+            const float g[4] = {g4[j4].x, g4[j4].y, g4[j4].z, g4[j4].w};
+            const float b[4] = {b4[j4].x, b4[j4].y, b4[j4].z, b4[j4].w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int j = j4 * 4 + u;
@@ -662,89 +684,69 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
               split2(h0, h1, hh[j2], hl[j2]);
               split2(v0, v1, vh[j2], vl[j2]);
             }
-            const int odd = chunk & 1;
-            if (!odd) {
-              if (etid == 0 && pending_box >= 0) {
-                // the previous box was issued two chunks ago: by now its store has landed (and has long left the
-                // staging buffer) -> publish it to the producer, then the staging buffer may be refilled
-                tc::tma_store_wait_all();
-                fence_proxy_async_all();
-                tc::mbar_arrive(&sb_full[pending_box]);
-                pending_box = -1;
-              }
-              tc::named_bar_sync(1 + grp, 128);
-            }
-            const int cc0 = odd * 4 + is_v * 2;
-            const int rh = box_row, rv = box_row + 16;
-            *reinterpret_cast<uint4*>(hi_box + rh * 128 + (((cc0) ^ (rh & 7)) << 4)) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-            *reinterpret_cast<uint4*>(hi_box + rh * 128 + (((cc0 + 1) ^ (rh & 7)) << 4)) = make_uint4(hh[4], hh[5], hh[6], hh[7]);
-            *reinterpret_cast<uint4*>(lo_box + rh * 128 + (((cc0) ^ (rh & 7)) << 4)) = make_uint4(hl[0], hl[1], hl[2], hl[3]);
-            *reinterpret_cast<uint4*>(lo_box + rh * 128 + (((cc0 + 1) ^ (rh & 7)) << 4)) = make_uint4(hl[4], hl[5], hl[6], hl[7]);
-            *reinterpret_cast<uint4*>(hi_box + rv * 128 + (((cc0) ^ (rv & 7)) << 4)) = make_uint4(vh[0], vh[1], vh[2], vh[3]);
-            *reinterpret_cast<uint4*>(hi_box + rv * 128 + (((cc0 + 1) ^ (rv & 7)) << 4)) = make_uint4(vh[4], vh[5], vh[6], vh[7]);
-            *reinterpret_cast<uint4*>(lo_box + rv * 128 + (((cc0) ^ (rv & 7)) << 4)) = make_uint4(vl[0], vl[1], vl[2], vl[3]);
-            *reinterpret_cast<uint4*>(lo_box + rv * 128 + (((cc0 + 1) ^ (rv & 7)) << 4)) = make_uint4(vl[4], vl[5], vl[6], vl[7]);
-            if (odd) {
-              tc::fence_proxy_async_smem();
-              tc::named_bar_sync(1 + grp, 128);
-              if (etid == 0) {
-                const int c_out = nh * kBN + (chunk >> 1) * 64;
-                tc::tma_store_2d(&tm_sb_hi, hi_box, c_out, sb_row);
-                tc::tma_store_2d(&tm_sb_lo, lo_box, c_out, sb_row);
-                tc::tma_store_commit();
-                pending_box = nh * 4 + (chunk >> 1);
+            // 16-byte stores straight into the SB planes of this CTA (the lines stay in L2 and are re-read by TMA a
+            // few microseconds later); after the second chunk of a 64-column box every thread publishes it
+            {
+              __half* sb_hi_p = p.sb_hi + ((size_t)sb_row + box_row) * H + col0 + chunk * 32;
+              __half* sb_lo_p = p.sb_lo + ((size_t)sb_row + box_row) * H + col0 + chunk * 32;
+              *reinterpret_cast<uint4*>(sb_hi_p) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+              *reinterpret_cast<uint4*>(sb_hi_p + 8) = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+              *reinterpret_cast<uint4*>(sb_lo_p) = make_uint4(hl[0], hl[1], hl[2], hl[3]);
+              *reinterpret_cast<uint4*>(sb_lo_p + 8) = make_uint4(hl[4], hl[5], hl[6], hl[7]);
+              *reinterpret_cast<uint4*>(sb_hi_p + 16 * H) = make_uint4(vh[0], vh[1], vh[2], vh[3]);
+              *reinterpret_cast<uint4*>(sb_hi_p + 16 * H + 8) = make_uint4(vh[4], vh[5], vh[6], vh[7]);
+              *reinterpret_cast<uint4*>(sb_lo_p + 16 * H) = make_uint4(vl[0], vl[1], vl[2], vl[3]);
+              *reinterpret_cast<uint4*>(sb_lo_p + 16 * H + 8) = make_uint4(vl[4], vl[5], vl[6], vl[7]);
+              if (chunk & 1) {
+                fence_proxy_async_all();                           // generic-proxy stores -> visible to the TMA loads
+                tc::mbar_arrive(&sb_full[nh * 4 + (chunk >> 1)]);
               }
             }
           }
         }
         // the accumulator is drained: hand it back to the MMA issuer (leader's barrier, both CTAs arrive)
         tc::fence_before_sync();
-        tc::mbar_arrive_cluster(tc::mapa_shared(&tempty[grp], 0));
-        if (!layer2) {
-          // the last box of this item: wait for it right away (the accumulator has already been handed back)
-          if (etid == 0 && pending_box >= 0) {
-            tc::tma_store_wait_all();
-            fence_proxy_async_all();
-            tc::mbar_arrive(&sb_full[pending_box]);
-            pending_box = -1;
-          }
-        } else {
+        tc::mbar_arrive_cluster(tc::mapa_shared(&tempty[buf], 0));
+        if (layer2) {
           // fused output layer: combine the two column halves of every point's lane pair, then the two n halves
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             pa[c] += __shfl_xor_sync(0xffffffffu, pa[c], 16);
             pv[c] += __shfl_xor_sync(0xffffffffu, pv[c], 16);
           }
-          if (nh == 0) {
-            tc::mbar_wait(out_free, (uint32_t)((ti & 1) ^ 1));
-            if (!is_v) {
-              float* sl = slot + pl * 8;
-              sl[0] = pa[0]; sl[1] = pa[1]; sl[2] = pa[2]; sl[3] = pv[0]; sl[4] = pv[1]; sl[5] = pv[2];
-            }
-            tc::mbar_arrive(out_half);
-          } else {
-            tc::mbar_wait(out_half, (uint32_t)(ti & 1));
-            if (!is_v) {
-              const float* sl = slot + pl * 8;
-              const float a0 = pa[0] + sl[0], a1 = pa[1] + sl[1], a2 = pa[2] + sl[2];
-              const float t0 = pv[0] + sl[3], t1 = pv[1] + sl[4], t2 = pv[2] + sl[5];
-              if (live) {
-                const float* g = p.gate + (size_t)f * p.ld_hyper + 3 * H;
-                const float* bf = p.biasf + (size_t)f * p.ld_hyper + 3 * H;
-                const float dy0 = fmaf(a0, g[0], bf[0]);
-                const float dy1 = fmaf(a1, g[1], bf[1]);
-                const float dy2 = fmaf(a2, g[2], bf[2]);
-                const float e0 = p.e[3 * (size_t)pt], e1 = p.e[3 * (size_t)pt + 1], e2 = p.e[3 * (size_t)pt + 2];
-                const float div = (g[0] * t0) * e0 + (g[1] * t1) * e1 + (g[2] * t2) * e2;
-                p.kout[pt] = p.reverse ? make_float4(-dy0, -dy1, -dy2, div) : make_float4(dy0, dy1, dy2, -div);
+          // slot[grp][nh][point][6]; the slots of a tile may be written once group 1 has consumed the previous tile's
+          if (nh == 0) tc::mbar_wait(out_free, (uint32_t)((ti & 1) ^ 1));
+          if (!is_v) {
+            float* sl = slot + ((grp * 2 + nh) * 64 + pl) * 6;
+            sl[0] = pa[0]; sl[1] = pa[1]; sl[2] = pa[2]; sl[3] = pv[0]; sl[4] = pv[1]; sl[5] = pv[2];
+          }
+          if (nh == 1) {
+            tc::mbar_arrive(out_half);                             // 256 arrivals: both groups have written both halves
+            if (grp == 1) {
+              tc::mbar_wait(out_half, (uint32_t)(ti & 1));
+              if (!is_v) {
+                float a[6];
+#pragma unroll
+                for (int c = 0; c < 6; ++c)
+                  a[c] = (slot[(0 * 64 + pl) * 6 + c] + slot[(1 * 64 + pl) * 6 + c]) +
+                         (slot[(2 * 64 + pl) * 6 + c] + slot[(3 * 64 + pl) * 6 + c]);
+                if (live) {
+                  const float* g = p.gate + (size_t)f * p.ld_hyper + 3 * H;
+                  const float* bf = p.biasf + (size_t)f * p.ld_hyper + 3 * H;
+                  const float dy0 = fmaf(a[0], g[0], bf[0]);
+                  const float dy1 = fmaf(a[1], g[1], bf[1]);
+                  const float dy2 = fmaf(a[2], g[2], bf[2]);
+                  const float e0 = p.e[3 * (size_t)pt], e1 = p.e[3 * (size_t)pt + 1], e2 = p.e[3 * (size_t)pt + 2];
+                  const float div = (g[0] * a[3]) * e0 + (g[1] * a[4]) * e1 + (g[2] * a[5]) * e2;
+                  p.kout[pt] = p.reverse ? make_float4(-dy0, -dy1, -dy2, div) : make_float4(dy0, dy1, dy2, -div);
+                }
               }
+              tc::mbar_arrive(out_free);
             }
-            tc::mbar_arrive(out_free);
           }
         }
       }
     }
-    if (etid == 0) tc::tma_store_wait_all();
     if (range_max > 65504.f) atomicOr(p.range_flag, 1);
   } else {
     // --------------------------------------------------------------------------------------------- layer-0 warps
@@ -752,6 +754,7 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
     const int cg = lane & 7;                                      // 8-channel group inside a 64-channel k-chunk
     const float dt = (float)p.st->dt;
     float range_max = 0.f;
+    long long l0_wait = 0;
     for (int i = 0; i < n_iter; ++i) {
       const int tile = 2 * (cluster_id + i * n_clusters) + (int)rank;
       float ys[4][3], ev[4][3];
@@ -780,7 +783,9 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
         ev[r][0] = p.e[3 * (size_t)pt]; ev[r][1] = p.e[3 * (size_t)pt + 1]; ev[r][2] = p.e[3 * (size_t)pt + 2];
         fr[r] = pt / p.P;
       }
+      const long long l0c = (p.debug && threadIdx.x == 320) ? clock64() : 0;
       if (i > 0) tc::mbar_wait(sa_free, (uint32_t)((i - 1) & 1)); // layer-1 products of the previous tile are done
+      if (p.debug && threadIdx.x == 320) l0_wait += clock64() - l0c;
 #pragma unroll 1
       for (int kc = 0; kc < 8; ++kc) {
         const int j0 = kc * 64 + cg * 8;
@@ -792,6 +797,12 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
+          if (r == 2 && kc > 0) {
+            // publish the PREVIOUS k-chunk here, half a chunk of compute after its stores were issued: the proxy fence
+            // (generic-proxy stores -> visible to the TMA loads) then finds them already performed and does not stall
+            fence_proxy_async_all();
+            tc::mbar_arrive(&sa_full[kc - 1]);
+          }
           const float4* g4p = reinterpret_cast<const float4*>(p.gate + (size_t)fr[r] * p.ld_hyper + j0);
           const float4* b4p = reinterpret_cast<const float4*>(p.biasf + (size_t)fr[r] * p.ld_hyper + j0);
           float g[8], bf[8];
@@ -828,11 +839,12 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
           *reinterpret_cast<uint4*>(p.sa_hi + row_v * H + j0) = make_uint4(vh[0], vh[1], vh[2], vh[3]);
           *reinterpret_cast<uint4*>(p.sa_lo + row_v * H + j0) = make_uint4(vl[0], vl[1], vl[2], vl[3]);
         }
-        fence_proxy_async_all();                                  // generic-proxy stores -> visible to the TMA loads
-        tc::mbar_arrive(&sa_full[kc]);
       }
+      fence_proxy_async_all();
+      tc::mbar_arrive(&sa_full[7]);
     }
     if (range_max > 65504.f) atomicOr(p.range_flag, 1);
+    if (p.debug && threadIdx.x == 320) p.debug[cta * 8 + 7] = l0_wait;
   }
   tc::fence_before_sync();
   tc::cluster_sync_all();
@@ -895,6 +907,7 @@ int make_plan(Plan& plan, const Weights& w, __half* a_hi, __half* a_lo, __half* 
     plan.sa_lo = (__half*)(base + (size_t)fused_grid * tile_bytes);
     __half* sb_hi = (__half*)(base + (size_t)2 * fused_grid * tile_bytes);
     __half* sb_lo = (__half*)(base + (size_t)3 * fused_grid * tile_bytes);
+    plan.sb_hi = sb_hi; plan.sb_lo = sb_lo;
     ok &= caspr_make_tmap_f16(&plan.tm_sa[0], plan.sa_hi, (uint64_t)fused_grid * 128, 512, kBM);
     ok &= caspr_make_tmap_f16(&plan.tm_sa[1], plan.sa_lo, (uint64_t)fused_grid * 128, 512, kBM);
     ok &= caspr_make_tmap_f16(&plan.tm_sb[0], sb_hi, (uint64_t)fused_grid * 128, 512, kBM);
@@ -904,6 +917,8 @@ int make_plan(Plan& plan, const Weights& w, __half* a_hi, __half* a_lo, __half* 
   if (!ok) return CASPR_ELAUNCH;
   return CASPR_OK;
 }
+
+long long* g_debug_buf = nullptr;
 
 bool fused_enabled() {
   static int mode = -1;
@@ -929,7 +944,19 @@ int enqueue_fused(const Plan& plan, const float4* y0, const float4* kbuf, size_t
   fused::Params p;
   p.y0 = y0; p.kbuf = kbuf; p.kstride = kstride; p.e = e; p.W0 = W0; p.W3 = W3; p.gate = gate; p.biasf = biasf;
   p.ld_hyper = ld_hyper; p.n = n; p.P = P; p.stage = stage; p.reverse = reverse; p.n_tiles = (n + 63) / 64; p.st = st;
-  p.kout = kout; p.range_flag = range_flag; p.sa_hi = plan.sa_hi; p.sa_lo = plan.sa_lo;
+  p.kout = kout; p.range_flag = range_flag; p.sa_hi = plan.sa_hi; p.sa_lo = plan.sa_lo; p.sb_hi = plan.sb_hi; p.sb_lo = plan.sb_lo;
+  p.debug = nullptr;
+  {
+    // CASPR_CNF_FUSED_DEBUG=1: cycle counters of the producer / MMA threads of the LAST launch, printed at exit by
+    // tools/fused_debug.py through caspr_cnf_fused_debug_read
+    static int dbg = -1;
+    if (dbg < 0) { const char* e2 = getenv("CASPR_CNF_FUSED_DEBUG"); dbg = (e2 && e2[0] == '1') ? 1 : 0; }
+    if (dbg) {
+      if (!g_debug_buf && cudaMalloc(&g_debug_buf, 148 * 8 * sizeof(long long)) != cudaSuccess) return CASPR_ELAUNCH;
+      cudaMemsetAsync(g_debug_buf, 0, 148 * 8 * sizeof(long long), s);
+      p.debug = g_debug_buf;
+    }
+  }
   caspr_prof_begin(CASPR_PROF_CNF_FUSED_TC, s);
   CASPR_COUNT();
   fused::cnf_fused_eval_kernel<<<plan.fused_grid, fused::kThreads, fused::kSmemBytes, s>>>(
@@ -984,5 +1011,7 @@ int enqueue_last_finish(float* acc6, const float* e, int pt0, int n, int P, cons
   CASPR_CHECK_LAUNCH();
   return CASPR_OK;
 }
+
+long long* fused_debug_buffer() { return g_debug_buf; }
 
 }  // namespace cnf_tc

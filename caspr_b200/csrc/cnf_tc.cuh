@@ -24,7 +24,7 @@ struct Plan {
   int n_tiles;
   // fused evaluation kernel: per-CTA scratch planes (SA, SB: one 128-row tile per CTA) and their tensor maps
   CUtensorMap tm_sa[2], tm_sb[2];     // [hi/lo]
-  __half *sa_hi, *sa_lo;
+  __half *sa_hi, *sa_lo, *sb_hi, *sb_lo;
   int fused_grid;                     // CTAs of the fused kernel (0: fused path not available)
 };
 
@@ -44,6 +44,7 @@ int make_plan(Plan& plan, const Weights& w, __half* a_hi, __half* a_lo, __half* 
               void* fused_scratch = nullptr, int fused_grid = 0);
 // whether the fused single-launch evaluation is used (CASPR_CNF_FUSED=0 selects the four-kernel path)
 bool fused_enabled();
+long long* fused_debug_buffer();
 // One dynamics evaluation (all four layers) for ALL points into kout, one launch.
 int enqueue_fused(const Plan& plan, const float4* y0, const float4* kbuf, size_t kstride, const float* e,
                   const float* W0, const float* W3, int n, int P, int stage, int reverse, const float* gate,

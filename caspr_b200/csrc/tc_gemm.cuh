@@ -214,7 +214,7 @@ gemm_fp16x3_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
     tc::prefetch_tmap(&tm_w_hi);
     tc::prefetch_tmap(&tm_w_lo);
     for (int s = 0; s < kPairStages; ++s) {
-      tc::mbar_init(&full[s], 2);            // leader's arrive.expect_tx + the peer producer's remote arrive
+      tc::mbar_init(&full[s], 1);            // the leader's arrive.expect_tx; the peer only contributes bytes
       tc::mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -244,8 +244,7 @@ gemm_fp16x3_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
           tc::mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sb = smem + stage * kPairStageBytes;
           const uint32_t lead_full = tc::mapa_shared(&full[stage], 0);
-          if (rank == 0) tc::mbar_arrive_expect_tx(&full[stage], 2 * kPairStageBytes);
-          else tc::mbar_arrive_cluster(lead_full);
+          if (rank == 0) tc::mbar_arrive_expect_tx(&full[stage], 2 * kPairStageBytes);   // bytes of BOTH CTAs
           tc::tma_load_2d_pair(sb, &tm_a_hi, lead_full, (kc0 + kc) * kBK, m_tile * kBM);
           tc::tma_load_2d_pair(sb + kATile, &tm_a_lo, lead_full, (kc0 + kc) * kBK, m_tile * kBM);
           tc::tma_load_2d_pair(sb + 2 * kATile, &tm_w_hi, lead_full, (kc0 + kc) * kBK,

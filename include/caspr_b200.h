@@ -396,6 +396,10 @@ size_t caspr_emd_workspace_bytes(int B, int n, int m);
 int caspr_emd(const float* xyz1, const float* xyz2, int B, int n, int m, float* cost, void* workspace,
               size_t workspace_bytes, void* stream);
 
+/* Profiling aid for the fused CNF evaluation kernel (CASPR_CNF_FUSED_DEBUG=1): per-CTA cycle counters of its TMA
+ * producer and MMA threads for the last launch, 8 counters per CTA (see csrc/cnf.cu); synchronises the device. */
+int caspr_cnf_fused_debug_read(long long* out, int count);
+
 /* Correspondence-RANSAC rigid pose (reference utils/evaluations.py:360-380: open3d
  * registration_ransac_based_on_correspondence with identity correspondences, ransac_n = 4, threshold 0.015,
  * RANSACConvergenceCriteria(50000, 5000), TransformationEstimationPointToPoint(False)).  open3d is absent from the
