@@ -74,7 +74,7 @@ SIGNATURES = {
     'caspr_linear_tc_prepare_weights': (c_int, [_P, c_int, c_int, c_int, _P, c_size_t, _P]),
     'caspr_gn_table': (c_int, [_P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P]),
     'caspr_linear_tc': (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P,
-                                POINTER(GnFold), POINTER(GnStats), _P, c_size_t, _P]),
+                                POINTER(GnFold), POINTER(GnStats), c_int, _P, c_size_t, _P]),
     'caspr_groupnorm': (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_float, c_int, c_int, _P,
                                 c_int, _P, c_int, _P]),
     'caspr_augment_xyz': (c_int, [_P, c_int, _P, _P]),

@@ -773,7 +773,7 @@ int enqueue_aug_eval(const AdjWorkspace& w, const caspr_cnf_weights* cw, const f
   // (2n x H) . W^T on the tcgen05 fp16x3 GEMM: rows [0,n) = activations, rows [n,2n) = tangents
   auto tc_product = [&](const float* X, int widx, float* Y) {
     return caspr_linear_tc(X, H, nullptr, H, nullptr, Y, H, 2 * n, H, H, CASPR_ACT_NONE, CASPR_ACT_NONE, w.prep[widx],
-                           nullptr, nullptr, w.tc_ws, w.tc_ws_bytes, s);
+                           nullptr, nullptr, 0, w.tc_ws, w.tc_ws_bytes, s);
   };
   if (tc) {
     int rc = tc_product(b.Ha, 0, w.A1);

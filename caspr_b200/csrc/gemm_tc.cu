@@ -208,6 +208,7 @@ void launch_split_rows(const float* x, int ld, long long rows, int cols, long lo
 
 struct LinearEpilogue {
   const float* bias;
+  int bias_rps;           // 0: one bias vector; > 0: bias is (samples, cout), row r uses bias row r / bias_rps
   const float* x_inv;     // per-row 1/scale of X
   const float* w_inv;     // per-output-channel 1/scale of W
   float* Y;
@@ -229,6 +230,8 @@ struct LinearEpilogue {
     row = (long long)m_tile * kBM + q * 32 + lane;
     col0 = n_tile * kBN;
     inv = x_inv[row];       // planes are padded to whole tiles, so the index is always valid
+    bias_row = bias;
+    if (bias && bias_rps > 0) bias_row = bias + ((row < rows ? row : rows - 1) / bias_rps) * (long long)cout;
     if (stats) {
       const long long warp_row = row - lane;
       st_live = warp_row < rows;
@@ -247,7 +250,7 @@ struct LinearEpilogue {
     if (full) {
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) {
-        const float4 b4 = bias ? *reinterpret_cast<const float4*>(bias + c + j4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 b4 = bias ? *reinterpret_cast<const float4*>(bias_row + c + j4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 w4 = *reinterpret_cast<const float4*>(w_inv + c + j4 * 4);
         v[4 * j4 + 0] = fmaf(__uint_as_float(r[4 * j4 + 0]), inv * w4.x, b4.x);
         v[4 * j4 + 1] = fmaf(__uint_as_float(r[4 * j4 + 1]), inv * w4.y, b4.y);
@@ -257,7 +260,7 @@ struct LinearEpilogue {
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        v[j] = c + j < cout ? fmaf(__uint_as_float(r[j]), inv * w_inv[c + j], bias ? bias[c + j] : 0.f) : 0.f;
+        v[j] = c + j < cout ? fmaf(__uint_as_float(r[j]), inv * w_inv[c + j], bias ? bias_row[c + j] : 0.f) : 0.f;
     }
     if (stats && st_live) {
       // running (sum, sum of squares) of the current channel group; columns are the same in every lane, so the
@@ -287,6 +290,7 @@ struct LinearEpilogue {
         if (c + j < cout) y[j] = act_apply(v[j], act_out);
     }
   }
+  const float* bias_row;
   // per-thread state of the running group
   double* st_row;
   float st_s, st_q;
@@ -614,9 +618,10 @@ extern "C" int caspr_linear_tc_prepare_weights(const float* W, int ldw, int Cin,
 extern "C" int caspr_linear_tc(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y,
                                int ldy, int rows, int Cin, int Cout, int act_in, int act_out,
                                const void* prepared_weights, const caspr_gn_fold* in_norm,
-                               const caspr_gn_stats* out_stats, void* workspace, size_t workspace_bytes,
-                               void* stream) {
+                               const caspr_gn_stats* out_stats, int bias_rows_per_sample, void* workspace,
+                               size_t workspace_bytes, void* stream) {
   CASPR_REQUIRE(X && (W || prepared_weights) && Y && workspace && rows > 0 && Cin > 0 && Cout > 0);
+  CASPR_REQUIRE(bias_rows_per_sample >= 0 && (bias_rows_per_sample == 0 || (bias && Cout % 4 == 0)));
   if (in_norm)
     CASPR_REQUIRE(in_norm->table && in_norm->rows_per_sample > 0);
   if (out_stats)
@@ -669,7 +674,7 @@ extern "C" int caspr_linear_tc(const float* X, int ldx, const float* W, int ldw,
       cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
     return CASPR_ELAUNCH;
   LinearEpilogue epi{};
-  epi.bias = bias; epi.x_inv = xinv; epi.w_inv = winv; epi.Y = Y; epi.ldy = ldy; epi.rows = rows; epi.cout = Cout;
+  epi.bias = bias; epi.bias_rps = bias_rows_per_sample; epi.x_inv = xinv; epi.w_inv = winv; epi.Y = Y; epi.ldy = ldy; epi.rows = rows; epi.cout = Cout;
   epi.act_out = act_out;
   if (out_stats) {
     epi.stats = out_stats->stats; epi.st_rows_per_sample = out_stats->rows_per_sample;

@@ -102,10 +102,18 @@ class TPointNet2(nn.Module):
         R = B * T * N
         x4 = x.view(R, 4)
         L, G, Pf = self.local_feat_size, self.global_feat_size, self.space_time_pt_feat
-        feat = torch.empty(R, L + G + Pf, dtype=torch.float32, device=x.device)
+        # The head's first layer sees [local L | global max G (the SAME vector for every point of a sequence) |
+        # pointfeat Pf] (tpointnet2.py:96, pointnet.py:44-46).  The G constant channels contribute one vector per
+        # sequence, W[:, L:L+G] . gmax_b: it is computed once per sequence and enters the GEMM as a per-sequence bias,
+        # so the GEMM runs over K = L + Pf = 576 instead of 1600 and the repeated global feature never exists.
+        split_head = ops.tc_eligible(R, L + Pf, self.latent_feat_size) and (T * N) % 32 == 0
+        width = L + Pf if split_head else L + G + Pf
+        feat = torch.empty(R, width, dtype=torch.float32, device=x.device)
+        pf_off = L if split_head else L + G
         # global spatio-temporal PointNet on (B, T*N) points (tpointnet2.py:75-76)
-        gmax, _ = self.global_extract.forward_rows(x4, B, T * N, pointfeat_out=feat[:, L + G:])
-        ops.broadcast_rows(gmax, T * N, feat[:, L:L + G])
+        gmax, _ = self.global_extract.forward_rows(x4, B, T * N, pointfeat_out=feat[:, pf_off:pf_off + Pf])
+        if not split_head:
+            ops.broadcast_rows(gmax, T * N, feat[:, L:L + G])
         # per-frame PointNet++ (tpointnet2.py:79-93)
         local_in = self._local_input(x4)
         trace = None
@@ -115,8 +123,20 @@ class TPointNet2(nn.Module):
             trace.setdefault('ball_idx', [])
         self.local_extract.forward_rows(local_in.view(B * T, N, -1), out=feat[:, :L], trace=trace)
         # head (tpointnet2.py:99-113)
-        h2, st2 = ops.conv_gn_relu_conv(feat, self.conv1, self.bn1, self.conv2, B, T * N, 16,
-                                        out=feat if self.latent_feat_size == feat.shape[1] else None, stats_b=True)
+        if split_head:
+            w1 = self.conv1.weight
+            w_pts = ops.derived_weight(w1, 'head_points', lambda w: torch.cat([w[:, :L, 0], w[:, L + G:, 0]], dim=1))
+            w_glb = ops.derived_weight(w1, 'head_global', lambda w: w[:, L:L + G, 0])
+            seq_bias = ops.linear(gmax, w_glb, self.conv1.bias, engine='simt')                 # (B, 1600)
+            h1, st1 = ops.linear(feat, w_pts, seq_bias, engine='tc', out_stats=(B, T * N, 16),
+                                 bias_rows_per_sample=T * N, weight_key=w1)
+            pn = ops.PendingNorm(st1, B, T * N, 16, self.latent_feat_size, self.bn1.weight, self.bn1.bias, relu=True,
+                                 eps=self.bn1.eps)
+            h2, st2 = ops.linear(h1, self.conv2.weight, self.conv2.bias, out=h1, engine='tc', in_norm=pn,
+                                 out_stats=(B, T * N, 16))
+        else:
+            h2, st2 = ops.conv_gn_relu_conv(feat, self.conv1, self.bn1, self.conv2, B, T * N, 16,
+                                            out=feat if self.latent_feat_size == feat.shape[1] else None, stats_b=True)
         z0 = torch.empty(B, self.latent_feat_size, dtype=torch.float32, device=x.device)
         ops.groupnorm(h2, B, T * N, 16, self.bn2.weight, self.bn2.bias, relu=False, write_back=self.regress_tnocs,
                       maxout=z0, stats=st2)

@@ -143,14 +143,19 @@ def _aligned_bytes(nbytes, device):
     return buf, (buf.data_ptr() + 1023) // 1024 * 1024
 
 
-def _prepared_weights(weight, w2d):
+def _prepared_weights(weight, w2d, owner=None):
     """fp16 hi/lo planes of `weight`, cached per tensor OBJECT (weak reference: recycled storage addresses of
-    a freed model never alias), storage pointer and in-place version counter."""
+    a freed model never alias), storage pointer and in-place version counter.  `owner`: the parameter a derived
+    matrix (e.g. a column subset) was built from; its version then invalidates the planes."""
+    if owner is not None:
+        version_of = owner
+    else:
+        version_of = weight
     key = id(weight)
     hit = _WEIGHT_PLANES.get(key)
     if hit is not None:
         ref, ptr, version, buf, planes_ptr = hit
-        if ref() is weight and ptr == w2d.data_ptr() and version == weight._version:
+        if ref() is weight and ptr == w2d.data_ptr() and version == version_of._version:
             return planes_ptr
     cout, cin = w2d.shape
     nbytes = lib.caspr_linear_tc_weight_bytes(cin, cout)
@@ -159,7 +164,7 @@ def _prepared_weights(weight, w2d):
     check(lib.caspr_linear_tc_prepare_weights(_p(w2d), cin, cin, cout, ctypes.c_void_p(planes_ptr), nbytes, _stream()),
           'caspr_linear_tc_prepare_weights')
     ref = weakref.ref(weight, lambda _r, k=key: _WEIGHT_PLANES.pop(k, None))
-    _WEIGHT_PLANES[key] = (ref, w2d.data_ptr(), weight._version, buf, planes_ptr)
+    _WEIGHT_PLANES[key] = (ref, w2d.data_ptr(), version_of._version, buf, planes_ptr)
     return planes_ptr
 
 
@@ -182,6 +187,24 @@ class PendingNorm(object):
                                      float(self.eps), _p(self.gamma), _p(self.beta), _p(self._table), _stream()),
                   'caspr_gn_table')
         return self._table
+
+
+_DERIVED = {}
+
+
+def derived_weight(param, tag, fn):
+    """A matrix derived from `param` (column subsets of the head's first layer), rebuilt when the parameter's storage
+    or in-place version changes; cached per parameter object."""
+    key = (id(param), tag)
+    hit = _DERIVED.get(key)
+    if hit is not None:
+        ref, ptr, version, value = hit
+        if ref() is param and ptr == param.data_ptr() and version == param._version:
+            return value
+    value = fn(param.detach()).contiguous()
+    ref = weakref.ref(param, lambda _r, k=key: _DERIVED.pop(k, None))
+    _DERIVED[key] = (ref, param.data_ptr(), param._version, value)
+    return value
 
 
 def tc_eligible(rows, cin, cout):
@@ -207,13 +230,15 @@ def conv_gn_relu_conv(x, conv_a, gn_a, conv_b, samples, rows_per_sample, groups,
 
 
 def linear(x, weight, bias=None, out=None, act_in=ACT_NONE, act_out=ACT_NONE, engine='auto', in_norm=None,
-           out_stats=None):
+           out_stats=None, bias_rows_per_sample=0, weight_key=None):
     """1x1 Conv1d / Linear on rows: y = act_out(act_in(x) @ W^T + b).
 
     x (rows, Cin) view; weight (Cout, Cin) or Conv1d-shaped (Cout, Cin, 1); out optional (rows, Cout) view.
     engine: 'auto' (tensor cores for large layers), 'tc' or 'simt'.
     Tensor-core engine only: in_norm = PendingNorm of x (normalise while splitting the operand);
-    out_stats = (samples, rows_per_sample, groups): also return the fp64 GroupNorm statistics of y."""
+    out_stats = (samples, rows_per_sample, groups): also return the fp64 GroupNorm statistics of y;
+    bias_rows_per_sample > 0: `bias` is (rows / bias_rows_per_sample, Cout), one bias row per sample;
+    weight_key: the parameter `weight` was derived from (its version keys the cache of split planes)."""
     x, ldx = _rows2d(x, 'x')
     w = weight.reshape(weight.shape[0], weight.shape[1])
     _f32(w, 'weight')
@@ -229,8 +254,8 @@ def linear(x, weight, bias=None, out=None, act_in=ACT_NONE, act_out=ACT_NONE, en
         engine = LINEAR_ENGINE if (LINEAR_ENGINE == 'simt' or cin >= 16) else 'simt'
     if engine == 'auto':
         engine = 'tc' if (rows >= TC_MIN_ROWS and cin >= TC_MIN_CIN and cout >= TC_MIN_COUT) else 'simt'
-    if engine != 'tc' and (in_norm is not None or out_stats is not None):
-        raise ValueError('GroupNorm folding is implemented by the tensor-core linear only')
+    if engine != 'tc' and (in_norm is not None or out_stats is not None or bias_rows_per_sample):
+        raise ValueError('GroupNorm folding / per-sample bias are implemented by the tensor-core linear only')
     if engine == 'tc':
         fold_s = stats_s = None
         stats_t = None
@@ -244,12 +269,12 @@ def linear(x, weight, bias=None, out=None, act_in=ACT_NONE, act_out=ACT_NONE, en
         ws, ws_ptr = _aligned_bytes(ws_bytes, x.device)
         # weights are split once per (storage, in-place version); CUDA graphs that captured a call are keyed
         # by the same versions (TPointNet2._param_key), so a weight update re-captures with fresh planes
-        prepared = _prepared_weights(weight, w)
+        prepared = _prepared_weights(weight, w, weight_key)
         _count('linear_tc')
         check(lib.caspr_linear_tc(_p(x), ldx, _p(w), cin, _p(bias), _p(out), ldy, rows, cin, cout, act_in, act_out,
                                   ctypes.c_void_p(prepared) if prepared else None,
                                   ctypes.byref(fold_s) if fold_s is not None else None,
-                                  ctypes.byref(stats_s) if stats_s is not None else None,
+                                  ctypes.byref(stats_s) if stats_s is not None else None, int(bias_rows_per_sample),
                                   ctypes.c_void_p(ws_ptr), ws_bytes, _stream()), 'caspr_linear_tc')
         return (out, stats_t) if out_stats is not None else out
     _count('linear')

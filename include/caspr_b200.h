@@ -160,7 +160,7 @@ int caspr_linear_tc_prepare_weights(const float* W, int ldw, int Cin, int Cout, 
 int caspr_linear_tc(const float* X, int ldx, const float* W, int ldw, const float* bias,
                     float* Y, int ldy, int rows, int Cin, int Cout, int act_in, int act_out,
                     const void* prepared_weights, const caspr_gn_fold* in_norm, const caspr_gn_stats* out_stats,
-                    void* workspace, size_t workspace_bytes, void* stream);
+                    int bias_rows_per_sample, void* workspace, size_t workspace_bytes, void* stream);
 
 /* GroupNorm over samples of `rows_per_sample` consecutive rows (torch.nn.GroupNorm(groups, C)
  * on (samples, C, rows_per_sample)), eps as given; optional ReLU; optional max over the rows
