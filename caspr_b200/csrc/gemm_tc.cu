@@ -241,54 +241,54 @@ struct LinearEpilogue {
       st_s = 0.f; st_q = 0.f;
     }
   }
+  // Code size matters here: the epilogue warps of a GEMM with a short k-loop are instruction-fetch bound if this body
+  // is large (the first version inlined the statistics flush 32 times: 8.7 k instructions, "no instruction" was the
+  // top stall reason and a 128 x 256 tile took 36 us).  One vector path (cout % 4 == 0 is required), statistics with
+  // at most one group boundary per chunk (channels per group >= 32 is required), activation outside the main loop.
   __device__ __forceinline__ void chunk(int chunk, uint32_t (&r)[32]) {
     const int c = col0 + chunk * 32;
     if (c >= cout) return;                              // warp-uniform
     const bool row_ok = row < rows;
-    const bool full = vec_ok && c + 32 <= cout;
     float v[32];
-    if (full) {
 #pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        const float4 b4 = bias ? *reinterpret_cast<const float4*>(bias_row + c + j4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 w4 = *reinterpret_cast<const float4*>(w_inv + c + j4 * 4);
-        v[4 * j4 + 0] = fmaf(__uint_as_float(r[4 * j4 + 0]), inv * w4.x, b4.x);
-        v[4 * j4 + 1] = fmaf(__uint_as_float(r[4 * j4 + 1]), inv * w4.y, b4.y);
-        v[4 * j4 + 2] = fmaf(__uint_as_float(r[4 * j4 + 2]), inv * w4.z, b4.z);
-        v[4 * j4 + 3] = fmaf(__uint_as_float(r[4 * j4 + 3]), inv * w4.w, b4.w);
+    for (int j4 = 0; j4 < 8; ++j4) {
+      const bool ok = c + 4 * j4 < cout;                // warp-uniform; cout % 4 == 0
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) {
+        w4 = *reinterpret_cast<const float4*>(w_inv + c + j4 * 4);
+        if (bias) b4 = *reinterpret_cast<const float4*>(bias_row + c + j4 * 4);
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        v[j] = c + j < cout ? fmaf(__uint_as_float(r[j]), inv * w_inv[c + j], bias ? bias_row[c + j] : 0.f) : 0.f;
+      v[4 * j4 + 0] = fmaf(__uint_as_float(r[4 * j4 + 0]), inv * w4.x, b4.x);
+      v[4 * j4 + 1] = fmaf(__uint_as_float(r[4 * j4 + 1]), inv * w4.y, b4.y);
+      v[4 * j4 + 2] = fmaf(__uint_as_float(r[4 * j4 + 2]), inv * w4.z, b4.z);
+      v[4 * j4 + 3] = fmaf(__uint_as_float(r[4 * j4 + 3]), inv * w4.w, b4.w);
     }
     if (stats && st_live) {
-      // running (sum, sum of squares) of the current channel group; columns are the same in every lane, so the
-      // group boundaries are warp-uniform and a finished group is reduced over the warp's 32 rows once
+      // running (sum, sum of squares) of the current channel group; a group has >= 32 channels, so at most one
+      // boundary falls into this chunk: columns before it extend the running group, the others start the next one.
+      // Padded columns (>= cout) hold 0 (zero weight rows, w_inv = 0) and padded rows are masked.
+      float s1 = 0.f, q1 = 0.f;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        if (c + j >= st_next) {
-          flush_stats();
-          st_s = 0.f; st_q = 0.f; ++st_g; st_next += st_cpg;
-        }
-        if (row_ok && c + j < cout) {
-          st_s += v[j];
-          st_q = fmaf(v[j], v[j], st_q);
-        }
+        const float x = row_ok ? v[j] : 0.f;
+        if (c + j >= st_next) { s1 += x; q1 = fmaf(x, x, q1); }
+        else { st_s += x; st_q = fmaf(x, x, st_q); }
+      }
+      if (c + 32 >= st_next) {                          // warp-uniform: the running group ends inside this chunk
+        flush_stats();
+        st_s = s1; st_q = q1; ++st_g; st_next += st_cpg;
       }
     }
     if (!row_ok) return;
-    float* y = Y + row * ldy + c;
-    if (full) {
+    if (act_out == CASPR_ACT_RELU) {
 #pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4)
-        reinterpret_cast<float4*>(y)[j4] = make_float4(act_apply(v[4 * j4], act_out), act_apply(v[4 * j4 + 1], act_out),
-                                                       act_apply(v[4 * j4 + 2], act_out), act_apply(v[4 * j4 + 3], act_out));
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (c + j < cout) y[j] = act_apply(v[j], act_out);
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
     }
+    float* y = Y + row * ldy + c;
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4)
+      if (c + 4 * j4 < cout)
+        reinterpret_cast<float4*>(y)[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
   }
   const float* bias_row;
   // per-thread state of the running group
@@ -621,7 +621,11 @@ extern "C" int caspr_linear_tc(const float* X, int ldx, const float* W, int ldw,
                                const caspr_gn_stats* out_stats, int bias_rows_per_sample, void* workspace,
                                size_t workspace_bytes, void* stream) {
   CASPR_REQUIRE(X && (W || prepared_weights) && Y && workspace && rows > 0 && Cin > 0 && Cout > 0);
-  CASPR_REQUIRE(bias_rows_per_sample >= 0 && (bias_rows_per_sample == 0 || (bias && Cout % 4 == 0)));
+  CASPR_REQUIRE(bias_rows_per_sample >= 0 && (bias_rows_per_sample == 0 || bias));
+  // the epilogue stores float4 pieces and keeps one running GroupNorm group per chunk of 32 columns
+  CASPR_REQUIRE(Cout % 4 == 0 && ldy % 4 == 0 && ((uintptr_t)Y & 15) == 0 && (!bias || ((uintptr_t)bias & 15) == 0));
+  if (out_stats) CASPR_REQUIRE(Cout / out_stats->groups >= 32);
+  CASPR_REQUIRE(act_out == CASPR_ACT_NONE || act_out == CASPR_ACT_RELU);     // sigmoid outputs: caspr_linear
   if (in_norm)
     CASPR_REQUIRE(in_norm->table && in_norm->rows_per_sample > 0);
   if (out_stats)

@@ -5,6 +5,8 @@ sub-module names (``local_extract``, ``global_extract``, ``conv1..3``, ``bn1..2`
 parameter shapes as the reference; all math in libcaspr_b200.so on channels-last rows, with
 the [local | global-max | pointfeat] concat of tpointnet2.py:96 assembled in place.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -106,7 +108,8 @@ class TPointNet2(nn.Module):
         # pointfeat Pf] (tpointnet2.py:96, pointnet.py:44-46).  The G constant channels contribute one vector per
         # sequence, W[:, L:L+G] . gmax_b: it is computed once per sequence and enters the GEMM as a per-sequence bias,
         # so the GEMM runs over K = L + Pf = 576 instead of 1600 and the repeated global feature never exists.
-        split_head = ops.tc_eligible(R, L + Pf, self.latent_feat_size) and (T * N) % 32 == 0
+        split_head = (ops.tc_eligible(R, L + Pf, self.latent_feat_size) and (T * N) % 32 == 0 and
+                      os.environ.get('CASPR_HEAD_SPLIT', '1') != '0')
         width = L + Pf if split_head else L + G + Pf
         feat = torch.empty(R, width, dtype=torch.float32, device=x.device)
         pf_off = L if split_head else L + G

@@ -208,7 +208,8 @@ def derived_weight(param, tag, fn):
 
 
 def tc_eligible(rows, cin, cout):
-    return LINEAR_ENGINE != 'simt' and rows >= TC_MIN_ROWS and cin >= TC_MIN_CIN and cout >= TC_MIN_COUT
+    return (LINEAR_ENGINE != 'simt' and rows >= TC_MIN_ROWS and cin >= TC_MIN_CIN and cout >= TC_MIN_COUT and
+            cout % 4 == 0)
 
 
 def conv_gn_relu_conv(x, conv_a, gn_a, conv_b, samples, rows_per_sample, groups, out=None, stats_b=False):
@@ -217,7 +218,9 @@ def conv_gn_relu_conv(x, conv_a, gn_a, conv_b, samples, rows_per_sample, groups,
     normalised intermediate never exists in memory.  Returns y (and y's statistics if stats_b)."""
     rows, cin = x.shape
     ca, cb = conv_a.weight.shape[0], conv_b.weight.shape[0]
-    fold = tc_eligible(rows, cin, ca) and tc_eligible(rows, ca, cb) and rows_per_sample % 32 == 0
+    # the GEMM epilogue keeps one running GroupNorm group per 32-column chunk: groups of >= 32 channels only
+    fold = (tc_eligible(rows, cin, ca) and tc_eligible(rows, ca, cb) and rows_per_sample % 32 == 0 and
+            ca // groups >= 32 and (not stats_b or cb // groups >= 32))
     if fold:
         h, st = linear(x, conv_a.weight, conv_a.bias, engine='tc', out_stats=(samples, rows_per_sample, groups))
         pn = PendingNorm(st, samples, rows_per_sample, groups, ca, gn_a.weight, gn_a.bias, relu=True, eps=gn_a.eps)
@@ -254,6 +257,11 @@ def linear(x, weight, bias=None, out=None, act_in=ACT_NONE, act_out=ACT_NONE, en
         engine = LINEAR_ENGINE if (LINEAR_ENGINE == 'simt' or cin >= 16) else 'simt'
     if engine == 'auto':
         engine = 'tc' if (rows >= TC_MIN_ROWS and cin >= TC_MIN_CIN and cout >= TC_MIN_COUT) else 'simt'
+    if engine == 'tc' and (cout % 4 or ldy % 4 or out.data_ptr() % 16 or (bias is not None and bias.data_ptr() % 16)
+                           or act_out == ACT_SIGMOID):
+        if in_norm is not None or out_stats is not None or bias_rows_per_sample:
+            raise ValueError('tensor-core linear needs Cout % 4 == 0 and 16-byte aligned output / bias rows')
+        engine = 'simt'
     if engine != 'tc' and (in_norm is not None or out_stats is not None or bias_rows_per_sample):
         raise ValueError('GroupNorm folding / per-sample bias are implemented by the tensor-core linear only')
     if engine == 'tc':
