@@ -158,7 +158,9 @@ def test_conv_gn_relu_conv_fold_matches_unfused(ops):
     """GroupNorm folded around the tensor-core GEMMs (statistics in the epilogue, normalisation in the next
     operand split) against fp64 torch and against the unfused kernel sequence."""
     g = torch.Generator().manual_seed(4)
-    samples, rps, cin, ca, cb = 3, 1024, 96, 128, 80
+    # groups of 32 and 40 channels: the epilogue keeps one running group per 32-column chunk (>= 32 channels per group),
+    # 40 puts the group boundaries at every possible position inside a chunk
+    samples, rps, cin, ca, cb = 3, 1024, 96, 512, 640
     x = torch.randn(samples * rps, cin, generator=g)
     conv_a = torch.nn.Conv1d(cin, ca, 1)
     conv_b = torch.nn.Conv1d(ca, cb, 1)
@@ -183,6 +185,13 @@ def test_conv_gn_relu_conv_fold_matches_unfused(ops):
     finally:
         ops.LINEAR_ENGINE = old
     assert _rel(y, y2) < 1e-5
+    # groups of fewer than 32 channels are not folded (separate GroupNorm pass); same numbers
+    conv_c, gn_c = torch.nn.Conv1d(cin, 128, 1).to(DEV), torch.nn.GroupNorm(16, 128).to(DEV)
+    conv_d = torch.nn.Conv1d(128, 80, 1).to(DEV)
+    y3, st3 = ops.conv_gn_relu_conv(x.to(DEV), conv_c, gn_c, conv_d, samples, rps, 16, stats_b=True)
+    assert st3 is None
+    ref3 = conv_d.double()(torch.relu(gn_c.double()(conv_c.double()(ref_in.to(DEV))))).transpose(1, 2).reshape(-1, 80)
+    assert _rel(y3, ref3) < 1e-5
 
 
 def test_linear_strided_views(ops):

@@ -88,8 +88,8 @@ def test_ransac_protocol_size_and_error_metrics(lib_built):
     gen = torch.Generator(device='cuda').manual_seed(6)
     res = metrics.ransac_camera_pose(pred_tnocs, pcl, generator=gen)
     assert float(res['fitness'].min()) > 0.6
-    Rg_t = torch.from_numpy(Rg).float().view(B, T, 3, 3).cuda()
-    tg_t = torch.from_numpy(tg).float().view(B, T, 3).cuda()
+    Rg_t = torch.from_numpy(Rg).view(B, T, 3, 3).cuda()          # float64, as the reference's pose data
+    tg_t = torch.from_numpy(tg).view(B, T, 3).cuda()
     err = metrics.ransac_pose_errors(res['R'], res['t'], Rg_t, tg_t, pred_tnocs, pcl)
     assert float(err['rot'].max()) < 1.0 and float(err['trans'].max()) < 0.01
     for b in range(B):
