@@ -579,6 +579,283 @@ extern "C" int caspr_linear_wgrad_tc(const float* dY, int lddy, const float* X, 
 }
 
 namespace {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-ball MLP of a set-abstraction scale on the tensor cores (pointnet2.py:649-708 as used by SA levels 3-5):
+//   [Conv1d(k=1) -> GroupNorm(16) over each BALL of ns rows -> ReLU] x 2 -> Conv1d -> GroupNorm -> max over the ball.
+// A 128-row accumulator tile holds whole balls (ns = 16 or 32 consecutive rows) and a GroupNorm group is CPG = C/16
+// consecutive channels, so the epilogue of each GEMM normalises in registers (two passes over the thread's values,
+// ball reductions by warp shuffles) and emits the NEXT layer's fp16 hi / lo operand planes directly (fixed power-of-
+// two scale: normalised activations are bounded) or, for the last layer, the max over the ball.  Replaces, per layer,
+// the sequence  GEMM (fp32 rows out) -> per-ball GroupNorm kernel (read + write) -> operand split (read + write).
+constexpr float kBallPlaneScale = 512.f;      // |GroupNorm output| <= |gamma| sqrt(ns*CPG) + |beta| << 65504 / 512
+
+template <int CPG, bool LAST>
+struct BallNormEpilogue {
+  static constexpr bool kReadsTmem = true;
+  static constexpr int kChunk = (32 / CPG) * CPG;               // 32, or 24 for groups of 6 channels (C = 96)
+  static constexpr int kGroups = kChunk / CPG;
+  const float* bias;
+  const float* x_inv;      // per-row 1/scale of the A planes, or nullptr: inv_const for every row
+  float inv_const;
+  const float* w_inv;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int ns;
+  long long rows;
+  int cout;
+  __half* out_hi;          // !LAST: operand planes of the next layer [rows_pad][ld_out]
+  __half* out_lo;
+  int ld_out;
+  float* maxout;           // LAST: (balls, cout) with row stride ld_max
+  int ld_max;
+  int* range_flag;
+  // per-thread tile state
+  long long row;
+  int col0, lane;
+  float inv;
+
+  __device__ __forceinline__ void setup(uint8_t*, const CUtensorMap*, const CUtensorMap*, int) {}
+  __device__ __forceinline__ void tile_begin(int m_tile, int n_tile, int q, int ln) {
+    row = (long long)m_tile * kBM + q * 32 + ln;
+    col0 = n_tile * kBN;
+    lane = ln;
+    inv = x_inv ? x_inv[row] : inv_const;
+  }
+  __device__ __forceinline__ float ball_sum(float v) const {
+    for (int off = ns >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+  }
+  __device__ __forceinline__ void tile(uint32_t taddr) {
+    const bool row_ok = row < rows;                             // uniform over a ball
+    const int ncols = min(kBN, cout - col0);
+    const float inv_n = 1.f / (float)(ns * CPG);
+    float range_max = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < ncols; c += kChunk) {
+      uint32_t r[kChunk];
+#pragma unroll
+      for (int i = 0; i < kChunk / 8; ++i) tc::tmem_ld_32x8(taddr + c + 8 * i, r + 8 * i);
+      tc::tmem_ld_wait();
+      float x[kChunk];
+#pragma unroll
+      for (int j4 = 0; j4 < kChunk / 4; ++j4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(w_inv + col0 + c + j4 * 4);
+        const float4 b4 = *reinterpret_cast<const float4*>(bias + col0 + c + j4 * 4);
+        x[4 * j4 + 0] = fmaf(__uint_as_float(r[4 * j4 + 0]), inv * w4.x, b4.x);
+        x[4 * j4 + 1] = fmaf(__uint_as_float(r[4 * j4 + 1]), inv * w4.y, b4.y);
+        x[4 * j4 + 2] = fmaf(__uint_as_float(r[4 * j4 + 2]), inv * w4.z, b4.z);
+        x[4 * j4 + 3] = fmaf(__uint_as_float(r[4 * j4 + 3]), inv * w4.w, b4.w);
+      }
+      // GroupNorm per (ball, group): mean, then centred second moment (two passes over registers)
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < CPG; ++k) s += x[g * CPG + k];
+        const float mean = ball_sum(s) * inv_n;
+        float qv = 0.f;
+#pragma unroll
+        for (int k = 0; k < CPG; ++k) {
+          const float d = x[g * CPG + k] - mean;
+          x[g * CPG + k] = d;
+          qv = fmaf(d, d, qv);
+        }
+        const float rstd = 1.f / sqrtf(ball_sum(qv) * inv_n + eps);
+#pragma unroll
+        for (int k = 0; k < CPG; ++k) x[g * CPG + k] *= rstd;
+      }
+#pragma unroll
+      for (int j4 = 0; j4 < kChunk / 4; ++j4) {
+        const float4 g4 = *reinterpret_cast<const float4*>(gamma + col0 + c + j4 * 4);
+        const float4 e4 = *reinterpret_cast<const float4*>(beta + col0 + c + j4 * 4);
+        x[4 * j4 + 0] = fmaf(x[4 * j4 + 0], g4.x, e4.x);
+        x[4 * j4 + 1] = fmaf(x[4 * j4 + 1], g4.y, e4.y);
+        x[4 * j4 + 2] = fmaf(x[4 * j4 + 2], g4.z, e4.z);
+        x[4 * j4 + 3] = fmaf(x[4 * j4 + 3], g4.w, e4.w);
+      }
+      if (LAST) {
+        // max over the ball's rows (no ReLU before it, pointnet2.py:693-698): integer warp reductions on an
+        // order-preserving encoding; lane l of the ball keeps columns l (+ 16 when ns = 16)
+        const unsigned mask = ns == 32 ? 0xffffffffu : (lane < 16 ? 0x0000ffffu : 0xffff0000u);
+        const int l = lane & (ns - 1);
+        float keep0 = 0.f, keep1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j) {
+          int e = __float_as_int(x[j]);
+          e ^= (e >> 31) & 0x7fffffff;
+          e = __reduce_max_sync(mask, e);
+          e ^= (e >> 31) & 0x7fffffff;
+          const float m = __int_as_float(e);
+          if (j == l) keep0 = m;
+          if (ns == 16 && j == l + 16) keep1 = m;
+        }
+        if (row_ok) {
+          float* o = maxout + (row / ns) * ld_max + col0 + c;
+          if (ns == 32) {
+            if (l < kChunk) o[l] = keep0;
+          } else {
+            o[l] = keep0;
+            if (l + 16 < kChunk) o[l + 16] = keep1;
+          }
+        }
+      } else {
+        if (row_ok) {
+          __half* ph = out_hi + row * ld_out + col0 + c;
+          __half* pl = out_lo + row * ld_out + col0 + c;
+#pragma unroll
+          for (int j8 = 0; j8 < kChunk / 8; ++j8) {
+            uint32_t h[4], lo4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float a = fmaxf(x[8 * j8 + 2 * u], 0.f) * kBallPlaneScale;
+              const float b = fmaxf(x[8 * j8 + 2 * u + 1], 0.f) * kBallPlaneScale;
+              range_max = fmaxf(range_max, fmaxf(a, b));
+              tcg::split2(a, b, h[u], lo4[u]);
+            }
+            *reinterpret_cast<uint4*>(ph + 8 * j8) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(pl + 8 * j8) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
+          }
+        }
+      }
+    }
+    if (!LAST && row_ok && col0 + kBN >= cout) {
+      // zero the K padding of the next layer's operand (columns cout .. ld_out)
+      for (int cc = cout; cc < ld_out; cc += 8) {
+        *reinterpret_cast<uint4*>(out_hi + row * ld_out + cc) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(out_lo + row * ld_out + cc) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    if (!LAST && range_max > 65504.f) atomicOr(range_flag, 1);
+  }
+  __device__ __forceinline__ void chunk(int, uint32_t (&)[32]) {}
+  __device__ __forceinline__ void finish() {}
+};
+
+struct SaMlpLayout {
+  long long rows_pad;
+  int kpad[3];
+  size_t off_xinv, off_hi[3], off_lo[3], off_flag, total;
+};
+SaMlpLayout sa_mlp_layout(long long rows, int cin, int c1, int c2) {
+  SaMlpLayout l;
+  l.rows_pad = (rows + kBM - 1) / kBM * kBM;
+  const int k[3] = {cin, c1, c2};
+  size_t p = 0;
+  auto take = [&](size_t bytes) { size_t r = p; p += align_up(bytes, 1024); return r; };
+  l.off_xinv = take((size_t)l.rows_pad * 4);
+  for (int i = 0; i < 3; ++i) {
+    l.kpad[i] = (k[i] + kBK - 1) / kBK * kBK;
+    l.off_hi[i] = take((size_t)l.rows_pad * l.kpad[i] * 2);
+    l.off_lo[i] = take((size_t)l.rows_pad * l.kpad[i] * 2);
+  }
+  l.off_flag = take(256);
+  l.total = p;
+  return l;
+}
+
+template <int CPG, bool LAST>
+int sa_mlp_layer(const __half* a_hi, const __half* a_lo, long long rows_pad, int k_pad, const float* x_inv, float inv_const,
+                 const void* prepared, int cin, int cout, const float* bias, const float* gamma, const float* beta,
+                 float eps, int ns, long long rows, __half* out_hi, __half* out_lo, int ld_out, float* maxout,
+                 int ld_max, int* range_flag, int num_sms, cudaStream_t s) {
+  const WeightLayout wl = make_weight_layout(cin, cout);
+  if (wl.k_pad != k_pad) return CASPR_EINVAL;
+  const char* wbase = (const char*)prepared;
+  CUtensorMap tm_ahi, tm_alo, tm_whi, tm_wlo;
+  bool ok = true;
+  ok &= caspr_make_tmap_f16(&tm_ahi, a_hi, (uint64_t)rows_pad, (uint64_t)k_pad, kBM);
+  ok &= caspr_make_tmap_f16(&tm_alo, a_lo, (uint64_t)rows_pad, (uint64_t)k_pad, kBM);
+  ok &= caspr_make_tmap_f16(&tm_whi, wbase + wl.off_whi, (uint64_t)wl.cout_pad, (uint64_t)k_pad, tcg::w_box_rows());
+  ok &= caspr_make_tmap_f16(&tm_wlo, wbase + wl.off_wlo, (uint64_t)wl.cout_pad, (uint64_t)k_pad, tcg::w_box_rows());
+  if (!ok) return CASPR_ELAUNCH;
+  BallNormEpilogue<CPG, LAST> epi{};
+  epi.bias = bias; epi.x_inv = x_inv; epi.inv_const = inv_const; epi.w_inv = (const float*)(wbase + wl.off_winv);
+  epi.gamma = gamma; epi.beta = beta; epi.eps = eps; epi.ns = ns; epi.rows = rows; epi.cout = cout;
+  epi.out_hi = out_hi; epi.out_lo = out_lo; epi.ld_out = ld_out; epi.maxout = maxout; epi.ld_max = ld_max;
+  epi.range_flag = range_flag;
+  CASPR_COUNT();
+  if (tcg::launch_gemm_pair(tm_ahi, tm_alo, tm_whi, tm_wlo, (int)(rows_pad / kBM), wl.cout_pad / kBN, k_pad / kBK, epi,
+                            num_sms, s) != cudaSuccess)
+    return CASPR_ELAUNCH;
+  return CASPR_OK;
+}
+
+template <bool LAST>
+int sa_mlp_layer_dispatch(int cout, const __half* a_hi, const __half* a_lo, long long rows_pad, int k_pad,
+                          const float* x_inv, float inv_const, const void* prepared, int cin, const float* bias,
+                          const float* gamma, const float* beta, float eps, int ns, long long rows, __half* out_hi,
+                          __half* out_lo, int ld_out, float* maxout, int ld_max, int* range_flag, int num_sms,
+                          cudaStream_t s) {
+#define CASPR_SA_LAYER(CPG)                                                                                          \
+  return sa_mlp_layer<CPG, LAST>(a_hi, a_lo, rows_pad, k_pad, x_inv, inv_const, prepared, cin, cout, bias, gamma, beta, \
+                                 eps, ns, rows, out_hi, out_lo, ld_out, maxout, ld_max, range_flag, num_sms, s)
+  switch (cout) {
+    case 64: CASPR_SA_LAYER(4);
+    case 96: CASPR_SA_LAYER(6);
+    case 128: CASPR_SA_LAYER(8);
+    case 256: CASPR_SA_LAYER(16);
+    case 512: CASPR_SA_LAYER(32);
+    default: return CASPR_EINVAL;
+  }
+#undef CASPR_SA_LAYER
+}
+
+}  // namespace
+
+extern "C" int caspr_sa_mlp_tc_supported(int ns, int Cin, int C1, int C2, int C3) {
+  auto okc = [](int c) { return c == 64 || c == 96 || c == 128 || c == 256 || c == 512; };
+  return (ns == 16 || ns == 32) && Cin >= 64 && okc(C1) && okc(C2) && okc(C3) && tcg::use_pair();
+}
+
+extern "C" size_t caspr_sa_mlp_tc_workspace_bytes(long long rows, int Cin, int C1, int C2) {
+  if (rows <= 0 || Cin <= 0 || C1 <= 0 || C2 <= 0) return 0;
+  return sa_mlp_layout(rows, Cin, C1, C2).total;
+}
+
+extern "C" int caspr_sa_mlp_tc(const float* X, int ldx, long long rows, int Cin, int ns,
+                               const void* prep1, const float* b1, const float* g1, const float* e1, int C1,
+                               const void* prep2, const float* b2, const float* g2, const float* e2, int C2,
+                               const void* prep3, const float* b3, const float* g3, const float* e3, int C3,
+                               float eps, float* maxout, int ld_max, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  CASPR_REQUIRE(X && prep1 && prep2 && prep3 && b1 && b2 && b3 && g1 && g2 && g3 && e1 && e2 && e3 && maxout && workspace);
+  CASPR_REQUIRE(rows > 0 && rows % ns == 0 && ldx >= Cin && ld_max >= C3);
+  CASPR_REQUIRE(caspr_sa_mlp_tc_supported(ns, Cin, C1, C2, C3));
+  CASPR_REQUIRE(((uintptr_t)workspace & 1023) == 0 && (((uintptr_t)prep1 | (uintptr_t)prep2 | (uintptr_t)prep3) & 1023) == 0);
+  const SaMlpLayout l = sa_mlp_layout(rows, Cin, C1, C2);
+  if (workspace_bytes < l.total) return CASPR_EWORKSPACE;
+  CASPR_REQUIRE(l.rows_pad / kBM < (1ll << 30));
+  cudaStream_t s = (cudaStream_t)stream;
+  char* base = (char*)workspace;
+  float* xinv = (float*)(base + l.off_xinv);
+  __half* hi[3];
+  __half* lo[3];
+  for (int i = 0; i < 3; ++i) { hi[i] = (__half*)(base + l.off_hi[i]); lo[i] = (__half*)(base + l.off_lo[i]); }
+  int* flag = (int*)(base + l.off_flag);
+  if (cudaMemsetAsync(flag, 0, sizeof(int), s) != cudaSuccess) return CASPR_ELAUNCH;
+  int dev = 0, num_sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return CASPR_ELAUNCH;
+  // operand planes of the grouped input rows (per-row power-of-two scale)
+  CASPR_COUNT(); launch_split_rows(X, ldx, rows, Cin, l.rows_pad, l.kpad[0], 0, hi[0], lo[0], xinv, NormFold(), 148 * 8, s);
+  CASPR_CHECK_LAUNCH();
+  int rc = sa_mlp_layer_dispatch<false>(C1, hi[0], lo[0], l.rows_pad, l.kpad[0], xinv, 0.f, prep1, Cin, b1, g1, e1, eps, ns,
+                                        rows, hi[1], lo[1], l.kpad[1], nullptr, 0, flag, num_sms, s);
+  if (rc) return rc;
+  rc = sa_mlp_layer_dispatch<false>(C2, hi[1], lo[1], l.rows_pad, l.kpad[1], nullptr, 1.f / kBallPlaneScale, prep2, C1, b2,
+                                    g2, e2, eps, ns, rows, hi[2], lo[2], l.kpad[2], nullptr, 0, flag, num_sms, s);
+  if (rc) return rc;
+  rc = sa_mlp_layer_dispatch<true>(C3, hi[2], lo[2], l.rows_pad, l.kpad[2], nullptr, 1.f / kBallPlaneScale, prep3, C2, b3,
+                                   g3, e3, eps, ns, rows, nullptr, nullptr, 0, maxout, ld_max, flag, num_sms, s);
+  if (rc) return rc;
+  CASPR_CHECK_LAUNCH();
+  return CASPR_OK;
+}
+
+namespace {
 }  // namespace
 
 extern "C" size_t caspr_linear_tc_workspace_bytes(int rows, int Cin, int Cout) {

@@ -25,6 +25,7 @@
 //   void finish();                                     // once, after the last tile
 #pragma once
 #include <stdlib.h>
+#include <type_traits>
 #include "tc_common.cuh"
 
 namespace tcg {
@@ -178,6 +179,13 @@ gemm_fp16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 // leaves room for a 3-deep ring.  Roles per CTA as above; only the leader's warp 1 issues MMAs; smem stages and
 // accumulators are released / published to both CTAs with multicast commits; the leader's `full` barrier collects
 // the TMA bytes of both CTAs; both CTAs' epilogue threads arrive on the leader's `tempty`.
+// Epilogue functors that define `static constexpr bool kReadsTmem = true` get `tile(taddr)` instead of eight
+// `chunk()` calls (pair kernel only): they choose their own column grouping (e.g. 24 columns = 4 GroupNorm groups of 6).
+template <class E, class = void>
+struct epilogue_reads_tmem : std::false_type {};
+template <class E>
+struct epilogue_reads_tmem<E, std::enable_if_t<E::kReadsTmem>> : std::true_type {};
+
 constexpr int kPairStages = 3;
 constexpr int kPairWTile = (kBN / 2) * kBK * 2;                      // 16 KB: this CTA's half of the W tile
 constexpr int kPairStageBytes = 2 * kATile + 2 * kPairWTile;        // 64 KB
@@ -305,12 +313,16 @@ gemm_fp16x3_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
       tc::fence_after_sync();
       if (valid) {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * kBN;
+        if constexpr (epilogue_reads_tmem<Epilogue>::value) {
+          epi.tile(taddr);                                        // the functor issues its own tcgen05.ld
+        } else {
 #pragma unroll 1
-        for (int chunk = 0; chunk < kBN / 32; ++chunk) {
-          uint32_t r[32];
-          tc::tmem_ld_32x32(taddr + chunk * 32, r);
-          tc::tmem_ld_wait();
-          epi.chunk(chunk, r);
+          for (int chunk = 0; chunk < kBN / 32; ++chunk) {
+            uint32_t r[32];
+            tc::tmem_ld_32x32(taddr + chunk * 32, r);
+            tc::tmem_ld_wait();
+            epi.chunk(chunk, r);
+          }
         }
       }
       tc::fence_before_sync();
@@ -369,6 +381,26 @@ inline cudaError_t launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo,
                                                                         m_tiles, n_tiles, k_chunks, skip_flag, epi,
                                                                         k_splits);
   }
+  return cudaGetLastError();
+}
+
+// pair kernel only (epilogues with kReadsTmem); returns cudaErrorNotSupported when CASPR_TC_PAIR=0
+template <class Epilogue>
+inline cudaError_t launch_gemm_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
+                                    const CUtensorMap& w_lo, int m_tiles, int n_tiles, int k_chunks, const Epilogue& epi,
+                                    int num_sms, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!use_pair()) return cudaErrorNotSupported;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_fp16x3_pair_kernel<Epilogue>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kPairSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  long long clusters = (long long)((m_tiles + 1) / 2) * n_tiles;
+  if (clusters > num_sms / 2) clusters = num_sms / 2;
+  gemm_fp16x3_pair_kernel<Epilogue><<<(int)(2 * clusters), kThreads, kPairSmemBytes, s>>>(
+      a_hi, a_lo, w_hi, w_lo, a_hi, a_lo, 0, m_tiles, n_tiles, k_chunks, nullptr, epi, 1);
   return cudaGetLastError();
 }
 

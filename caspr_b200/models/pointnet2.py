@@ -51,6 +51,10 @@ class PointNetFeatureExtractor(nn.Module):
                     ops.linear_gn_ball(h, conv.weight, conv.bias, gn.weight, gn.bias, ns, relu=False,
                                        want_rows=False, maxout=out)
             return out
+        widths = [c.weight.shape[0] for c in self.conv_layers]
+        if ops.sa_mlp_tc_supported(ns, rows.shape[1], widths, rows.shape[0]):
+            # SA levels 3-5: three tcgen05 GEMMs whose epilogues do the per-ball GroupNorm / ReLU / max
+            return ops.sa_mlp_tc(rows, ns, self.conv_layers, self.bn_layers, out)
         for i, (conv, gn) in enumerate(zip(self.conv_layers, self.bn_layers)):
             h = ops.linear(h, conv.weight, conv.bias)
             if i < last:

@@ -312,6 +312,36 @@ def linear_gn_ball(x, weight, bias, gamma, beta, ns, relu, want_rows=True, maxou
     return y
 
 
+SA_MLP_TC = True                # module-wide switch: per-ball GroupNorm inside the tensor-core GEMM epilogues (SA 3-5)
+
+
+def sa_mlp_tc_supported(ns, cin, widths, rows):
+    return (SA_MLP_TC and LINEAR_ENGINE != 'simt' and len(widths) == 3 and rows >= TC_MIN_ROWS and
+            bool(lib.caspr_sa_mlp_tc_supported(ns, cin, *widths)))
+
+
+def sa_mlp_tc(rows, ns, convs, norms, out):
+    """Per-ball MLP of a set-abstraction scale on the tensor cores: rows (balls*ns, Cin) grouped points ->
+    out (balls, C3) view (may be a column slice).  Three [conv, per-ball GroupNorm(16)] layers, ReLU after the first two,
+    max over the ball; the normalisation runs in the GEMM epilogues."""
+    rows, ldx = _rows2d(rows, 'rows')
+    n, cin = rows.shape
+    out, ld_out = _rows2d(out, 'out')
+    args = []
+    for conv, gn in zip(convs, norms):
+        w = conv.weight.reshape(conv.weight.shape[0], conv.weight.shape[1])
+        assert w.is_contiguous() and w.dtype == torch.float32
+        args += [ctypes.c_void_p(_prepared_weights(conv.weight, w)), _p(conv.bias), _p(gn.weight), _p(gn.bias),
+                 w.shape[0]]
+    c1, c2 = convs[0].weight.shape[0], convs[1].weight.shape[0]
+    nb = lib.caspr_sa_mlp_tc_workspace_bytes(n, cin, c1, c2)
+    ws, ws_ptr = _aligned_bytes(nb, rows.device)
+    _count('sa_mlp_tc')
+    check(lib.caspr_sa_mlp_tc(_p(rows), ldx, n, cin, ns, *args, float(norms[0].eps), _p(out), ld_out,
+                              ctypes.c_void_p(ws_ptr), nb, _stream()), 'caspr_sa_mlp_tc')
+    return out
+
+
 SA_FUSED = True                 # module-wide switch (accuracy / timing studies): fused set-abstraction scale kernel
 
 

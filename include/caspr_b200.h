@@ -111,6 +111,20 @@ int caspr_linear_gn_ball(const float* X, int ldx, const float* W, int ldw, const
                          const float* gamma, const float* beta, float eps, int rows, int Cin, int Cout,
                          int ns, int relu, float* Y, int ldy, float* maxout, int ld_max, void* stream);
 
+/* Per-ball MLP of a set-abstraction scale on the tensor cores (pointnet2.py:649-708 as used by SA levels 3-5):
+ * X (rows, Cin) grouped rows (caspr_group_points), balls of `ns` (16 or 32) consecutive rows ->
+ * [Conv1d(k=1) + GroupNorm(16) per ball + ReLU] x 2 -> Conv1d + GroupNorm -> max over the ball -> maxout (rows/ns, C3).
+ * The GroupNorm of every layer runs in the epilogue of its tcgen05 GEMM (a 128-row accumulator tile holds whole
+ * balls), which emits the next layer's fp16 operand planes directly.  prep1..3: caspr_linear_tc_prepare_weights
+ * blocks of the three weight matrices.  Widths in {64, 96, 128, 256, 512}, Cin >= 64 (caspr_sa_mlp_tc_supported). */
+int caspr_sa_mlp_tc_supported(int ns, int Cin, int C1, int C2, int C3);
+size_t caspr_sa_mlp_tc_workspace_bytes(long long rows, int Cin, int C1, int C2);
+int caspr_sa_mlp_tc(const float* X, int ldx, long long rows, int Cin, int ns,
+                    const void* prep1, const float* b1, const float* g1, const float* e1, int C1,
+                    const void* prep2, const float* b2, const float* g2, const float* e2, int C2,
+                    const void* prep3, const float* b3, const float* g3, const float* e3, int C3,
+                    float eps, float* maxout, int ld_max, void* workspace, size_t workspace_bytes, void* stream);
+
 /* One whole scale of a set-abstraction level in a single kernel (pointnet2.py:391-401,649-708): group gather
  * ([xyz[idx]-centre | feat[idx]], caspr_group_points) -> three layers Conv1d(k=1) + GroupNorm(16) (+ReLU after the
  * first two, pointnet2.py:693) with per-ball statistics -> max over the ball's ns rows.  Activations never leave

@@ -295,6 +295,46 @@ def test_sa_fused_matches_unfused_reference(ops, ns, widths, C):
     assert float(out[:, :5].abs().sum()) == 0 and float(out[:, 5 + widths[2]:].abs().sum()) == 0
 
 
+@pytest.mark.parametrize('ns,cin,widths', [(16, 131, (64, 64, 128)), (32, 131, (64, 96, 128)),
+                                           (32, 259, (128, 256, 256)), (16, 515, (256, 256, 512))])
+def test_sa_mlp_tc_matches_reference_chain(ops, ns, cin, widths):
+    """Per-ball MLP of SA levels 3-5 with the GroupNorm inside the tcgen05 GEMM epilogues (caspr_sa_mlp_tc) against the
+    same chain in fp64 torch: ragged ball count (partial 128-row tile), padded balls (a ball holding copies of ONE row:
+    zero variance), groups of 4 / 6 / 8 / 16 / 32 channels, output written into a column slice."""
+    g = torch.Generator().manual_seed(ns + cin)
+    balls = 301
+    rows = torch.randn(balls, ns, cin, generator=g)
+    rows[5] = rows[5, :1]                                  # padded ball: every sample is the same point
+    rows[77, 3:] = rows[77, 2:3]                           # mostly padded
+    rows = rows.reshape(balls * ns, cin).to(DEV)
+    convs, norms = [], []
+    dims = [cin] + list(widths)
+    for i in range(3):
+        conv = torch.nn.Conv1d(dims[i], dims[i + 1], 1)
+        gn = torch.nn.GroupNorm(16, dims[i + 1])
+        with torch.no_grad():
+            gn.weight.copy_(torch.rand(dims[i + 1], generator=g) + 0.5)
+            gn.bias.copy_(0.2 * torch.randn(dims[i + 1], generator=g))
+        convs.append(conv.to(DEV))
+        norms.append(gn.to(DEV))
+    assert ops.sa_mlp_tc_supported(ns, cin, list(widths), balls * ns)
+    out = torch.zeros(balls, widths[2] + 12, device=DEV)
+    ops.sa_mlp_tc(rows, ns, convs, norms, out[:, 4:4 + widths[2]])
+    h = rows.double().view(balls, ns, cin).transpose(1, 2)
+    for i in range(3):
+        h = torch.nn.functional.conv1d(h, convs[i].weight.double(), convs[i].bias.double())
+        h = torch.nn.functional.group_norm(h, 16, norms[i].weight.double(), norms[i].bias.double(), eps=1e-5)
+        if i < 2:
+            h = h.relu()
+    ref = h.max(2)[0]
+    # zero-variance balls divide rounding noise by sqrt(eps) = 316 in any fp32 implementation
+    assert _rel(out[:, 4:4 + widths[2]], ref) < 2e-4
+    ok = torch.ones(balls, dtype=torch.bool)
+    ok[5] = ok[77] = False
+    assert _rel(out[ok, 4:4 + widths[2]], ref[ok]) < 2e-5
+    assert float(out[:, :4].abs().sum()) == 0 and float(out[:, 4 + widths[2]:].abs().sum()) == 0
+
+
 def test_augment_and_broadcast(ops):
     x, _ = synthetic_sequences(1, 2, 100, seed=0)
     x4 = x.view(-1, 4)
