@@ -593,7 +593,8 @@ constexpr float kBallPlaneScale = 512.f;      // |GroupNorm output| <= |gamma| s
 template <int CPG, bool LAST>
 struct BallNormEpilogue {
   static constexpr bool kReadsTmem = true;
-  static constexpr int kChunk = (32 / CPG) * CPG;               // 32, or 24 for groups of 6 channels (C = 96)
+  static constexpr int kChunk = (CPG == 6) ? 24 : 32;           // whole groups, a multiple of 8 columns (C = 96: 24)
+  static_assert(kChunk % CPG == 0 && kChunk % 8 == 0, "a chunk holds whole GroupNorm groups");
   static constexpr int kGroups = kChunk / CPG;
   const float* bias;
   const float* x_inv;      // per-row 1/scale of the A planes, or nullptr: inv_const for every row
