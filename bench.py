@@ -428,7 +428,7 @@ def run_ours(args, rank, world, local_rank):
     ms = ev0.elapsed_time(ev1)
     nfe = [int(v) for v in model.get_nfe()]
     prof = {}
-    for name, kid in (('cnf_mid_layer_kernel', 0), ('cnf_tc_layer_kernel', 1)):
+    for name, kid in (('cnf_mid_layer_kernel', 0), ('cnf_tc_layer_kernel', 1), ('cnf_fused_eval_kernel', 4)):
         tot, cnt = ctypes.c_double(), ctypes.c_longlong()
         lib.caspr_profile_read(kid, ctypes.byref(tot), ctypes.byref(cnt))
         prof[name] = (tot.value, cnt.value)
@@ -491,37 +491,42 @@ def run_ours(args, rank, world, local_rank):
     peaks = load_peaks()
     value = world * pts_per_step * args.steps / (ms * 1e-3)
     e2e_value = world * pts_per_step * args.steps / (ms_e2e * 1e-3)
-    # dominant kernel: the H x H layers of the CNF dynamics over [activation ; tangent] rows
+    # dominant kernel: the dynamics evaluation of the CNF.  Fused engine (default): ONE launch of cnf_fused_eval_kernel
+    # evaluates the whole ODEnet with its forward-mode divergence for all points: ALGORITHMIC work per point-evaluation
+    # = 2 x 2 x (3 H + H H + H H + H 3) = 2 109 440 FLOP.  Four-kernel path (CASPR_CNF_FUSED=0): one H x H
+    # ConcatSquash layer over {activation, tangent} rows per launch.
     H = 512
     n_pts = B * Tq * P
-    # ALGORITHMIC flops: one H x H ConcatSquash layer over {activation, tangent} rows of every point, two such
-    # layers per dynamics evaluation.  The tensor-core engine pipelines the point set in two halves on two
-    # streams, so a launch covers n_pts / chunks points; flops per launch follow from the launch count.
+    eval_flop = 2.0 * 2 * n_pts * (3 * H + H * H + H * H + H * 3)
     layer_flop = 2.0 * 2 * n_pts * H * H
     chunks = 2 if (os.environ.get('CASPR_CNF_PIPELINE_HALVES') == '1' and (n_pts + 63) // 64 >= 296) else 1
-    if prof['cnf_tc_layer_kernel'][1] > 0:
-        kname = 'gemm_fp16x3_kernel<CnfEpilogue> (tcgen05, 3 fp16 MMAs per algorithmic MAC)'
+    if prof['cnf_fused_eval_kernel'][1] > 0:
+        kname, engine_key = 'cnf_fused_eval_kernel (tcgen05 cta_group::2, fp16x3: 3 MMAs per algorithmic MAC)', 'fused'
+        flop_per_launch, mma_flop = eval_flop, 3 * 2 * layer_flop
+        prof[kname] = prof['cnf_fused_eval_kernel']
+    elif prof['cnf_tc_layer_kernel'][1] > 0:
+        kname, engine_key = 'gemm_fp16x3_pair_kernel<CnfEpilogue> (tcgen05, 3 fp16 MMAs per algorithmic MAC)', 'tc'
+        flop_per_launch, mma_flop = layer_flop / chunks, 3 * layer_flop / chunks
         prof[kname] = prof['cnf_tc_layer_kernel']
     else:
-        kname = 'cnf_mid_layer_kernel'
+        kname, engine_key = 'cnf_mid_layer_kernel', 'simt'
+        flop_per_launch, mma_flop = layer_flop, None
 
     tot_ms, cnt = prof[kname]
     roofline = None
     if cnt > 0:
         avg_ms = tot_ms / cnt
-        flop_per_launch = layer_flop / chunks
         achieved = flop_per_launch / (avg_ms * 1e-3) / 1e12
         # DRAM bytes per launch: read from the committed summary of the ncu --set full capture of this kernel on this
-        # shape (profiles/traffic.json, written by tools/ncu_summary.py --traffic); None when no capture matches
-        traffic, traffic_src = lookup_traffic('tc' if 'tcgen05' in kname else 'simt', n_pts // chunks)
+        # shape (profiles/traffic.json, written from the ncu report); None when no capture matches
+        traffic, traffic_src = lookup_traffic(engine_key, n_pts // chunks)
         roofline = {'bound': 'tensor', 'kernel': kname, 'achieved': achieved, 'peak': peaks['tf_sustained'],
                     'unit': 'TFLOP/s', 'frac': achieved / peaks['tf_sustained'], 'traffic': traffic,
-                    'traffic_unit': 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, average of '
-                                    'the two H x H layers)', 'traffic_source': traffic_src,
+                    'traffic_unit': 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)',
+                    'traffic_source': traffic_src,
                     'peak_source': peaks['source'] + ' bf16 dense sustained', 'launches': cnt,
                     'avg_launch_ms': avg_ms, 'share_of_step': tot_ms / (ms / args.steps) / args.steps,
-                    'flop_per_launch': flop_per_launch,
-                    'mma_flop_per_launch': 3 * flop_per_launch if 'tcgen05' in kname else None,
+                    'flop_per_launch': flop_per_launch, 'mma_flop_per_launch': mma_flop,
                     'note': 'achieved = algorithmic fp32-grade FLOP / CUDA-event time; the fp16x3 split issues 3x '
                             'that many tensor-core FLOP, so frac <= 1/3 by construction'}
 

@@ -957,12 +957,12 @@ int enqueue_fused(const Plan& plan, const float4* y0, const float4* kbuf, size_t
       p.debug = g_debug_buf;
     }
   }
-  caspr_prof_begin(CASPR_PROF_CNF_FUSED_TC, s);
+  caspr_prof_begin(CASPR_PROF_CNF_EVAL_FUSED, s);
   CASPR_COUNT();
   fused::cnf_fused_eval_kernel<<<plan.fused_grid, fused::kThreads, fused::kSmemBytes, s>>>(
       plan.tm_sa[0], plan.tm_sa[1], plan.tm_sb[0], plan.tm_sb[1], plan.tm_w[0][0], plan.tm_w[0][1], plan.tm_w[1][0],
       plan.tm_w[1][1], p);
-  caspr_prof_end(CASPR_PROF_CNF_FUSED_TC, s);
+  caspr_prof_end(CASPR_PROF_CNF_EVAL_FUSED, s);
   CASPR_CHECK_LAUNCH();
   return CASPR_OK;
 }

@@ -48,6 +48,10 @@ class TPointNet2(nn.Module):
         # launch eagerly.
         self.use_cuda_graph = True
         self._graphs = {}
+        # measured on B200 (config 2): 14.5 ms with the overlap, 14.1 ms without (the persistent GEMM CTAs and the FPS CTAs
+        # do not co-reside), so it is off unless CASPR_ENCODER_OVERLAP=1
+        self.overlap_branches = os.environ.get('CASPR_ENCODER_OVERLAP', '0') == '1'
+        self._side = {}
 
     def _local_input(self, x4):
         """tpointnet2.py:79-90: xyz ++ (x^2,y^2,z^2) ++ (xz,xy,yz) as rows."""
@@ -93,6 +97,12 @@ class TPointNet2(nn.Module):
         _lib.lib.caspr_launch_count_add(n_kernels)
         return z0_s.clone(), (None if tnocs_s is None else tnocs_s.clone())
 
+    def _side_stream(self, device):
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        if key not in self._side:
+            self._side[key] = torch.cuda.Stream(device=device)
+        return self._side[key]
+
     def _param_key(self):
         """Identity of the parameter storage the captured kernels read plus the in-place version counters
         (the graph references fp16 weight planes derived from the values: ops._prepared_weights)."""
@@ -113,10 +123,22 @@ class TPointNet2(nn.Module):
         width = L + Pf if split_head else L + G + Pf
         feat = torch.empty(R, width, dtype=torch.float32, device=x.device)
         pf_off = L if split_head else L + G
-        # global spatio-temporal PointNet on (B, T*N) points (tpointnet2.py:75-76)
-        gmax, _ = self.global_extract.forward_rows(x4, B, T * N, pointfeat_out=feat[:, pf_off:pf_off + Pf])
-        if not split_head:
-            ops.broadcast_rows(gmax, T * N, feat[:, L:L + G])
+        # global spatio-temporal PointNet on (B, T*N) points (tpointnet2.py:75-76).  It is independent of the PointNet++
+        # branch until the head, and the first thing that branch does is the latency-bound farthest-point-sampling /
+        # ball-query chain (80 CTAs on a 148-SM part): run the PointNet on a second stream underneath it.  The fork and
+        # join are stream dependencies, so they are captured into the encoder's CUDA graph like everything else.
+        main = torch.cuda.current_stream(x.device)
+        side = self._side_stream(x.device) if self.overlap_branches else None
+        if side is not None:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                gmax, _ = self.global_extract.forward_rows(x4, B, T * N, pointfeat_out=feat[:, pf_off:pf_off + Pf])
+                if not split_head:
+                    ops.broadcast_rows(gmax, T * N, feat[:, L:L + G])
+        else:
+            gmax, _ = self.global_extract.forward_rows(x4, B, T * N, pointfeat_out=feat[:, pf_off:pf_off + Pf])
+            if not split_head:
+                ops.broadcast_rows(gmax, T * N, feat[:, L:L + G])
         # per-frame PointNet++ (tpointnet2.py:79-93)
         local_in = self._local_input(x4)
         trace = None
@@ -125,6 +147,10 @@ class TPointNet2(nn.Module):
             trace.setdefault('fps_idx', [])
             trace.setdefault('ball_idx', [])
         self.local_extract.forward_rows(local_in.view(B * T, N, -1), out=feat[:, :L], trace=trace)
+        if side is not None:
+            # join: everything the side stream touched is still referenced here, and the next fork starts with
+            # side.wait_stream(main), so no block is recycled across the two streams without an ordering edge
+            main.wait_stream(side)
         # head (tpointnet2.py:99-113)
         if split_head:
             w1 = self.conv1.weight

@@ -51,7 +51,8 @@ void caspr_launch_count_add(unsigned long long n);
  * caspr_profile_enable(1) clears the records and starts recording one event pair around every
  * launch of the kernels below; caspr_profile_read waits for the recorded events and returns the
  * summed device time and the number of launches recorded. */
-enum { CASPR_PROF_CNF_MID_SIMT = 0, CASPR_PROF_CNF_FUSED_TC = 1, CASPR_PROF_LINEAR = 2, CASPR_PROF_FPS = 3 };
+enum { CASPR_PROF_CNF_MID_SIMT = 0, CASPR_PROF_CNF_FUSED_TC = 1, CASPR_PROF_LINEAR = 2, CASPR_PROF_FPS = 3,
+       CASPR_PROF_CNF_EVAL_FUSED = 4 /* cnf_fused_eval_kernel: one whole dynamics evaluation per launch */ };
 void caspr_profile_enable(int on);
 int caspr_profile_read(int kernel_id, double* total_ms, long long* launches);
 
