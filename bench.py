@@ -341,8 +341,10 @@ def time_training_config(rank, world, dev, steps=3, warmup=3, B=8, T=5, N=1024):
     n0 = _lib.lib.caspr_launch_count()
     losses = [step(True) for _ in range(steps)]
     launches = _lib.lib.caspr_launch_count() - n0
-    tot, ar = _max_over_ranks([sum(phase), phase[2]], dev, world)
-    ms, ar_ms = tot / steps, ar / steps
+    # the all-reduce event pair of a rank that finished its backward early also times its wait for the slowest rank:
+    # the MIN over ranks is the collective itself (last arrival -> done), the MAX includes the skew
+    tot, ar_max, neg_ar_min = _max_over_ranks([sum(phase), phase[2], -phase[2]], dev, world)
+    ms, ar_ms, ar_wait_ms = tot / steps, -neg_ar_min / steps, ar_max / steps
     nbytes = flat.flat.numel() * 4
     out = {'ms_per_step': round(ms, 3), 'value': world * B * T * N / (ms * 1e-3), 'unit': 'trained points/s',
            'steps': steps, 'warmup': warmup,
@@ -352,6 +354,7 @@ def time_training_config(rank, world, dev, steps=3, warmup=3, B=8, T=5, N=1024):
            'phase_ms_forward_backward_allreduce_adam_bufsync': [round(v / steps, 3) for v in phase],
            'loss': losses[-1], 'gradient_bytes': nbytes, 'gpu_launches_per_step': int(launches // steps),
            'allreduce_ms': round(ar_ms, 3) if world > 1 else None,
+           'allreduce_ms_incl_skew_max_rank': round(ar_wait_ms, 3) if world > 1 else None,
            # NCCL bus bandwidth of a ring/tree all-reduce: 2 (n-1)/n x bytes / time; NVLink 5 offers 900 GB/s per direction
            'allreduce_busbw_gbs': round(2.0 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9, 1) if world > 1 else None}
     return out
