@@ -141,6 +141,7 @@ int cnf_flow_impl(const float* x_in, const float* logp_in, const float* e, const
     if (step_id >= kMaxSteps) { hst.status = CASPR_ESOLVER_MAXSTEPS; break; }
   }
   if (engine == CASPR_CNF_TC_FP16X3) {
+    release_l2_persistence(s);
     int h_range = 0;
     if (cudaMemcpyAsync(&h_range, w.range_flag, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
         cudaStreamSynchronize(s) != cudaSuccess)

@@ -2,6 +2,7 @@
 // adjoint backward (cnf_adjoint.cu).  Everything lives in an anonymous namespace: each including translation
 // unit gets its own copy.
 #pragma once
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
@@ -867,8 +868,55 @@ int prepare_engine(const CnfWorkspace& w, const caspr_cnf_weights* cw, int n, in
   if (rc) return rc;
   int fgrid = cnf_tc::fused_grid_for(n, *num_sms);
   if (fgrid > w.fused_grid) fgrid = w.fused_grid;
+  {
+    // Experiment (CASPR_CNF_L2_PERSIST=1): mark the per-CTA scratch of the fused kernel as persisting in L2 so that its
+    // dirty lines are not written back to HBM between the tile that writes them and the tile that overwrites them.
+    static int persist = -1;
+    if (persist < 0) { const char* e2 = getenv("CASPR_CNF_L2_PERSIST"); persist = (e2 && e2[0] == '1') ? 1 : 0; }
+    if (persist && cnf_tc::fused_enabled()) {
+      cudaDeviceProp prop;
+      if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+        size_t bytes = cnf_tc::fused_scratch_bytes(fgrid);
+        size_t set_aside = bytes < (size_t)prop.persistingL2CacheMaxSize ? bytes : (size_t)prop.persistingL2CacheMaxSize;
+        static size_t limit_set = 0;                 // the set-aside is configured once per process (it is a device-wide
+        if (set_aside > limit_set) {                 // reconfiguration); lines only persist while a window is active
+          cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside);
+          limit_set = set_aside;
+        }
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        attr.accessPolicyWindow.base_ptr = w.fused_scratch;
+        attr.accessPolicyWindow.num_bytes = bytes < (size_t)prop.accessPolicyMaxWindowSize ? bytes : (size_t)prop.accessPolicyMaxWindowSize;
+        attr.accessPolicyWindow.hitRatio = 1.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
+        static bool printed = false;
+        if (!printed) {
+          fprintf(stderr, "[caspr] L2 persistence: set-aside %zu MB (max %d MB), window %zu MB (max %d MB)\n", set_aside >> 20,
+                  prop.persistingL2CacheMaxSize >> 20, (size_t)attr.accessPolicyWindow.num_bytes >> 20,
+                  prop.accessPolicyMaxWindowSize >> 20);
+          printed = true;
+        }
+      }
+    }
+  }
   return cnf_tc::make_plan(*plan, w.tcw, (__half*)w.Ha, (__half*)w.Va, (__half*)w.Hb, (__half*)w.Vb, n,
                            cnf_tc::fused_enabled() ? w.fused_scratch : nullptr, fgrid);
+}
+
+// end of a solve: close the access-policy window and hand the persisting lines back to normal use
+void release_l2_persistence(cudaStream_t s) {
+  const char* e2 = getenv("CASPR_CNF_L2_PERSIST");
+  if (!(e2 && e2[0] == '1') || !cnf_tc::fused_enabled()) return;
+  cudaStreamAttrValue attr;
+  memset(&attr, 0, sizeof(attr));
+  attr.accessPolicyWindow.num_bytes = 0;
+  attr.accessPolicyWindow.hitRatio = 0.f;
+  attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+  attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+  cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
+  cudaCtxResetPersistingL2Cache();
 }
 
 bool weights_ok(const caspr_cnf_weights* cw) {

@@ -519,7 +519,10 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
       const long long dbg_t0 = p.debug ? clock64() : 0;
       auto load_item = [&](const CUtensorMap* a_hi, const CUtensorMap* a_lo, const CUtensorMap* w_hi,
                            const CUtensorMap* w_lo, int a_row, int nh, const uint64_t* chunk_bars, uint32_t chunk_parity) {
-        for (int kc = 0; kc < 8; ++kc) {
+        for (int kk = 0; kk < 8; ++kk) {
+          // layer-2 items take the k-chunks in the order their SB boxes are published: the two epilogue groups write
+          // boxes (4, 5) and (6, 7) of the n1 half concurrently, so box 6 lands long before box 5
+          const int kc = (chunk_bars == sb_full && kk >= 5 && kk <= 6) ? 11 - kk : kk;
           const long long c0 = p.debug ? clock64() : 0;
           tc::mbar_wait(&empty[stage], phase ^ 1);
           const long long c1 = p.debug ? clock64() : 0;
