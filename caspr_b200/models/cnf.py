@@ -10,7 +10,7 @@ state_dict keys ``chain.{0,2}.{weight,bias,step,running_mean,running_var}``,
 The modules are parameter containers: ``SequentialFlow.forward`` hands the whole chain
 [MovingBatchNorm, CNF, MovingBatchNorm] to ``caspr_cnf_flow`` — one device-resident dopri5
 solve that evaluates the dynamics MLP, its Hutchinson divergence and the step controller in
-CUDA (no per-step host synchronisation, no autograd VJP).
+CUDA (the host only polls the 8-word solver state once per attempted step; no autograd VJP).
 """
 import torch
 import torch.nn as nn
@@ -153,7 +153,10 @@ class CNF(nn.Module):
             ctx_dim = layers[0]._hyper_gate.weight.shape[1] - 1
             for d in tensors:
                 for k in d:
-                    d[k] = d[k].to(torch.float32).contiguous()
+                    # the pack holds POINTERS to the parameters: a converted copy would go stale after optimizer steps
+                    if d[k].dtype != torch.float32 or not d[k].is_contiguous():
+                        raise TypeError('the CNF kernels read the ODEnet parameters in place: they must be contiguous '
+                                        'float32 tensors (got %s, contiguous=%s)' % (d[k].dtype, d[k].is_contiguous()))
             self._pack = ops.CnfWeightPack(tensors, hidden, ctx_dim)
             self._pack_key = key
         return self._pack

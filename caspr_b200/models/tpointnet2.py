@@ -97,6 +97,12 @@ class TPointNet2(nn.Module):
         _lib.lib.caspr_launch_count_add(n_kernels)
         return z0_s.clone(), (None if tnocs_s is None else tnocs_s.clone())
 
+    def reset_graphs(self):
+        """Forget the captured CUDA graphs and the cached weight planes (needed after weight edits that bypass the
+        version counters, e.g. through `.data`)."""
+        self._graphs.clear()
+        ops.invalidate_weight_cache()
+
     def _side_stream(self, device):
         key = device.index if device.index is not None else torch.cuda.current_device()
         if key not in self._side:

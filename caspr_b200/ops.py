@@ -207,6 +207,14 @@ def derived_weight(param, tag, fn):
     return value
 
 
+def invalidate_weight_cache():
+    """Drop every cached set of fp16 weight planes / derived matrices.  The caches are keyed by the parameters' in-place
+    version counters, which `p.data.copy_()`-style edits do NOT bump: call this (and `model.encoder.reset_graphs()`)
+    after modifying weights through `.data`."""
+    _WEIGHT_PLANES.clear()
+    _DERIVED.clear()
+
+
 def tc_eligible(rows, cin, cout):
     return (LINEAR_ENGINE != 'simt' and rows >= TC_MIN_ROWS and cin >= TC_MIN_CIN and cout >= TC_MIN_COUT and
             cout % 4 == 0)
@@ -427,6 +435,10 @@ def broadcast_rows(src, rows_per_sample, dst):
 
 
 # ------------------------------------------------------------------------------ latent ODE
+LATENT_MAX_TIMES = 64                    # csrc/latent_ode.cu: kMaxTimes
+LATENT_MAX_STAGING_BYTES = 200 * 1024    # B * max(H, D) floats of staging per CTA
+
+
 def latent_ode_solve(z0, weights, biases, times, rtol, atol):
     """dopri5 solve of the latent dynamics MLP.  z0 (B,D); times: increasing python floats /
     1-D tensor (times[0] = start).  Returns out (nT,B,D) and the info list [status,nfe,acc,rej,...]."""
@@ -436,6 +448,14 @@ def latent_ode_solve(z0, weights, biases, times, rtol, atol):
     H = weights[0].shape[0]
     tl = [float(t) for t in times]
     nT = len(tl)
+    # limits of the cooperative solver (csrc/latent_ode.cu): the output-time table lives in shared memory
+    if nT > LATENT_MAX_TIMES:
+        raise ValueError('caspr_latent_ode_solve handles at most %d distinct time stamps per call, got %d '
+                         '(reconstruct(timestamps=...) with more steps: query them in several calls)'
+                         % (LATENT_MAX_TIMES, nT))
+    if B * max(H, D) * 4 > LATENT_MAX_STAGING_BYTES:
+        raise ValueError('caspr_latent_ode_solve stages B x max(H, D) floats in shared memory (<= %d KB): B = %d is too '
+                         'large; split the batch' % (LATENT_MAX_STAGING_BYTES // 1024, B))
     h_times = (ctypes.c_double * nT)(*tl)
     out = torch.empty(nT, B, D, dtype=torch.float32, device=z0.device)
     info = torch.zeros(8, dtype=torch.int32, device=z0.device)
