@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-clock-sampler', action='store_true',
                     help='do not spawn the nvidia-smi sampler (it hangs under ncu): lets bench.py itself be profiled')
+    ap.add_argument('--no-cuda-graph', action='store_true',
+                    help='launch the encoder kernels eagerly instead of replaying its CUDA graph (per-kernel ncu lists)')
     ap.add_argument('--no-extra-configs', action='store_true',
                     help='skip the "configs" block (BASELINE configs[2..4] per-GPU shards)')
     ap.add_argument('--ref-budget-s', type=float, default=240.0,
@@ -386,6 +388,8 @@ def run_ours(args, rank, world, local_rank):
     sd, x, y, e, kwargs, (B, T, N, P, Tq) = make_inputs(args.workload, rank, args.cnf_init)
     model = CaSPR().to(dev).eval()
     model.load_state_dict(sd)
+    if args.no_cuda_graph:
+        model.encoder.use_cuda_graph = False
     x_pin = x.pin_memory()
     x_dev, y_dev, e_dev = x.to(dev), y.to(dev), e.to(dev)
     kw_dev = dict(kwargs)
