@@ -119,7 +119,11 @@ int cnf_flow_impl(const float* x_in, const float* logp_in, const float* e, const
     CASPR_COUNT(); cnf_passthrough_kernel<<<ceil_div(n, 256), 256, 0, s>>>(w.y0, n, post, reverse, have_logp, x_out, logp_out);
     CASPR_CHECK_LAUNCH();
   }
-  const int kBatch = 1, kMaxSteps = 100000;
+  // Steps enqueued between two polls of the solver state.  Every kernel of a step exits at once when the solve has
+  // finished, so enqueueing one speculative step costs ~10 empty launches at the end of the solve and hides the
+  // launch + synchronisation gap (~60 us) of every other step.  Lock-step mode polls every step (its hook is a
+  // collective all ranks must call the same number of times).
+  const int kBatch = sync ? 1 : 2, kMaxSteps = 100000;
   int step_id = 0;
   CnfState hst;
   for (;;) {
