@@ -57,7 +57,7 @@ def parse_args():
                     help='launch the encoder kernels eagerly instead of replaying its CUDA graph (per-kernel ncu lists)')
     ap.add_argument('--no-extra-configs', action='store_true',
                     help='skip the "configs" block (BASELINE configs[2..4] per-GPU shards)')
-    ap.add_argument('--ref-budget-s', type=float, default=240.0,
+    ap.add_argument('--ref-budget-s', type=float, default=180.0,
                     help='--impl reference: wall-clock budget for the timed steps (each step is the full batch)')
     return ap.parse_args()
 

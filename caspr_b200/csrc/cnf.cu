@@ -225,9 +225,10 @@ extern "C" int caspr_cnf_feval(const float* y, const float* e, const float* ctx,
 
 // Profiling aid: with CASPR_CNF_FUSED_DEBUG=1 the fused evaluation kernel records, per CTA, the cycles its TMA producer
 // and MMA threads spent waiting ([0] stage free, [1] layer-0 / layer-1 output ready, [2] producer total, [4] accumulator
-// free, [5] operands landed, [6] MMA thread total) during its LAST launch.  Copies count (<= 148*8) counters to `out`.
+// free, [5] operands landed, [6] MMA thread total) during its LAST launch.  Slots [8 + 8g + k] / [8 + 8g + 4 + k]: cycles epilogue group g waited for / worked on items of
+// kind k (L1.n0, L1.n1, L2.n0, L2.n1).  24 counters per CTA; copies count (<= 148*24) counters to `out`.
 extern "C" int caspr_cnf_fused_debug_read(long long* out, int count) {
-  CASPR_REQUIRE(out && count > 0 && count <= 148 * 8);
+  CASPR_REQUIRE(out && count > 0 && count <= 148 * 24);
   long long* buf = cnf_tc::fused_debug_buffer();
   if (!buf) return CASPR_EINVAL;
   if (cudaDeviceSynchronize() != cudaSuccess) return CASPR_ELAUNCH;

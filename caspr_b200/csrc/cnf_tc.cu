@@ -441,8 +441,16 @@ struct Params {
   __half* sa_lo;
   __half* sb_hi;           // scratch SB planes, same shape
   __half* sb_lo;
+  int dbg_mode;            // timing experiments only (CASPR_CNF_FUSED_DEBUG=2: no SB stores, 3: no split / range)
   long long* debug;        // optional [gridDim.x][8] cycle counters of the producer / MMA threads (CASPR_CNF_FUSED_DEBUG)
 };
+
+// 32-byte global store (sm_100: st.global.v8.b32): halves the number of (instruction, line) pairs the LSU handles
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&a)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a[0]), "r"(a[1]), "r"(a[2]),
+               "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7])
+               : "memory");
+}
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
@@ -518,7 +526,8 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
       long long dbg_empty = 0, dbg_dep = 0, dbg_dep2 = 0;
       const long long dbg_t0 = p.debug ? clock64() : 0;
       auto load_item = [&](const CUtensorMap* a_hi, const CUtensorMap* a_lo, const CUtensorMap* w_hi,
-                           const CUtensorMap* w_lo, int a_row, int nh, const uint64_t* chunk_bars, uint32_t chunk_parity) {
+                           const CUtensorMap* w_lo, int a_row, int nh, const uint64_t* chunk_bars, uint32_t chunk_parity,
+                           bool chunk_layout64) {
         for (int kk = 0; kk < 8; ++kk) {
           // layer-2 items take the k-chunks in the order their SB boxes are published: the two epilogue groups write
           // boxes (4, 5) and (6, 7) of the n1 half concurrently, so box 6 lands long before box 5
@@ -531,8 +540,18 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
           uint8_t* sb = smem + stage * kStageBytes;
           const uint32_t lead_full = tc::mapa_shared(&full[stage], 0);
           if (rank == 0) tc::mbar_arrive_expect_tx(&full[stage], 2 * kStageBytes);       // bytes of BOTH CTAs
-          tc::tma_load_2d_pair(sb, a_hi, lead_full, kc * 64, a_row);
-          tc::tma_load_2d_pair(sb + kATile, a_lo, lead_full, kc * 64, a_row);
+          if (chunk_layout64) {
+            // A from SB: two [128][32] sub-chunk boxes per plane (64-byte swizzle), sub-chunk s of this CTA at rows
+            // (cta * 16 + s) * 128 of the [.][32] tensor
+            const int r0 = (cta * 16 + 2 * kc) * kBM;
+            tc::tma_load_2d_pair(sb, a_hi, lead_full, 0, r0);
+            tc::tma_load_2d_pair(sb + kATile / 2, a_hi, lead_full, 0, r0 + kBM);
+            tc::tma_load_2d_pair(sb + kATile, a_lo, lead_full, 0, r0);
+            tc::tma_load_2d_pair(sb + kATile + kATile / 2, a_lo, lead_full, 0, r0 + kBM);
+          } else {
+            tc::tma_load_2d_pair(sb, a_hi, lead_full, kc * 64, a_row);
+            tc::tma_load_2d_pair(sb + kATile, a_lo, lead_full, kc * 64, a_row);
+          }
           tc::tma_load_2d_pair(sb + 2 * kATile, w_hi, lead_full, kc * 64, nh * kBN + (int)rank * (kBN / 2));
           tc::tma_load_2d_pair(sb + 2 * kATile + kWTile, w_lo, lead_full, kc * 64, nh * kBN + (int)rank * (kBN / 2));
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -540,14 +559,14 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
       };
       for (int i = 0; i < n_iter; ++i) {
         const uint32_t par = (uint32_t)(i & 1);
-        load_item(&tm_sa_hi, &tm_sa_lo, &tm_w1_hi, &tm_w1_lo, cta * kBM, 0, sa_full, par);
-        load_item(&tm_sa_hi, &tm_sa_lo, &tm_w1_hi, &tm_w1_lo, cta * kBM, 1, nullptr, 0);
-        load_item(&tm_sb_hi, &tm_sb_lo, &tm_w2_hi, &tm_w2_lo, cta * kBM, 0, sb_full, par);
-        load_item(&tm_sb_hi, &tm_sb_lo, &tm_w2_hi, &tm_w2_lo, cta * kBM, 1, nullptr, 0);
+        load_item(&tm_sa_hi, &tm_sa_lo, &tm_w1_hi, &tm_w1_lo, cta * kBM, 0, sa_full, par, false);
+        load_item(&tm_sa_hi, &tm_sa_lo, &tm_w1_hi, &tm_w1_lo, cta * kBM, 1, nullptr, 0, false);
+        load_item(&tm_sb_hi, &tm_sb_lo, &tm_w2_hi, &tm_w2_lo, cta * kBM, 0, sb_full, par, true);
+        load_item(&tm_sb_hi, &tm_sb_lo, &tm_w2_hi, &tm_w2_lo, cta * kBM, 1, nullptr, 0, true);
       }
       if (p.debug) {
-        p.debug[cta * 8 + 0] = dbg_empty; p.debug[cta * 8 + 1] = dbg_dep; p.debug[cta * 8 + 2] = clock64() - dbg_t0;
-        p.debug[cta * 8 + 3] = dbg_dep2;
+        p.debug[cta * 24 + 0] = dbg_empty; p.debug[cta * 24 + 1] = dbg_dep; p.debug[cta * 24 + 2] = clock64() - dbg_t0;
+        p.debug[cta * 24 + 3] = dbg_dep2;
       }
     }
   } else if (warp == 1) {
@@ -558,7 +577,7 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
       uint32_t phase = 0;
       long long dbg_tempty = 0, dbg_full = 0;
       const long long dbg_t0 = p.debug ? clock64() : 0;
-      auto mma_item = [&]() {
+      auto mma_item = [&](bool a_layout64) {
         const int buf = it & 1;
         const long long c0 = p.debug ? clock64() : 0;
         tc::mbar_wait(&tempty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
@@ -571,16 +590,30 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
           if (p.debug) dbg_full += clock64() - c1;
           tc::fence_after_sync();
           const uint32_t sb = tc::smem_u32(smem + stage * kStageBytes);
-          const uint64_t a_hi = tc::make_desc_k128(sb);
-          const uint64_t a_lo = tc::make_desc_k128(sb + kATile);
           const uint64_t w_hi = tc::make_desc_k128(sb + 2 * kATile);
           const uint64_t w_lo = tc::make_desc_k128(sb + 2 * kATile + kWTile);
+          if (a_layout64) {
+            // A planes as two [128][32] sub-chunk boxes (64-byte swizzle): K steps 0-1 in the first, 2-3 in the second
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t adv = (uint64_t)(ks * 2);
-            tc::umma_f16_ss_pair(d_tmem, a_hi + adv, w_hi + adv, idesc, (kc | ks) != 0);
-            tc::umma_f16_ss_pair(d_tmem, a_lo + adv, w_hi + adv, idesc, 1);
-            tc::umma_f16_ss_pair(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t off = (uint32_t)(ks >> 1) * (kATile / 2);
+              const uint64_t a_hi = tc::make_desc_k64(sb + off) + (uint64_t)((ks & 1) * 2);
+              const uint64_t a_lo = tc::make_desc_k64(sb + kATile + off) + (uint64_t)((ks & 1) * 2);
+              const uint64_t adv = (uint64_t)(ks * 2);
+              tc::umma_f16_ss_pair(d_tmem, a_hi, w_hi + adv, idesc, (kc | ks) != 0);
+              tc::umma_f16_ss_pair(d_tmem, a_lo, w_hi + adv, idesc, 1);
+              tc::umma_f16_ss_pair(d_tmem, a_hi, w_lo + adv, idesc, 1);
+            }
+          } else {
+            const uint64_t a_hi = tc::make_desc_k128(sb);
+            const uint64_t a_lo = tc::make_desc_k128(sb + kATile);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t adv = (uint64_t)(ks * 2);
+              tc::umma_f16_ss_pair(d_tmem, a_hi + adv, w_hi + adv, idesc, (kc | ks) != 0);
+              tc::umma_f16_ss_pair(d_tmem, a_lo + adv, w_hi + adv, idesc, 1);
+              tc::umma_f16_ss_pair(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+            }
           }
           tc::umma_commit_pair(&empty[stage], 3);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -589,14 +622,14 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
         ++it;
       };
       for (int i = 0; i < n_iter; ++i) {
-        mma_item();
-        mma_item();
+        mma_item(false);
+        mma_item(false);
         tc::umma_commit_pair(sa_free, 3);            // both layer-1 products of tile i have consumed SA
-        mma_item();
-        mma_item();
+        mma_item(true);
+        mma_item(true);
       }
       if (p.debug) {
-        p.debug[cta * 8 + 4] = dbg_tempty; p.debug[cta * 8 + 5] = dbg_full; p.debug[cta * 8 + 6] = clock64() - dbg_t0;
+        p.debug[cta * 24 + 4] = dbg_tempty; p.debug[cta * 24 + 5] = dbg_full; p.debug[cta * 24 + 6] = clock64() - dbg_t0;
       }
     }
   } else if (warp < 10) {
@@ -608,6 +641,7 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
     const int pl = q * 16 + (lane & 15);                          // point of this lane within the tile
     const int box_row = q * 32 + (lane & 15);
     float range_max = 0.f;
+    int pending_box = -1;                                         // 64-column box of SB stored but not yet published
     int it = 0;                                                   // item counter (all roles count alike)
     for (int i = 0; i < n_iter; ++i) {
       for (int sub = 0; sub < 4; ++sub) {
@@ -624,7 +658,9 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
         const int col0 = nh * kBN + is_v * 16;
         const float* gp = p.gate + (size_t)f * p.ld_hyper + (layer2 ? 2 * H : H) + col0;
         const float* bp = p.biasf + (size_t)f * p.ld_hyper + (layer2 ? 2 * H : H) + col0;
+        const long long ec0 = (p.debug && etid == 0) ? clock64() : 0;
         tc::mbar_wait(&tfull[buf], acc_phase);
+        const long long ec1 = (p.debug && etid == 0) ? clock64() : 0;
         tc::fence_after_sync();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * kBN;
         float pa[3] = {0.f, 0.f, 0.f}, pv[3] = {0.f, 0.f, 0.f};
@@ -679,6 +715,13 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
             }
           } else {
             uint32_t hh[8], hl[8], vh[8], vl[8];
+            if (p.dbg_mode == 3) {
+#pragma unroll
+              for (int j2 = 0; j2 < 8; ++j2) {
+                hh[j2] = __float_as_uint(ho[2 * j2]); hl[j2] = __float_as_uint(ho[2 * j2 + 1]);
+                vh[j2] = __float_as_uint(vo[2 * j2]); vl[j2] = __float_as_uint(vo[2 * j2 + 1]);
+              }
+            } else {
 #pragma unroll
             for (int j2 = 0; j2 < 8; ++j2) {
               const float h0 = ho[2 * j2] * kActScale, h1 = ho[2 * j2 + 1] * kActScale;
@@ -687,29 +730,48 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
               split2(h0, h1, hh[j2], hl[j2]);
               split2(v0, v1, vh[j2], vl[j2]);
             }
+            }
             // 16-byte stores straight into the SB planes of this CTA (the lines stay in L2 and are re-read by TMA a
-            // few microseconds later); after the second chunk of a 64-column box every thread publishes it
+            // few microseconds later).  A 64-column box is published (proxy fence + arrive) one chunk LATER, just
+            // before the next chunk's stores: its own stores have been performed by then, so the fence does not stall
+            // the warp (publishing right after the stores cost ~2.5 k cycles per chunk, measured).
             {
-              __half* sb_hi_p = p.sb_hi + ((size_t)sb_row + box_row) * H + col0 + chunk * 32;
-              __half* sb_lo_p = p.sb_lo + ((size_t)sb_row + box_row) * H + col0 + chunk * 32;
-              *reinterpret_cast<uint4*>(sb_hi_p) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-              *reinterpret_cast<uint4*>(sb_hi_p + 8) = make_uint4(hh[4], hh[5], hh[6], hh[7]);
-              *reinterpret_cast<uint4*>(sb_lo_p) = make_uint4(hl[0], hl[1], hl[2], hl[3]);
-              *reinterpret_cast<uint4*>(sb_lo_p + 8) = make_uint4(hl[4], hl[5], hl[6], hl[7]);
-              *reinterpret_cast<uint4*>(sb_hi_p + 16 * H) = make_uint4(vh[0], vh[1], vh[2], vh[3]);
-              *reinterpret_cast<uint4*>(sb_hi_p + 16 * H + 8) = make_uint4(vh[4], vh[5], vh[6], vh[7]);
-              *reinterpret_cast<uint4*>(sb_lo_p + 16 * H) = make_uint4(vl[0], vl[1], vl[2], vl[3]);
-              *reinterpret_cast<uint4*>(sb_lo_p + 16 * H + 8) = make_uint4(vl[4], vl[5], vl[6], vl[7]);
-              if (chunk & 1) {
+              if (pending_box >= 0) {
                 fence_proxy_async_all();                           // generic-proxy stores -> visible to the TMA loads
-                tc::mbar_arrive(&sb_full[nh * 4 + (chunk >> 1)]);
+                tc::mbar_arrive(&sb_full[pending_box]);
+                pending_box = -1;
               }
+              // SB layout [CTA][sub-chunk = nh*8 + chunk][row][32 fp16]: lanes L / L+16 hold the two 32-byte halves of
+              // a row's 64 bytes, the warp's 16 h rows (then its 16 v rows) are one contiguous kilobyte
+              const size_t sub_base = ((size_t)(cta * 16 + nh * 8 + chunk) * kBM + box_row) * 32 + is_v * 16;
+              __half* sb_hi_p = p.sb_hi + sub_base;
+              __half* sb_lo_p = p.sb_lo + sub_base;
+              if (p.dbg_mode != 2) {
+                st_global_v8(sb_hi_p, hh);
+                st_global_v8(sb_lo_p, hl);
+                st_global_v8(sb_hi_p + 16 * 32, vh);
+                st_global_v8(sb_lo_p + 16 * 32, vl);
+              }
+              if (chunk & 1) pending_box = nh * 4 + (chunk >> 1);
             }
           }
+        }
+        if (!layer2) {
+          // hand the accumulator back first (below), the last box of the item is published right after
+        }
+        if (p.debug && etid == 0) {
+          const long long ec2 = clock64();
+          p.debug[cta * 24 + 8 + grp * 8 + sub] += ec1 - ec0;          // wait for the accumulator, per item kind
+          p.debug[cta * 24 + 8 + grp * 8 + 4 + sub] += ec2 - ec1;      // chunk loop, per item kind
         }
         // the accumulator is drained: hand it back to the MMA issuer (leader's barrier, both CTAs arrive)
         tc::fence_before_sync();
         tc::mbar_arrive_cluster(tc::mapa_shared(&tempty[buf], 0));
+        if (pending_box >= 0) {                                    // last box of a layer-1 item
+          fence_proxy_async_all();
+          tc::mbar_arrive(&sb_full[pending_box]);
+          pending_box = -1;
+        }
         if (layer2) {
           // fused output layer: combine the two column halves of every point's lane pair, then the two n halves
 #pragma unroll
@@ -798,6 +860,8 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
           const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.W0 + 3 * j0) + j4);
           wl0[4 * j4] = w4.x; wl0[4 * j4 + 1] = w4.y; wl0[4 * j4 + 2] = w4.z; wl0[4 * j4 + 3] = w4.w;
         }
+        float g[8], bf[8];
+        int fr_loaded = -1;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           if (r == 2 && kc > 0) {
@@ -806,14 +870,18 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
             fence_proxy_async_all();
             tc::mbar_arrive(&sa_full[kc - 1]);
           }
-          const float4* g4p = reinterpret_cast<const float4*>(p.gate + (size_t)fr[r] * p.ld_hyper + j0);
-          const float4* b4p = reinterpret_cast<const float4*>(p.biasf + (size_t)fr[r] * p.ld_hyper + j0);
-          float g[8], bf[8];
+          // gate / bias of this channel group: the same for every point of a frame, so they are fetched once per
+          // k-chunk and only re-fetched for a point of another frame (tiles straddle frames when P % 64 != 0)
+          if (r == 0 || fr[r] != fr_loaded) {
+            const float4* g4p = reinterpret_cast<const float4*>(p.gate + (size_t)fr[r] * p.ld_hyper + j0);
+            const float4* b4p = reinterpret_cast<const float4*>(p.biasf + (size_t)fr[r] * p.ld_hyper + j0);
 #pragma unroll
-          for (int j4 = 0; j4 < 2; ++j4) {
-            const float4 a = g4p[j4], b = b4p[j4];
-            g[4 * j4] = a.x; g[4 * j4 + 1] = a.y; g[4 * j4 + 2] = a.z; g[4 * j4 + 3] = a.w;
-            bf[4 * j4] = b.x; bf[4 * j4 + 1] = b.y; bf[4 * j4 + 2] = b.z; bf[4 * j4 + 3] = b.w;
+            for (int j4 = 0; j4 < 2; ++j4) {
+              const float4 a = g4p[j4], b = b4p[j4];
+              g[4 * j4] = a.x; g[4 * j4 + 1] = a.y; g[4 * j4 + 2] = a.z; g[4 * j4 + 3] = a.w;
+              bf[4 * j4] = b.x; bf[4 * j4 + 1] = b.y; bf[4 * j4 + 2] = b.z; bf[4 * j4 + 3] = b.w;
+            }
+            fr_loaded = fr[r];
           }
           uint32_t hh[4], hl[4], vh[4], vl[4];
 #pragma unroll
@@ -847,7 +915,7 @@ cnf_fused_eval_kernel(const __grid_constant__ CUtensorMap tm_sa_hi, const __grid
       tc::mbar_arrive(&sa_full[7]);
     }
     if (range_max > 65504.f) atomicOr(p.range_flag, 1);
-    if (p.debug && threadIdx.x == 320) p.debug[cta * 8 + 7] = l0_wait;
+    if (p.debug && threadIdx.x == 320) p.debug[cta * 24 + 7] = l0_wait;
   }
   tc::fence_before_sync();
   tc::cluster_sync_all();
@@ -913,8 +981,11 @@ int make_plan(Plan& plan, const Weights& w, __half* a_hi, __half* a_lo, __half* 
     plan.sb_hi = sb_hi; plan.sb_lo = sb_lo;
     ok &= caspr_make_tmap_f16(&plan.tm_sa[0], plan.sa_hi, (uint64_t)fused_grid * 128, 512, kBM);
     ok &= caspr_make_tmap_f16(&plan.tm_sa[1], plan.sa_lo, (uint64_t)fused_grid * 128, 512, kBM);
-    ok &= caspr_make_tmap_f16(&plan.tm_sb[0], sb_hi, (uint64_t)fused_grid * 128, 512, kBM);
-    ok &= caspr_make_tmap_f16(&plan.tm_sb[1], sb_lo, (uint64_t)fused_grid * 128, 512, kBM);
+    // SB is stored as [CTA][16 sub-chunks of 32 columns][128 rows][32 fp16]: an epilogue warp's 16 rows of a 32-column
+    // chunk are ONE contiguous kilobyte (8 full lines per store instruction instead of 32 partial ones); TMA brings a
+    // sub-chunk back as a [128][32] box with the 64-byte swizzle
+    ok &= caspr_make_tmap_f16_box32(&plan.tm_sb[0], sb_hi, (uint64_t)fused_grid * 16 * 128, 32, kBM);
+    ok &= caspr_make_tmap_f16_box32(&plan.tm_sb[1], sb_lo, (uint64_t)fused_grid * 16 * 128, 32, kBM);
     plan.fused_grid = fused_grid;
   }
   if (!ok) return CASPR_ELAUNCH;
@@ -949,14 +1020,16 @@ int enqueue_fused(const Plan& plan, const float4* y0, const float4* kbuf, size_t
   p.ld_hyper = ld_hyper; p.n = n; p.P = P; p.stage = stage; p.reverse = reverse; p.n_tiles = (n + 63) / 64; p.st = st;
   p.kout = kout; p.range_flag = range_flag; p.sa_hi = plan.sa_hi; p.sa_lo = plan.sa_lo; p.sb_hi = plan.sb_hi; p.sb_lo = plan.sb_lo;
   p.debug = nullptr;
+  p.dbg_mode = 0;
   {
     // CASPR_CNF_FUSED_DEBUG=1: cycle counters of the producer / MMA threads of the LAST launch, printed at exit by
     // tools/fused_debug.py through caspr_cnf_fused_debug_read
     static int dbg = -1;
-    if (dbg < 0) { const char* e2 = getenv("CASPR_CNF_FUSED_DEBUG"); dbg = (e2 && e2[0] == '1') ? 1 : 0; }
+    if (dbg < 0) { const char* e2 = getenv("CASPR_CNF_FUSED_DEBUG"); dbg = (e2 && e2[0] >= '1' && e2[0] <= '9') ? e2[0] - '0' : 0; }
+    p.dbg_mode = dbg;
     if (dbg) {
-      if (!g_debug_buf && cudaMalloc(&g_debug_buf, 148 * 8 * sizeof(long long)) != cudaSuccess) return CASPR_ELAUNCH;
-      cudaMemsetAsync(g_debug_buf, 0, 148 * 8 * sizeof(long long), s);
+      if (!g_debug_buf && cudaMalloc(&g_debug_buf, 148 * 24 * sizeof(long long)) != cudaSuccess) return CASPR_ELAUNCH;
+      cudaMemsetAsync(g_debug_buf, 0, 148 * 24 * sizeof(long long), s);
       p.debug = g_debug_buf;
     }
   }

@@ -206,6 +206,16 @@ __device__ __forceinline__ uint64_t make_desc_k128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// Same for a K-major operand tile stored with the 64-byte swizzle: rows of 32 fp16 = 64 B, 8-row swizzle atoms of 512 B
+// (SBO), layout SWIZZLE_64B (4).  One UMMA_K (16 fp16 = 32 B) inside the atom adds 2 to the start-address field.
+__device__ __forceinline__ uint64_t make_desc_k64(uint32_t smem_addr) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
 // Instruction descriptor, kind::f16: fp16 A and B (format 0), fp32 accumulator, K-major A and B.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

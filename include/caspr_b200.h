@@ -412,7 +412,7 @@ int caspr_emd(const float* xyz1, const float* xyz2, int B, int n, int m, float* 
               size_t workspace_bytes, void* stream);
 
 /* Profiling aid for the fused CNF evaluation kernel (CASPR_CNF_FUSED_DEBUG=1): per-CTA cycle counters of its TMA
- * producer and MMA threads for the last launch, 8 counters per CTA (see csrc/cnf.cu); synchronises the device. */
+ * producer and MMA threads for the last launch, 24 counters per CTA (see csrc/cnf.cu); synchronises the device. */
 int caspr_cnf_fused_debug_read(long long* out, int count);
 
 /* Correspondence-RANSAC rigid pose (reference utils/evaluations.py:360-380: open3d
