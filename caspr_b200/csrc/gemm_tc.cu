@@ -215,6 +215,12 @@ struct LinearEpilogue {
   int ldy;
   int rows, cout, act_out;
   int vec_ok;
+  // use_tma: the fp32 rows leave through shared memory and TMA (full 128-byte lines; the direct path issues eight
+  // 16-byte stores per thread and chunk to 32 different lines each, which made the epilogue LSU-bound)
+  int use_tma;
+  uint8_t* stg;
+  const CUtensorMap* tm_y;
+  int etid, m_tile_cur, box_row, n_store;
   // optional GroupNorm statistics of the OUTPUT (before any normalisation): per (sample, group) sum and sum
   // of squares accumulated in fp64; requires rows_per_sample % 32 == 0 so a warp never straddles samples
   double* stats;
@@ -224,9 +230,12 @@ struct LinearEpilogue {
   int col0;
   float inv;
 
-  __device__ __forceinline__ void setup(uint8_t*, const CUtensorMap*, const CUtensorMap*, int) {}
+  __device__ __forceinline__ void setup(uint8_t* staging, const CUtensorMap* o_hi, const CUtensorMap*, int epi_tid) {
+    stg = staging; tm_y = o_hi; etid = epi_tid; n_store = 0;
+  }
   __device__ __forceinline__ void tile_begin(int m_tile, int n_tile, int q, int lane) {
     if (stats && st_live) flush_stats();               // statistics of the previous tile
+    m_tile_cur = m_tile; box_row = q * 32 + lane;
     row = (long long)m_tile * kBM + q * 32 + lane;
     col0 = n_tile * kBN;
     inv = x_inv[row];       // planes are padded to whole tiles, so the index is always valid
@@ -279,11 +288,29 @@ struct LinearEpilogue {
         st_s = s1; st_q = q1; ++st_g; st_next += st_cpg;
       }
     }
-    if (!row_ok) return;
     if (act_out == CASPR_ACT_RELU) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
     }
+    if (use_tma) {
+      // two staging buffers of [128 rows][128 B] (128-byte swizzle); rows / columns beyond the matrix are clipped by TMA
+      uint8_t* buf = stg + (n_store & 1) * (kBM * 128);
+      if (etid == 0) tc::tma_store_wait_read_but_one();            // the store issued two chunks ago has left `buf`
+      tc::named_bar_sync(1, 128);
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4)
+        *reinterpret_cast<float4*>(buf + box_row * 128 + ((j4 ^ (box_row & 7)) << 4)) =
+            make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+      tc::fence_proxy_async_smem();
+      tc::named_bar_sync(1, 128);
+      if (etid == 0) {
+        tc::tma_store_2d(tm_y, buf, c, m_tile_cur * kBM);
+        tc::tma_store_commit();
+      }
+      ++n_store;
+      return;
+    }
+    if (!row_ok) return;
     float* y = Y + row * ldy + c;
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4)
@@ -305,6 +332,7 @@ struct LinearEpilogue {
   }
   __device__ __forceinline__ void finish() {
     if (stats && st_live) flush_stats();
+    if (use_tma && etid == 0) tc::tma_store_wait_all();
   }
 };
 
@@ -705,18 +733,31 @@ struct BallNormEpilogue {
         if (row_ok) {
           __half* ph = out_hi + row * ld_out + col0 + c;
           __half* pl = out_lo + row * ld_out + col0 + c;
+          uint32_t h[kChunk / 2], lo2[kChunk / 2];
 #pragma unroll
-          for (int j8 = 0; j8 < kChunk / 8; ++j8) {
-            uint32_t h[4], lo4[4];
+          for (int u = 0; u < kChunk / 2; ++u) {
+            const float a = fmaxf(x[2 * u], 0.f) * kBallPlaneScale;
+            const float b = fmaxf(x[2 * u + 1], 0.f) * kBallPlaneScale;
+            range_max = fmaxf(range_max, fmaxf(a, b));
+            tcg::split2(a, b, h[u], lo2[u]);
+          }
+          if (kChunk == 32) {
+            // 32-byte stores (st.global.v8.b32): half as many (instruction, line) pairs for the LSU as 16-byte stores
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float a = fmaxf(x[8 * j8 + 2 * u], 0.f) * kBallPlaneScale;
-              const float b = fmaxf(x[8 * j8 + 2 * u + 1], 0.f) * kBallPlaneScale;
-              range_max = fmaxf(range_max, fmaxf(a, b));
-              tcg::split2(a, b, h[u], lo4[u]);
+            for (int j16 = 0; j16 < kChunk / 16; ++j16) {
+              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ph + 16 * j16),
+                           "r"(h[8 * j16]), "r"(h[8 * j16 + 1]), "r"(h[8 * j16 + 2]), "r"(h[8 * j16 + 3]),
+                           "r"(h[8 * j16 + 4]), "r"(h[8 * j16 + 5]), "r"(h[8 * j16 + 6]), "r"(h[8 * j16 + 7]) : "memory");
+              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(pl + 16 * j16),
+                           "r"(lo2[8 * j16]), "r"(lo2[8 * j16 + 1]), "r"(lo2[8 * j16 + 2]), "r"(lo2[8 * j16 + 3]),
+                           "r"(lo2[8 * j16 + 4]), "r"(lo2[8 * j16 + 5]), "r"(lo2[8 * j16 + 6]), "r"(lo2[8 * j16 + 7]) : "memory");
             }
-            *reinterpret_cast<uint4*>(ph + 8 * j8) = make_uint4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<uint4*>(pl + 8 * j8) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
+          } else {
+#pragma unroll
+            for (int j8 = 0; j8 < kChunk / 8; ++j8) {
+              *reinterpret_cast<uint4*>(ph + 8 * j8) = make_uint4(h[4 * j8], h[4 * j8 + 1], h[4 * j8 + 2], h[4 * j8 + 3]);
+              *reinterpret_cast<uint4*>(pl + 8 * j8) = make_uint4(lo2[4 * j8], lo2[4 * j8 + 1], lo2[4 * j8 + 2], lo2[4 * j8 + 3]);
+            }
           }
         }
       }
@@ -964,9 +1005,16 @@ extern "C" int caspr_linear_tc(const float* X, int ldx, const float* W, int ldw,
   }
   epi.vec_ok = (ldy % 4 == 0) && (((uintptr_t)Y & 15) == 0) && (!bias || ((uintptr_t)bias & 15) == 0);
   const int m_tiles = (int)(l.rows_pad / kBM), n_tiles = l.cout_pad / kBN;
+  // fp32 output through TMA (full lines); CASPR_LINEAR_TMA_STORE=0 keeps the direct 16-byte stores
+  CUtensorMap tm_y = tm_xhi;
+  {
+    static int want = -1;
+    if (want < 0) { const char* e = getenv("CASPR_LINEAR_TMA_STORE"); want = (e && e[0] == '0') ? 0 : 1; }
+    epi.use_tma = want && caspr_make_tmap_f32_box32(&tm_y, Y, (uint64_t)rows, (uint64_t)Cout, (uint64_t)ldy, kBM);
+  }
   caspr_prof_begin(CASPR_PROF_LINEAR, s);
   CASPR_COUNT();
-  const cudaError_t lerr = tcg::launch_gemm(tm_xhi, tm_xlo, tm_whi, tm_wlo, tm_xhi, tm_xlo, 0, m_tiles, n_tiles,
+  const cudaError_t lerr = tcg::launch_gemm(tm_xhi, tm_xlo, tm_whi, tm_wlo, tm_y, tm_xlo, 0, m_tiles, n_tiles,
                                             l.k_pad / kBK, nullptr, epi, 1, num_sms, s);
   caspr_prof_end(CASPR_PROF_LINEAR, s);
   if (lerr != cudaSuccess) return CASPR_ELAUNCH;

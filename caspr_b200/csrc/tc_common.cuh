@@ -64,6 +64,8 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // the smem source of all committed stores has been read (the buffer may be overwritten)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// the smem source of all committed stores but the most recent one has been read
+__device__ __forceinline__ void tma_store_wait_read_but_one() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 // all committed stores but the most recent one are complete
 __device__ __forceinline__ void tma_store_wait_all_but_one() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
 // all committed stores are complete
@@ -268,5 +270,20 @@ static inline bool caspr_make_tmap_f16_box32(CUtensorMap* m, const void* base, u
   cuuint32_t estr[2] = {1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// fp32 row-major matrix [rows][cols] with leading dimension ld (elements), box = [box_rows][32 cols] (128-byte rows)
+// with the 128-byte swizzle: TMA-store map of epilogues that stage 32 fp32 columns at a time
+static inline bool caspr_make_tmap_f32_box32(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                                             uint32_t box_rows) {
+  caspr_encode_tiled_fn fn = caspr_get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 4};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
