@@ -577,10 +577,11 @@ def engine(request, ops):
 
 
 @pytest.mark.parametrize('eng', ENGINES)
-@pytest.mark.parametrize('frames,pts', [(3, 200), (2, 64), (5, 1000)])
+@pytest.mark.parametrize('frames,pts', [(3, 200), (2, 64), (5, 1000), (1, 10), (3, 100), (7, 777)])
 def test_cnf_feval_matches_oracle(case, ops, eng, frames, pts):
     """One dynamics evaluation (dy, -div): forward-mode divergence vs the reference's autograd VJP.
-    Ragged sizes exercise partial 64-point tiles and tiles straddling frames."""
+    Ragged sizes exercise partial 64-point tiles, tiles straddling frames, a single tile (the second CTA of the pair idles)
+    and odd tile counts (fused kernel: the last CTA pair has one live tile)."""
     _, gold, model, oracle, _, _ = case
     g = torch.Generator().manual_seed(3)
     y = torch.randn(frames, pts, 3, generator=g)
