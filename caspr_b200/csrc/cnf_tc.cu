@@ -11,15 +11,15 @@
 // into fp16 hi/lo planes scaled by a power of two chosen from max|W| (scales are undone exactly in
 // the epilogue through the pre-scaled gate).
 //
-// Kernel: persistent, warp-specialised, one CTA per SM (192 threads):
-//   warp 0   TMA producer  : per 64-wide k-chunk A_hi, A_lo (128x64) and W_hi, W_lo (256x64) tiles,
-//                            128-byte swizzle, 2-stage mbarrier ring (96 KB per stage)
-//   warp 1   MMA issuer    : 3 x tcgen05.mma (M=128, N=256, K=16) per k-step into one of two
-//                            256-column TMEM accumulators; tcgen05.commit frees the smem stage /
-//                            publishes the accumulator
-//   warps 2-5 epilogue     : tcgen05.ld, ConcatSquash gate/bias, softplus and the tangent's chain
-//                            rule, split to fp16 hi/lo (or fp32 for the last layer's input), stores
-// so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Two ways to run one dynamics evaluation on this layout:
+//   * cnf_fused_eval_kernel (default, further down): ONE launch for layer 0, both H x H layers, the output layer and
+//     the divergence; persistent CTA pairs (cta_group::2), the planes between the layers stay in an L2-resident per-CTA
+//     scratch.
+//   * the round-1 four-kernel path (CASPR_CNF_FUSED=0): cnf_tc_layer0_kernel -> two launches of the shared GEMM skeleton
+//     (tc_gemm.cuh) with CnfEpilogue<false> / CnfEpilogue<true> -> cnf_tc_last_finish_kernel; the planes make a round
+//     trip through HBM between the launches.  The skeleton is persistent and warp-specialised: TMA producer warp, MMA
+//     warp (3 x tcgen05.mma per k-step into one of two 256-column TMEM accumulators), four epilogue warps, so the
+//     epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
 #include "dopri5.cuh"
 #include "cnf_state.cuh"

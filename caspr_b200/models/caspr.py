@@ -145,6 +145,14 @@ class CaSPR(nn.Module):
         """caspr.py:269-308: -> (y, logp_y, x_rec, tnocs_pred)."""
         B, T, N, _ = x.size()
         z0, tnocs_pred = self.encode(x)
+        if y is None and sample_contours is None:
+            # The base samples come from the CPU generator (models/utils.py:25).  The encoder kernels have only been
+            # enqueued at this point and nothing else touches the generator before decode, so drawing here yields the
+            # reference's values while the GPU is busy encoding instead of idling during the draw.
+            Tq = T if timestamps is None else int(timestamps.numel())
+            samp_batch = B if constant_in_time else B * Tq
+            y = sample_gaussian((samp_batch, num_points, self.cnf_args.input_dim), truncate_std, device=x.device)
+            truncate_std = None
         if timestamps is None:
             all_times = x[:, :, 0, 3] / max_timestamp
         else:

@@ -20,9 +20,17 @@ def truncated_normal(tensor, mean=0, std=1, trunc_std=2):
 
 
 def sample_gaussian(size, truncate_std=None, device=None):
-    """utils.py:24-29: drawn with the CPU generator, then moved (parity with the reference's RNG stream)."""
-    y = torch.randn(*size).float()
-    y = y if device is None else y.to(device)
+    """utils.py:24-29: drawn with the CPU generator, then moved (parity with the reference's RNG stream).
+
+    The draw goes into pinned memory (`empty(pin_memory=True).normal_()` consumes the CPU generator exactly like
+    `torch.randn`) so that the host-to-device copy is asynchronous."""
+    dev = torch.device(device) if device is not None else None
+    if dev is not None and dev.type == 'cuda':
+        y = torch.empty(*size, dtype=torch.float32, pin_memory=True).normal_()
+        y = y.to(dev, non_blocking=True)
+    else:
+        y = torch.randn(*size).float()
+        y = y if dev is None else y.to(dev)
     if truncate_std is not None:
         truncated_normal(y, mean=0, std=1, trunc_std=truncate_std)
     return y
