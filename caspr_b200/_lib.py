@@ -69,6 +69,11 @@ SIGNATURES = {
     'caspr_sa_fused': (c_int, [_P, _P, _P, c_int, c_int, _P, c_int, c_int, c_int, c_int,
                                _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_int,
                                c_float, _P, c_int, _P]),
+    'caspr_sa_mma_supported': (c_int, [c_int, c_int, c_int, c_int, c_int]),
+    'caspr_sa_absmax': (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    'caspr_sa_mma': (c_int, [_P, _P, _P, c_int, c_int, _P, c_int, c_int, c_int, c_int,
+                             _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_int,
+                             c_float, _P, _P, c_int, _P]),
     'caspr_linear_tc_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'caspr_linear_tc_weight_bytes': (c_size_t, [c_int, c_int]),
     'caspr_linear_tc_prepare_weights': (c_int, [_P, c_int, c_int, c_int, _P, c_size_t, _P]),
@@ -77,6 +82,8 @@ SIGNATURES = {
                                 POINTER(GnFold), POINTER(GnStats), c_int, _P, c_size_t, _P]),
     'caspr_groupnorm': (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_float, c_int, c_int, _P,
                                 c_int, _P, c_int, _P]),
+    'caspr_groupnorm_project': (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_float, _P, c_int, _P, _P, _P,
+                                        c_int, c_int, _P, c_int, _P]),
     'caspr_augment_xyz': (c_int, [_P, c_int, _P, _P]),
     'caspr_strip_time': (c_int, [_P, c_int, _P, _P]),
     'caspr_broadcast_rows': (c_int, [_P, c_int, c_int, c_int, c_int, _P, c_int, _P]),

@@ -425,11 +425,22 @@ groupnorm_apply_kernel(float* __restrict__ X, int ldx, int rows_per_sample, int 
 // on the row, so statistics accumulate in registers and every load / store is a full 128-byte line.
 constexpr int kGnMaxQuadsPerLane = 16;          // C <= 2048
 
+// PROJ: the normalised row additionally feeds a narrow linear layer (<= 4 outputs, e.g. the encoder head's
+// 1600 -> 4 T-NOCS regression, tpointnet2.py:108-113) while it is still in registers: out = act(W . relu(v) + b),
+// one warp reduction per row, so the normalised activations are never written back nor read a second time.
+struct GnProject {
+  const float* W;        // (P, C) row-major, 16-byte aligned
+  const float* bias;     // (P) or nullptr
+  float* out;            // rows x ld_out
+  int P, ld_out, act;
+};
+
+template <bool PROJ>
 __global__ void __launch_bounds__(256)
 groupnorm_apply_vec_kernel(float* __restrict__ X, int ldx, int rows_per_sample, int C, int groups,
                            const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                            int relu, int write_back, const double* __restrict__ stats,
-                           unsigned* __restrict__ maxout_ordered, int ld_max) {
+                           unsigned* __restrict__ maxout_ordered, int ld_max, GnProject pj) {
   const int sample = blockIdx.y;
   const int r0 = blockIdx.x * kGnRowsPerCta;
   const int r1 = min(rows_per_sample, r0 + kGnRowsPerCta);
@@ -462,8 +473,10 @@ groupnorm_apply_vec_kernel(float* __restrict__ X, int ldx, int rows_per_sample, 
   }
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
+  const float4* w4 = reinterpret_cast<const float4*>(pj.W);
   for (int r = r0 + warp; r < r1; r += 8) {
     float4* row = reinterpret_cast<float4*>(base + (size_t)r * ldx);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < kGnMaxQuadsPerLane; ++k) {
       const int qi = lane + 32 * k;
@@ -478,6 +491,28 @@ groupnorm_apply_vec_kernel(float* __restrict__ X, int ldx, int rows_per_sample, 
         if (write_back) row[qi] = v;
         mx[k].x = fmaxf(mx[k].x, v.x); mx[k].y = fmaxf(mx[k].y, v.y);
         mx[k].z = fmaxf(mx[k].z, v.z); mx[k].w = fmaxf(mx[k].w, v.w);
+        if (PROJ) {
+          const float px = fmaxf(v.x, 0.f), py = fmaxf(v.y, 0.f), pz = fmaxf(v.z, 0.f), pw = fmaxf(v.w, 0.f);
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            if (o < pj.P) {
+              const float4 w = __ldg(w4 + (size_t)o * Q + qi);
+              acc[o] = fmaf(px, w.x, fmaf(py, w.y, fmaf(pz, w.z, fmaf(pw, w.w, acc[o]))));
+            }
+          }
+        }
+      }
+    }
+    if (PROJ) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], d);
+      }
+      if (lane < pj.P) {
+        float t = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+        if (pj.bias) t += __ldg(pj.bias + lane);
+        pj.out[((size_t)sample * rows_per_sample + r) * pj.ld_out + lane] = apply_act(t, pj.act);
       }
     }
   }
@@ -648,12 +683,42 @@ extern "C" int caspr_groupnorm(float* X, int ldx, int samples, int rows_per_samp
     CASPR_CHECK_LAUNCH();
   }
   if (vec) {
-    CASPR_COUNT(); groupnorm_apply_vec_kernel<<<grid, 256, 0, s>>>(X, ldx, rows_per_sample, C, groups, gamma, beta, eps,
-                                                                   relu, write_back, stats_ws, mo, ld_max);
+    CASPR_COUNT(); groupnorm_apply_vec_kernel<false><<<grid, 256, 0, s>>>(X, ldx, rows_per_sample, C, groups, gamma, beta,
+                                                                          eps, relu, write_back, stats_ws, mo, ld_max,
+                                                                          GnProject{});
   } else {
     CASPR_COUNT(); groupnorm_apply_kernel<<<grid, 256, 0, s>>>(X, ldx, rows_per_sample, C, groups, gamma, beta, eps, relu,
                                                write_back, stats_ws, mo, ld_max);
   }
+  CASPR_CHECK_LAUNCH();
+  if (mo) {
+    CASPR_COUNT(); decode_ordered_kernel<<<ceil_div(samples * C, 256), 256, 0, s>>>(mo, samples, C, ld_max);
+    CASPR_CHECK_LAUNCH();
+  }
+  return CASPR_OK;
+}
+
+extern "C" int caspr_groupnorm_project(const float* X, int ldx, int samples, int rows_per_sample, int C, int groups,
+                                       const float* gamma, const float* beta, float eps, float* maxout, int ld_max,
+                                       const double* stats, const float* W, const float* bias, int P, int act,
+                                       float* out, int ld_out, void* stream) {
+  CASPR_REQUIRE(X && gamma && beta && stats && W && out && samples > 0 && rows_per_sample > 0 && C > 0);
+  CASPR_REQUIRE(groups > 0 && groups <= 64 && C % groups == 0 && ldx >= C && P >= 1 && P <= 4 && ld_out >= P);
+  CASPR_REQUIRE(!maxout || ld_max >= C);
+  CASPR_REQUIRE((C / groups) % 4 == 0 && ldx % 4 == 0 && C <= 128 * kGnMaxQuadsPerLane);
+  CASPR_REQUIRE((((uintptr_t)X | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)W) & 15) == 0);
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid(ceil_div(rows_per_sample, kGnRowsPerCta), samples);
+  unsigned* mo = reinterpret_cast<unsigned*>(maxout);
+  if (mo) {
+    CASPR_COUNT(); fill_u32_kernel<<<ceil_div(samples * C, 256), 256, 0, s>>>(mo, samples, C, ld_max, 0u);
+    CASPR_CHECK_LAUNCH();
+  }
+  GnProject pj;
+  pj.W = W; pj.bias = bias; pj.out = out; pj.P = P; pj.ld_out = ld_out; pj.act = act;
+  CASPR_COUNT(); groupnorm_apply_vec_kernel<true><<<grid, 256, 0, s>>>(const_cast<float*>(X), ldx, rows_per_sample, C,
+                                                                       groups, gamma, beta, eps, 0, 0, stats, mo,
+                                                                       ld_max, pj);
   CASPR_CHECK_LAUNCH();
   if (mo) {
     CASPR_COUNT(); decode_ordered_kernel<<<ceil_div(samples * C, 256), 256, 0, s>>>(mo, samples, C, ld_max);

@@ -110,9 +110,17 @@ class PointNet2SetAbstraction(nn.Module):
             trace['ball_idx'].append(bq)
         out = torch.empty(Bp * M, self.get_num_features_out(), dtype=torch.float32, device=xyz.device)
         off = 0
+        absmax = None
         for s, (grouper, pointnet) in enumerate(zip(self.grouper_modules, self.pointnet_modules)):
             widths = [c.weight.shape[0] for c in pointnet.conv_layers]
-            if ops.sa_fused_supported(grouper.num_samples, self.pointnet_in_channels, widths):
+            if features is not None and ops.sa_mma_supported(grouper.num_samples, self.pointnet_in_channels, widths):
+                # levels 1-2 on the tensor cores: gather + three per-ball layers + max in one kernel, activations in
+                # mma fragments; one operand bound per level serves both scales
+                if absmax is None:
+                    absmax = ops.sa_absmax(xyz, features)
+                ops.sa_mma(xyz, new_xyz, features, bq[s], pointnet.conv_layers, pointnet.bn_layers,
+                           out[:, off:off + pointnet.feat_size], absmax)
+            elif ops.sa_fused_supported(grouper.num_samples, self.pointnet_in_channels, widths):
                 # levels 1-2: gather + three per-ball layers + max in ONE kernel, activations stay in registers
                 ops.sa_fused(xyz, new_xyz, features, bq[s], pointnet.conv_layers, pointnet.bn_layers,
                              out[:, off:off + pointnet.feat_size])

@@ -173,12 +173,18 @@ class TPointNet2(nn.Module):
             h2, st2 = ops.conv_gn_relu_conv(feat, self.conv1, self.bn1, self.conv2, B, T * N, 16,
                                             out=feat if self.latent_feat_size == feat.shape[1] else None, stats_b=True)
         z0 = torch.empty(B, self.latent_feat_size, dtype=torch.float32, device=x.device)
-        ops.groupnorm(h2, B, T * N, 16, self.bn2.weight, self.bn2.bias, relu=False, write_back=self.regress_tnocs,
-                      maxout=z0, stats=st2)
         tnocs = None
-        if self.regress_tnocs:
-            t = ops.linear(h2, self.conv3.weight, self.conv3.bias, act_in=ops.ACT_RELU, act_out=ops.ACT_SIGMOID)
-            tnocs = t[:, :4].reshape(B, T, N, 4)
+        if self.regress_tnocs and st2 is not None and os.environ.get('CASPR_HEAD_PROJECT', '1') != '0':
+            # bn2 + max-pool + conv3 + sigmoid in one read of h2 (no normalised write-back, no second pass)
+            t = ops.groupnorm_project(h2, B, T * N, 16, self.bn2.weight, self.bn2.bias, st2, self.conv3.weight,
+                                      self.conv3.bias, eps=self.bn2.eps, maxout=z0, act=ops.ACT_SIGMOID)
+            tnocs = t.view(B, T, N, 4)
+        else:
+            ops.groupnorm(h2, B, T * N, 16, self.bn2.weight, self.bn2.bias, relu=False,
+                          write_back=self.regress_tnocs, maxout=z0, stats=st2)
+            if self.regress_tnocs:
+                t = ops.linear(h2, self.conv3.weight, self.conv3.bias, act_in=ops.ACT_RELU, act_out=ops.ACT_SIGMOID)
+                tnocs = t[:, :4].reshape(B, T, N, 4)
         return z0, tnocs
 
     def loss(self, outputs, gt):

@@ -11,6 +11,7 @@ Conv1d/GroupNorm calls around them, and torchdiffeq's odeint (latent_ode_model.p
 cnf.py:102-119).
 """
 import ctypes
+import os
 import weakref
 
 import torch
@@ -351,6 +352,7 @@ def sa_mlp_tc(rows, ns, convs, norms, out):
 
 
 SA_FUSED = True                 # module-wide switch (accuracy / timing studies): fused set-abstraction scale kernel
+SA_MMA = os.environ.get('CASPR_SA_MMA', '1') != '0'     # its tensor-core (mma.sync) version, SA levels 1-2
 
 
 def sa_fused_supported(ns, cin, widths):
@@ -379,6 +381,41 @@ def sa_fused(xyz, new_xyz, feat, idx, convs, norms, out):
     return out
 
 
+def sa_mma_supported(ns, cin, widths):
+    return SA_MMA and len(widths) == 3 and bool(lib.caspr_sa_mma_supported(ns, cin, *widths))
+
+
+def sa_absmax(xyz, feat):
+    """Device scalar max(|feat|, 2 max|xyz|): an upper bound of every entry of the gathered rows of a set-abstraction
+    level, shared by its two scales (operand scale of `sa_mma`)."""
+    B, N, _ = xyz.shape
+    assert xyz.is_contiguous() and feat.dim() == 3 and feat.stride(2) == 1 and feat.stride(0) == N * feat.stride(1)
+    out = torch.empty(1, dtype=torch.float32, device=xyz.device)
+    _count('sa_absmax')
+    check(lib.caspr_sa_absmax(_p(xyz), _p(feat), feat.stride(1), feat.shape[2], B, N, _p(out), _stream()),
+          'caspr_sa_absmax')
+    return out
+
+
+def sa_mma(xyz, new_xyz, feat, idx, convs, norms, out, absmax=None):
+    """`sa_fused` with the three per-ball layers on the tensor cores (mma.sync, fp16x3 split); same arguments plus
+    the operand bound of `sa_absmax`."""
+    B, N, _ = xyz.shape
+    M, ns = idx.shape[1], idx.shape[2]
+    assert feat.dim() == 3 and feat.stride(2) == 1 and feat.stride(0) == N * feat.stride(1)
+    C, ld_feat = feat.shape[2], feat.stride(1)
+    out, ld_out = _rows2d(out, 'out')
+    args = []
+    for conv, gn in zip(convs, norms):
+        w = conv.weight.reshape(conv.weight.shape[0], conv.weight.shape[1])
+        assert w.is_contiguous() and w.dtype == torch.float32
+        args += [_p(w), _p(conv.bias), _p(gn.weight), _p(gn.bias), w.shape[0]]
+    _count('sa_mma')
+    check(lib.caspr_sa_mma(_p(xyz), _p(new_xyz), _p(feat), ld_feat, C, _p(idx), B, N, M, ns, *args,
+                           float(norms[0].eps), _p(absmax), _p(out), ld_out, _stream()), 'caspr_sa_mma')
+    return out
+
+
 def groupnorm(x, samples, rows_per_sample, groups, gamma, beta, eps=1e-5, relu=False, write_back=True,
               maxout=None, stats=None):
     """In-place GroupNorm(groups, C) over `samples` blocks of consecutive rows, fused ReLU / max-pool.
@@ -401,6 +438,29 @@ def groupnorm(x, samples, rows_per_sample, groups, gamma, beta, eps=1e-5, relu=F
                               int(relu), int(write_back), _p(maxout), ld_max, _p(stats), int(ready), _stream()),
           'caspr_groupnorm')
     return x
+
+
+def groupnorm_project(x, samples, rows_per_sample, groups, gamma, beta, stats, weight, bias, eps=1e-5, maxout=None,
+                      act=ACT_NONE):
+    """GroupNorm (statistics from the producing GEMM) -> max over each sample's rows (pre-ReLU) and
+    act(weight . relu(gn(x)) + bias) for a layer of <= 4 outputs, in one pass that leaves x untouched
+    (tpointnet2.py:104-113: bn2, the max-pool that yields z0, conv3 + sigmoid).  Returns (rows, P)."""
+    x, ldx = _rows2d(x, 'x')
+    C = x.shape[1]
+    assert x.shape[0] == samples * rows_per_sample
+    w2d = weight.reshape(weight.shape[0], -1)
+    _f32(w2d, 'weight')
+    assert w2d.shape[1] == C and w2d.is_contiguous() and 1 <= w2d.shape[0] <= 4
+    ld_max = 0
+    if maxout is not None:
+        maxout, ld_max = _rows2d(maxout, 'maxout')
+        assert maxout.shape == (samples, C)
+    out = torch.empty(x.shape[0], w2d.shape[0], dtype=torch.float32, device=x.device)
+    _count('groupnorm_project')
+    check(lib.caspr_groupnorm_project(_p(x), ldx, samples, rows_per_sample, C, groups, _p(gamma), _p(beta), float(eps),
+                                      _p(maxout), ld_max, _p(stats), _p(w2d), _p(bias), w2d.shape[0], int(act),
+                                      _p(out), out.shape[1], _stream()), 'caspr_groupnorm_project')
+    return out
 
 
 def augment_xyz(x4):

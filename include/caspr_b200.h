@@ -140,6 +140,21 @@ int caspr_sa_fused(const float* xyz, const float* new_xyz, const float* feat, in
                    const float* W3, const float* b3, const float* g3, const float* e3, int C3,
                    float eps, float* out, int ld_out, void* stream);
 
+/* The same scale on the tensor cores (warp-level mma.sync m16n8k16, fp16 hi/lo 3-product split, fp32 accumulate; a
+ * warp owns a 32-row tile and keeps every activation in accumulator / operand fragments).  Shapes of
+ * caspr_sa_mma_supported: the four scales of SA levels 1-2 (Cin = 3 + C = 9 or 99).  in_absmax: device scalar
+ * >= every |entry| of the gathered rows (caspr_sa_absmax computes max(|feat|, 2 max|xyz|)), from which the operand
+ * scale is taken; NULL = unscaled.  Requires B*N*max(ld_feat,3) < 2^32. */
+int caspr_sa_mma_supported(int ns, int Cin, int C1, int C2, int C3);
+int caspr_sa_absmax(const float* xyz, const float* feat, int ld_feat, int C, int B, int N, float* absmax,
+                    void* stream);
+int caspr_sa_mma(const float* xyz, const float* new_xyz, const float* feat, int ld_feat, int C,
+                 const int32_t* idx, int B, int N, int M, int ns,
+                 const float* W1, const float* b1, const float* g1, const float* e1, int C1,
+                 const float* W2, const float* b2, const float* g2, const float* e2, int C2,
+                 const float* W3, const float* b3, const float* g3, const float* e3, int C3,
+                 float eps, const float* in_absmax, float* out, int ld_out, void* stream);
+
 /* Same contract on the tcgen05 tensor cores: 3-product fp16 split ("fp16x3",
  * X_hi.W_hi + X_lo.W_hi + X_hi.W_lo, fp32 accumulate in TMEM), operands scaled per call by powers of
  * two taken from max|X| and max|W| (undone exactly in the epilogue).  Meant for the large layers
@@ -187,6 +202,16 @@ int caspr_groupnorm(float* X, int ldx, int samples, int rows_per_sample, int C, 
                     const float* gamma, const float* beta, float eps, int relu,
                     int write_back, float* maxout, int ld_max, double* stats_ws, int stats_ready,
                     void* stream);
+
+/* The encoder head's tail in one pass (tpointnet2.py:104-113): GroupNorm with ready statistics (as above,
+ * stats_ready = 1, no ReLU, X left untouched), max over the rows of each sample into maxout (may be NULL), and a
+ * narrow linear layer on the ReLU of the normalised row while it is in registers:
+ *   out[row, 0..P) = act(W (P, C) . relu(gn(X[row])) + bias),  1 <= P <= 4, act = CASPR_ACT_*.
+ * Requires (C/groups) % 4 == 0, ldx % 4 == 0, C <= 2048 and 16-byte aligned X, gamma, beta, W. */
+int caspr_groupnorm_project(const float* X, int ldx, int samples, int rows_per_sample, int C, int groups,
+                            const float* gamma, const float* beta, float eps, float* maxout, int ld_max,
+                            const double* stats, const float* W, const float* bias, int P, int act,
+                            float* out, int ld_out, void* stream);
 
 /* tpointnet2.py:79-90: x (R,4) rows [x,y,z,t] -> out (R,9) rows [x,y,z,x2,y2,z2,xz,xy,yz]. */
 int caspr_augment_xyz(const float* x4, int rows, float* out9, void* stream);

@@ -229,6 +229,35 @@ def test_groupnorm_matches_torch(ops, samples, rps, C, relu):
     assert _rel(mx2, ref.max(2)[0]) < 1e-5
 
 
+@pytest.mark.parametrize('samples,rps,C,P', [(2, 1000, 1600, 4), (3, 77, 64, 1), (1, 5120, 1600, 4), (4, 130, 256, 3)])
+def test_groupnorm_project_matches_chain(ops, samples, rps, C, P):
+    """bn2 -> max-pool -> ReLU -> conv3 -> sigmoid of the encoder head in one pass (tpointnet2.py:104-113) vs torch fp64;
+    the input must come back untouched."""
+    g = torch.Generator().manual_seed(C + rps)
+    x = torch.randn(samples * rps, C, generator=g) * 2 + 0.5
+    gamma = torch.rand(C, generator=g) + 0.5
+    beta = torch.randn(C, generator=g) * 0.1
+    w = torch.randn(P, C, 1, generator=g) / C ** 0.5
+    b = torch.randn(P, generator=g) * 0.1
+    xin = x.view(samples, rps, C).transpose(1, 2).double()
+    ref = torch.nn.functional.group_norm(xin, 16, gamma.double(), beta.double(), eps=1e-5)
+    ref_t = torch.sigmoid(torch.nn.functional.conv1d(ref.relu(), w.double(), b.double()))       # (samples, P, rps)
+    ref_t = ref_t.transpose(1, 2).reshape(samples * rps, P)
+    xs = x.view(samples, rps, 16, C // 16).double()
+    stats = torch.stack([xs.sum((1, 3)), (xs * xs).sum((1, 3))], dim=-1).to(DEV).contiguous()     # (samples, 16, 2)
+    xd = x.to(DEV).clone()
+    mx = torch.empty(samples, C, device=DEV)
+    t = ops.groupnorm_project(xd, samples, rps, 16, gamma.to(DEV), beta.to(DEV), stats, w.to(DEV), b.to(DEV),
+                              maxout=mx, act=ops.ACT_SIGMOID)
+    assert t.shape == (samples * rps, P)
+    assert (t.cpu().double() - ref_t).abs().max() < 2e-6
+    assert _rel(mx, ref.max(2)[0]) < 1e-5
+    assert torch.equal(xd.cpu(), x)
+    t2 = ops.groupnorm_project(xd, samples, rps, 16, gamma.to(DEV), beta.to(DEV), stats, w.to(DEV), None)
+    ref_lin = torch.nn.functional.conv1d(ref.relu(), w.double()).transpose(1, 2).reshape(samples * rps, P)
+    assert _rel(t2, ref_lin) < 1e-5
+
+
 @pytest.mark.parametrize('balls,ns,cin,cout,relu', [(100, 16, 9, 16, True), (37, 32, 9, 32, True), (64, 32, 32, 64, False),
                                                      (9, 16, 99, 32, True), (200, 16, 16, 16, False)])
 def test_linear_gn_ball_fused(ops, balls, ns, cin, cout, relu):
@@ -293,6 +322,54 @@ def test_sa_fused_matches_unfused_reference(ops, ns, widths, C):
     # padded balls divide rounding noise by sqrt(eps) = 316 in BOTH implementations: 2e-4 instead of 2e-5
     assert _rel(out[:, 5:5 + widths[2]], ref) < 2e-4
     assert float(out[:, :5].abs().sum()) == 0 and float(out[:, 5 + widths[2]:].abs().sum()) == 0
+
+
+@pytest.mark.parametrize('ns,widths,C', [(16, (16, 16, 32), 6), (32, (32, 32, 64), 6), (16, (32, 32, 64), 96),
+                                        (32, (32, 32, 64), 96)])
+@pytest.mark.parametrize('scale', [1.0, 1e-3])
+def test_sa_mma_matches_unfused_reference(ops, ns, widths, C, scale):
+    """The tensor-core version of the fused set-abstraction scale (mma.sync fragments, fp16 hi/lo split) against the fp64
+    chain on the same ball-query indices: ragged ball count (partial 32-row tile), strided feature view, padded balls,
+    output into a column slice, and inputs 1000x smaller (the operand scale taken from `sa_absmax` keeps the split exact)."""
+    g = torch.Generator().manual_seed(ns + C)
+    B, N, M = 3, 333, 77
+    xyz = (torch.rand(B, N, 3, generator=g) * scale).to(DEV)
+    _, new_xyz = ops.fps(xyz, M)
+    idx, _ = ops.ball_query2(xyz, new_xyz, 0.12 * scale, ns, 0.5 * scale, 32)
+    wide = (torch.randn(B, N, C + 3, generator=g) * scale).to(DEV)
+    feat = wide[:, :, 3:]
+    cin = 3 + C
+    convs, norms = [], []
+    dims = [cin] + list(widths)
+    for i in range(3):
+        conv = torch.nn.Conv1d(dims[i], dims[i + 1], 1)
+        gn = torch.nn.GroupNorm(16, dims[i + 1])
+        with torch.no_grad():
+            if i == 0:
+                conv.weight.mul_(1.0 / scale)              # keep the layer-1 output (and its conditioning) O(1)
+            gn.weight.copy_(torch.rand(dims[i + 1], generator=g) + 0.5)
+            gn.bias.copy_(0.2 * torch.randn(dims[i + 1], generator=g))
+        convs.append(conv.to(DEV))
+        norms.append(gn.to(DEV))
+    assert ops.sa_mma_supported(ns, cin, list(widths))
+    out = torch.zeros(B * M, widths[2] + 10, device=DEV)
+    absmax = ops.sa_absmax(xyz, feat)
+    assert float(absmax) == max(float(feat.abs().max()), 2 * float(xyz.abs().max()))
+    ops.sa_mma(xyz, new_xyz, feat, idx, convs, norms, out[:, 4:4 + widths[2]], absmax)
+    rows = ops.group_points(xyz, new_xyz, feat, idx).double()
+    h = rows.view(B * M, ns, cin).transpose(1, 2)
+    for i in range(3):
+        h = torch.nn.functional.conv1d(h, convs[i].weight.double(), convs[i].bias.double())
+        h = torch.nn.functional.group_norm(h, 16, norms[i].weight.double(), norms[i].bias.double(), eps=1e-5)
+        if i < 2:
+            h = h.relu()
+    ref = h.max(2)[0]
+    assert _rel(out[:, 4:4 + widths[2]], ref) < 2e-4             # padded balls: rounding noise / sqrt(eps), as above
+    assert float(out[:, :4].abs().sum()) == 0 and float(out[:, 4 + widths[2]:].abs().sum()) == 0
+    # the SIMT kernel is the same function: the two must agree as closely as either agrees with fp64
+    out2 = torch.zeros(B * M, widths[2], device=DEV)
+    ops.sa_fused(xyz, new_xyz, feat, idx, convs, norms, out2)
+    assert _rel(out[:, 4:4 + widths[2]], out2) < 2e-4
 
 
 @pytest.mark.parametrize('ns,cin,widths', [(16, 131, (64, 64, 128)), (32, 131, (64, 96, 128)),
