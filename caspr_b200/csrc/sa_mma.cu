@@ -249,19 +249,29 @@ sa_mma_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, 
   const bool vec2 = (ld_feat % 2 == 0) && ((reinterpret_cast<uintptr_t>(feat) & 7) == 0);
   const bool out2 = (ld_out % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
 
-  for (long long wt = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wt < tiles; wt += warps) {
-    // the thread's four rows: tile row g + 8q, q = 0..3 (m-tile q>>1, fragment half q&1)
-    long long ballq[4];
-    unsigned srow[4];
+  // source row (b*N + idx) of the thread's four rows of tile wt_: tile row g + 8q, q = 0..3 (m-tile q>>1, half q&1)
+  auto gather_rows = [&](long long wt_, unsigned (&sr)[4]) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const long long rowid = wt * 32 + g + 8 * q;
+      const long long rowid = wt_ * 32 + g + 8 * q;
       long long ball = rowid / NS;
       if (ball >= balls) ball = balls - 1;                     // idle rows shadow the last ball (never stored)
-      ballq[q] = ball;
-      const int b = (int)(ball / M);
-      srow[q] = (unsigned)b * (unsigned)N + (unsigned)idx[ball * NS + (int)(rowid % NS)];
+      sr[q] = (unsigned)(ball / M) * (unsigned)N + (unsigned)idx[ball * NS + (int)(rowid % NS)];
     }
+  };
+  const long long wt0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  unsigned srow[4] = {0u, 0u, 0u, 0u};
+  if (wt0 < tiles) gather_rows(wt0, srow);
+  for (long long wt = wt0; wt < tiles; wt += warps) {
+    long long ballq[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long long ball = (wt * 32 + g + 8 * q) / NS;
+      ballq[q] = ball < balls ? ball : balls - 1;
+    }
+    // the next tile's indices are fetched now: the dependent chain idx -> row address -> gather is off the critical path
+    unsigned srow_next[4] = {0u, 0u, 0u, 0u};
+    if (wt + warps < tiles) gather_rows(wt + warps, srow_next);
     // Layer 1 is split as  W x_r + b = (W x_ref + b) + W (x_r - x_ref)  with x_ref the ball's first row: the first
     // term once per ball in plain fp32 (lane = output channel), the second on the tensor cores.  Rows of a ball are
     // neighbours, so the differences are small and the per-ball GroupNorm - which divides by the spread of the ball,
@@ -275,23 +285,28 @@ sa_mma_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, 
       const int sl = item / C1, ch = item - sl * C1;
       long long ball = wt * BPT + sl;
       if (ball >= balls) ball = balls - 1;
-      const unsigned rs = (unsigned)(ball / M) * (unsigned)N + (unsigned)idx[ball * NS];
-      float acc = sB1[ch];
+      // row 0 of ball `sl` is tile row 16*sl*(NS==16): lane 0 holds it as q = 0 (or 2)
+      const unsigned r_a = __shfl_sync(0xffffffffu, srow[0], 0);
+      const unsigned r_b = NS == 32 ? r_a : __shfl_sync(0xffffffffu, srow[2], 0);
+      const unsigned rs = sl == 0 ? r_a : r_b;
+      float acc4[4] = {sB1[ch], 0.f, 0.f, 0.f};               // four chains: the sum is latency-, not throughput-bound
 #pragma unroll
       for (int d = 0; d < 3; ++d)
-        acc = fmaf(sW1t[d * C1 + ch], xyz[(size_t)rs * 3 + d] - new_xyz[ball * 3 + d], acc);
+        acc4[d + 1] = sW1t[d * C1 + ch] * (xyz[(size_t)rs * 3 + d] - new_xyz[ball * 3 + d]);
       const float* fr = feat + (size_t)rs * ld_feat;
       if (vec2 && C % 4 == 0 && ld_feat % 4 == 0 && ((reinterpret_cast<uintptr_t>(feat) & 15) == 0)) {
+#pragma unroll 4
         for (int k = 0; k < C; k += 4) {
           const float4 f = *reinterpret_cast<const float4*>(fr + k);
-          acc = fmaf(sW1t[(3 + k) * C1 + ch], f.x, acc);
-          acc = fmaf(sW1t[(4 + k) * C1 + ch], f.y, acc);
-          acc = fmaf(sW1t[(5 + k) * C1 + ch], f.z, acc);
-          acc = fmaf(sW1t[(6 + k) * C1 + ch], f.w, acc);
+          acc4[0] = fmaf(sW1t[(3 + k) * C1 + ch], f.x, acc4[0]);
+          acc4[1] = fmaf(sW1t[(4 + k) * C1 + ch], f.y, acc4[1]);
+          acc4[2] = fmaf(sW1t[(5 + k) * C1 + ch], f.z, acc4[2]);
+          acc4[3] = fmaf(sW1t[(6 + k) * C1 + ch], f.w, acc4[3]);
         }
       } else {
-        for (int k = 0; k < C; ++k) acc = fmaf(sW1t[(3 + k) * C1 + ch], fr[k], acc);
+        for (int k = 0; k < C; ++k) acc4[k & 3] = fmaf(sW1t[(3 + k) * C1 + ch], fr[k], acc4[k & 3]);
       }
+      const float acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
       // GroupNorm is invariant to a shift of the whole group: take out the mean of the group's constant terms, so
       // that what is normalised (h0 - m0) + W (x_r - x_ref) is of the size of the ball's spread, not of the entries
       constexpr int CPG1 = C1 / 16;
@@ -438,6 +453,8 @@ sa_mma_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, 
         }
       }
     }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) srow[q] = srow_next[q];
   }
 }
 

@@ -40,6 +40,11 @@ class CasprOracle(object):
         self.augment_pairs = augment_pairs
         self.nfe = [0, 0]            # [latent, cnf]   (caspr.py:198-202)
         self.trace = {}              # intermediate tensors for op-level parity tests
+        # {tag: ReLU sign pattern (bool) / max-pool winner index} recorded by ANOTHER implementation of the encoder.  When
+        # set, the encoder's discrete decisions are replayed from it instead of being taken from the oracle's own values
+        # (gradient parity with frozen decisions: tests/test_train_gpu.py); trace['flips'] counts where they differ.
+        self.decisions = None
+        self.record = None           # set to {} to have the oracle's own decisions stored under the same tags
 
     # ------------------------------------------------------------------ helpers
     def _conv(self, x, key):
@@ -49,28 +54,51 @@ class CasprOracle(object):
     def _gn(self, x, key):
         return F.group_norm(x, NUM_GROUPS, self.sd[key + '.weight'], self.sd[key + '.bias'], eps=1e-5)
 
+    def _relu(self, x, tag):
+        if self.record is not None:
+            self.record[tag] = x.detach() > 0
+        if self.decisions is None:
+            return F.relu(x)
+        mask = self.decisions[tag]
+        fl = self.trace.setdefault('flips', {'relu': 0, 'relu_total': 0, 'max': 0, 'max_total': 0})
+        fl['relu'] += int(((x > 0) != mask).sum())
+        fl['relu_total'] += mask.numel()
+        return x * mask.to(x.dtype)
+
+    def _max(self, x, tag):
+        """max over the last axis of (B, C, L)."""
+        if self.record is not None:
+            self.record[tag] = torch.max(x.detach(), 2)[1]
+        if self.decisions is None:
+            return torch.max(x, 2)[0]
+        arg = self.decisions[tag].long()
+        fl = self.trace.setdefault('flips', {'relu': 0, 'relu_total': 0, 'max': 0, 'max_total': 0})
+        fl['max'] += int((torch.max(x, 2)[1] != arg).sum())
+        fl['max_total'] += arg.numel()
+        return x.gather(2, arg.unsqueeze(2)).squeeze(2)
+
     # ------------------------------------------------------------------ encoder
     def pointnet_global(self, x):
         """pointnet.py:34-46.  x (B,4,L) -> (B,1088,L) = [global max 1024 | pointfeat 64]."""
         p = 'encoder.global_extract.'
         L = x.shape[2]
-        x = F.relu(self._gn(self._conv(x, p + 'conv1'), p + 'bn1'))
+        x = self._relu(self._gn(self._conv(x, p + 'conv1'), p + 'bn1'), 'pn_r0')
         pointfeat = x
-        x = F.relu(self._gn(self._conv(x, p + 'conv2'), p + 'bn2'))
+        x = self._relu(self._gn(self._conv(x, p + 'conv2'), p + 'bn2'), 'pn_r1')
         x = self._gn(self._conv(x, p + 'conv3'), p + 'bn3')
-        g = torch.max(x, 2, keepdim=True)[0]
+        g = self._max(x, 'pn_max').unsqueeze(2)
         self.trace['global_max'] = g[:, :, 0]
         return torch.cat([g.repeat(1, 1, L), pointfeat], 1)
 
-    def _sa_pointnet(self, x, prefix):
+    def _sa_pointnet(self, x, prefix, tag):
         """pointnet2.py:649-708 as used by SA (global_feat=True, GroupNorm, transposed input).
 
         x (B'*M, C, ns): [conv,GN,ReLU] x2, conv, GN (no ReLU, :693), max over ns (:698).
         """
-        x = F.relu(self._gn(self._conv(x, prefix + 'conv_layers.0'), prefix + 'bn_layers.0'))
-        x = F.relu(self._gn(self._conv(x, prefix + 'conv_layers.1'), prefix + 'bn_layers.1'))
+        x = self._relu(self._gn(self._conv(x, prefix + 'conv_layers.0'), prefix + 'bn_layers.0'), tag + '_r0')
+        x = self._relu(self._gn(self._conv(x, prefix + 'conv_layers.1'), prefix + 'bn_layers.1'), tag + '_r1')
         x = self._gn(self._conv(x, prefix + 'conv_layers.2'), prefix + 'bn_layers.2')
-        return torch.max(x, 2)[0]
+        return self._max(x, tag + '_max')
 
     def set_abstraction(self, level, xyz, features):
         """pointnet2.py:361-419."""
@@ -92,7 +120,7 @@ class CasprOracle(object):
                 torch.cat([gxyz, pn2.group_gather_by_index(features, bq)], dim=1)  # (B,3+C,M,ns)
             g = g.permute(0, 2, 1, 3).reshape(B * M, g.shape[1], ns)                # :397
             prefix = 'encoder.local_extract.set_abstractions.%d.pointnet_modules.%d.' % (level, s)
-            f = self._sa_pointnet(g, prefix)                                        # :401
+            f = self._sa_pointnet(g, prefix, 'sa%d_%d' % (level, s))                # :401
             outs.append(f.view(B, M, -1).transpose(1, 2))                           # :408
         return new_xyz, torch.cat(outs, dim=1)                                      # :414
 
@@ -105,8 +133,8 @@ class CasprOracle(object):
         if features is not None:                                                    # :521-523
             new = torch.cat([new, features], dim=1)
         p = 'encoder.local_extract.feature_propagators.%d.unit_pointnet.' % i
-        new = F.relu(self._gn(self._conv(new, p + '0'), p + '1'))
-        new = F.relu(self._gn(self._conv(new, p + '3'), p + '4'))
+        new = self._relu(self._gn(self._conv(new, p + '0'), p + '1'), 'fp%d_r0' % i)
+        new = self._relu(self._gn(self._conv(new, p + '3'), p + '4'), 'fp%d_r1' % i)
         return new
 
     def pointnet2(self, points):
@@ -127,7 +155,7 @@ class CasprOracle(object):
             self.trace['fp_out_%d' % i] = feat_list[ti]
             ti -= 1
         p = 'encoder.local_extract.final_layers.'
-        x = F.relu(self._gn(self._conv(feat_list[0], p + '0'), p + '1'))            # :247
+        x = self._relu(self._gn(self._conv(feat_list[0], p + '0'), p + '1'), 'final_r')   # :247
         x = self._conv(x, p + '3')
         return x.transpose(1, 2).contiguous()
 
@@ -149,13 +177,13 @@ class CasprOracle(object):
         lf = self.pointnet2(local_in).view(B, T * N, -1).transpose(2, 1).contiguous()   # :92-93
         self.trace['local_feat'] = lf
         feat = torch.cat([lf, g], dim=1)                                            # :96
-        feat = F.relu(self._gn(self._conv(feat, 'encoder.conv1'), 'encoder.bn1'))   # :99
+        feat = self._relu(self._gn(self._conv(feat, 'encoder.conv1'), 'encoder.bn1'), 'head_r0')   # :99
         feat = self._gn(self._conv(feat, 'encoder.conv2'), 'encoder.bn2')           # :100
         tnocs = None
         if self.regress_tnocs:
-            t_out = self._conv(F.relu(feat), 'encoder.conv3')                       # :105
+            t_out = self._conv(self._relu(feat, 'head_r1'), 'encoder.conv3')        # :105
             tnocs = torch.sigmoid(t_out[:, :4, :]).transpose(2, 1).contiguous().view(B, T, N, 4)
-        z0 = torch.max(feat, 2)[0]                                                  # :111
+        z0 = self._max(feat, 'head_max')                                            # :111
         return z0, tnocs
 
     # --------------------------------------------------------------- latent ODE

@@ -101,3 +101,29 @@ def test_adjoint_restatement_converges_to_backprop_through_the_steps(tol, bound)
     assert abs(float(la.detach()) - float(lb.detach())) <= 1e-6 * abs(float(lb.detach()))
     worst = max(float((a - b).abs().max()) / (float(b.abs().max()) + 1e-12) for a, b in zip(ga, gb))
     assert worst < bound, worst
+
+
+def test_decision_replay_reproduces_the_oracles_own_gradients():
+    """The frozen-decision machinery of the oracle encoder (`record` / `decisions`, used by the GPU test of the composed
+    encoder backward): replaying the oracle's OWN ReLU sign patterns and max-pool winners must change nothing - same z0,
+    same T-NOCS, same parameter gradients, zero differing decisions."""
+    torch.set_num_threads(8)
+    sd = synthetic_state_dict(0)
+    x, _ = synthetic_sequences(2, 2, 256, seed=6)
+    g = torch.Generator().manual_seed(8)
+    gz, gt = torch.randn(2, 1600, generator=g), torch.randn(2, 2, 256, 4, generator=g)
+    a = TrainOracle(sd)
+    a.record = {}
+    z0a, tna = a.encode(x)
+    ((z0a * gz).sum() + (tna * gt).sum()).backward()
+    assert len(a.record) == 3 + 5 * 2 * 3 + 5 * 2 + 1 + 3
+    b = TrainOracle(sd)
+    b.decisions = a.record
+    z0b, tnb = b.encode(x)
+    ((z0b * gz).sum() + (tnb * gt).sum()).backward()
+    assert b.trace['flips']['relu'] == 0 and b.trace['flips']['max'] == 0
+    assert torch.equal(z0a, z0b) and torch.equal(tna, tnb)
+    pa, pb = a.parameters(), b.parameters()
+    for k in pa:
+        if k.startswith('encoder.'):
+            assert torch.allclose(pa[k].grad, pb[k].grad, rtol=1e-5, atol=1e-7 * float(pa[k].grad.abs().max())), k
