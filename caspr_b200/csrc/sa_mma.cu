@@ -34,7 +34,7 @@ struct SaLayer {
 };
 
 __device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -61,16 +61,22 @@ __device__ __forceinline__ void pow2_scale(float m, float& s, float& inv) {
 template <int NT, int KC>
 __device__ __forceinline__ void mma_chunk(float (&acc)[2][NT][4], const uint32_t (&ahi)[2][4], const uint32_t (&alo)[2][4],
                                           const uint4* __restrict__ frag, int c, int lane) {
+  uint4 f[NT];                                                // {b0 hi, b1 hi, b0 lo, b1 lo}
 #pragma unroll
-  for (int j = 0; j < NT; ++j) {
-    const uint4 f = frag[(j * KC + c) * 32 + lane];           // {b0 hi, b1 hi, b0 lo, b1 lo}
+  for (int j = 0; j < NT; ++j) f[j] = frag[(j * KC + c) * 32 + lane];
+  // product-major order: the 2*NT accumulators are independent, so consecutive MMAs never wait on each other
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-      mma_f16(acc[mt][j], alo[mt], f.x, f.y);
-      mma_f16(acc[mt][j], ahi[mt], f.z, f.w);
-      mma_f16(acc[mt][j], ahi[mt], f.x, f.y);
-    }
-  }
+  for (int j = 0; j < NT; ++j)
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) mma_f16(acc[mt][j], alo[mt], f[j].x, f[j].y);
+#pragma unroll
+  for (int j = 0; j < NT; ++j)
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) mma_f16(acc[mt][j], ahi[mt], f[j].z, f[j].w);
+#pragma unroll
+  for (int j = 0; j < NT; ++j)
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) mma_f16(acc[mt][j], ahi[mt], f[j].x, f[j].y);
 }
 
 // acc * unscale + bias, then GroupNorm(16, 8*NT) over each ball of the tile (+ ReLU), in place.
