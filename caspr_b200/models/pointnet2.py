@@ -113,7 +113,8 @@ class PointNet2SetAbstraction(nn.Module):
         absmax = None
         for s, (grouper, pointnet) in enumerate(zip(self.grouper_modules, self.pointnet_modules)):
             widths = [c.weight.shape[0] for c in pointnet.conv_layers]
-            if features is not None and ops.sa_mma_supported(grouper.num_samples, self.pointnet_in_channels, widths):
+            if features is not None and ops.sa_mma_supported(grouper.num_samples, self.pointnet_in_channels, widths,
+                                                             features):
                 # levels 1-2 on the tensor cores: gather + three per-ball layers + max in one kernel, activations in
                 # mma fragments; one operand bound per level serves both scales
                 if absmax is None:

@@ -381,7 +381,10 @@ def sa_fused(xyz, new_xyz, feat, idx, convs, norms, out):
     return out
 
 
-def sa_mma_supported(ns, cin, widths):
+def sa_mma_supported(ns, cin, widths, feat=None):
+    """feat: the (B,N,C) feature view, if known - the kernel addresses rows with 32-bit offsets."""
+    if feat is not None and feat.shape[0] * feat.shape[1] * max(feat.stride(1), 3) >= 2 ** 32:
+        return False
     return SA_MMA and len(widths) == 3 and bool(lib.caspr_sa_mma_supported(ns, cin, *widths))
 
 
