@@ -435,8 +435,10 @@ struct GnProject {
   int P, ld_out, act;
 };
 
-template <bool PROJ>
-__global__ void __launch_bounds__(256)
+// NQ: channel quads per lane (ceil(C / 128)); a template parameter so that the per-lane arrays are exactly as long as
+// the layer needs (C = 512: 4 quads, 40 registers and full occupancy instead of the 128 of the generic 16-quad version)
+template <bool PROJ, int NQ>
+__global__ void __launch_bounds__(256, 2)
 groupnorm_apply_vec_kernel(float* __restrict__ X, int ldx, int rows_per_sample, int C, int groups,
                            const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                            int relu, int write_back, const double* __restrict__ stats,
@@ -461,10 +463,10 @@ groupnorm_apply_vec_kernel(float* __restrict__ X, int ldx, int rows_per_sample, 
   __syncthreads();
   // per-quad scale / shift: v*sc + sh with sc = rstd*gamma, sh = beta - mean*rstd*gamma would change the
   // rounding of (x - mean)*rstd*gamma + beta; keep the reference's operation order instead
-  float mu[kGnMaxQuadsPerLane], rs[kGnMaxQuadsPerLane];
-  float4 mx[kGnMaxQuadsPerLane];
+  float mu[NQ], rs[NQ];
+  float4 mx[NQ];
 #pragma unroll
-  for (int k = 0; k < kGnMaxQuadsPerLane; ++k) {
+  for (int k = 0; k < NQ; ++k) {
     const int qi = lane + 32 * k;
     const int g = qi < Q ? (qi * 4) / cpg : 0;
     mu[k] = s_mean[g];
@@ -478,7 +480,7 @@ groupnorm_apply_vec_kernel(float* __restrict__ X, int ldx, int rows_per_sample, 
     float4* row = reinterpret_cast<float4*>(base + (size_t)r * ldx);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int k = 0; k < kGnMaxQuadsPerLane; ++k) {
+    for (int k = 0; k < NQ; ++k) {
       const int qi = lane + 32 * k;
       if (qi < Q) {
         float4 v = row[qi];
@@ -518,7 +520,7 @@ groupnorm_apply_vec_kernel(float* __restrict__ X, int ldx, int rows_per_sample, 
   }
   if (maxout_ordered) {
 #pragma unroll
-    for (int k = 0; k < kGnMaxQuadsPerLane; ++k) {
+    for (int k = 0; k < NQ; ++k) {
       const int qi = lane + 32 * k;
       if (qi < Q && r0 + warp < r1) {
         unsigned* o = maxout_ordered + (size_t)sample * ld_max + qi * 4;
@@ -570,6 +572,21 @@ __global__ void broadcast_rows_kernel(const float* __restrict__ src, int ld_src,
     long long s = row / rows_per_sample;
     dst[row * ld_dst + c] = src[s * ld_src + c];
   }
+}
+
+template <bool PROJ>
+void launch_gn_apply_vec(dim3 grid, cudaStream_t s, float* X, int ldx, int rows_per_sample, int C, int groups,
+                         const float* gamma, const float* beta, float eps, int relu, int write_back, const double* stats,
+                         unsigned* mo, int ld_max, GnProject pj) {
+  const int nq = ceil_div(C, 128);
+#define CASPR_GN_VEC(NQ) \
+  groupnorm_apply_vec_kernel<PROJ, NQ><<<grid, 256, 0, s>>>(X, ldx, rows_per_sample, C, groups, gamma, beta, eps, relu, \
+                                                            write_back, stats, mo, ld_max, pj)
+  if (nq <= 4) CASPR_GN_VEC(4);
+  else if (nq <= 8) CASPR_GN_VEC(8);
+  else if (nq <= 13) CASPR_GN_VEC(13);
+  else CASPR_GN_VEC(16);
+#undef CASPR_GN_VEC
 }
 
 }  // namespace
@@ -683,9 +700,8 @@ extern "C" int caspr_groupnorm(float* X, int ldx, int samples, int rows_per_samp
     CASPR_CHECK_LAUNCH();
   }
   if (vec) {
-    CASPR_COUNT(); groupnorm_apply_vec_kernel<false><<<grid, 256, 0, s>>>(X, ldx, rows_per_sample, C, groups, gamma, beta,
-                                                                          eps, relu, write_back, stats_ws, mo, ld_max,
-                                                                          GnProject{});
+    CASPR_COUNT(); launch_gn_apply_vec<false>(grid, s, X, ldx, rows_per_sample, C, groups, gamma, beta, eps, relu, write_back,
+                                              stats_ws, mo, ld_max, GnProject{});
   } else {
     CASPR_COUNT(); groupnorm_apply_kernel<<<grid, 256, 0, s>>>(X, ldx, rows_per_sample, C, groups, gamma, beta, eps, relu,
                                                write_back, stats_ws, mo, ld_max);
@@ -716,9 +732,8 @@ extern "C" int caspr_groupnorm_project(const float* X, int ldx, int samples, int
   }
   GnProject pj;
   pj.W = W; pj.bias = bias; pj.out = out; pj.P = P; pj.ld_out = ld_out; pj.act = act;
-  CASPR_COUNT(); groupnorm_apply_vec_kernel<true><<<grid, 256, 0, s>>>(const_cast<float*>(X), ldx, rows_per_sample, C,
-                                                                       groups, gamma, beta, eps, 0, 0, stats, mo,
-                                                                       ld_max, pj);
+  CASPR_COUNT(); launch_gn_apply_vec<true>(grid, s, const_cast<float*>(X), ldx, rows_per_sample, C, groups, gamma, beta, eps,
+                                           0, 0, stats, mo, ld_max, pj);
   CASPR_CHECK_LAUNCH();
   if (mo) {
     CASPR_COUNT(); decode_ordered_kernel<<<ceil_div(samples * C, 256), 256, 0, s>>>(mo, samples, C, ld_max);
