@@ -14,20 +14,11 @@ namespace {
 constexpr float kFpsSkipMag = 1e-3f;   // upstream `if (mag <= 1e-3) continue;`
 constexpr float kFpsInit = 1e10f;
 
-__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
-    v = other > v ? other : v;
-  }
-  return v;
-}
-
 // One CTA per cloud.  Thread t owns points t, t+THREADS, ... (PPT of them) in registers
 // together with their running min-distance; the cloud is mirrored in shared memory (SoA)
 // only to fetch the coordinates of the last pick.  Each of the M-1 dependent iterations
-// costs one distance update per owned point, a 64-bit (distance bits | ~index) warp-shuffle
-// arg-max and ONE __syncthreads (the cross-warp stage is double-buffered).
+// costs one distance update per owned point, an arg-max over (distance bits, lowest index) as two
+// redux.sync per stage and ONE __syncthreads (the cross-warp stage is double-buffered).
 template <int THREADS, int PPT>
 __global__ void __launch_bounds__(THREADS)
 fps_kernel(const float* __restrict__ xyz, int N, int M, int32_t* __restrict__ idx,
@@ -70,27 +61,31 @@ fps_kernel(const float* __restrict__ xyz, int N, int M, int32_t* __restrict__ id
   if (tid == 0) spick[0] = 0;
   for (int j = 1; j < M; ++j) {
     const float lx = sx[last], ly = sy[last], lz = sz[last];
-    unsigned long long best = 0ull;
+    // arg-max with ties to the lowest index = max of the 64-bit key (distance bits | ~index), taken as two 32-bit
+    // warp reductions (redux.sync): the largest distance, then the lowest index among the lanes that hold it.
+    // Distances are >= 0, so their bit patterns order like the values.  0xffffffff = "no candidate".
+    unsigned bd = 0u, bk = 0xffffffffu;
 #pragma unroll
     for (int i = 0; i < PPT; ++i) {
       if (live[i]) {
         float d = sqdist_canonical(px[i], py[i], pz[i], lx, ly, lz);
         float d2 = fminf(d, temp[i]);
         temp[i] = d2;
-        unsigned k = (unsigned)(i * THREADS + tid);
-        unsigned long long key =
-            ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)(0xffffffffu - k);
-        best = key > best ? key : best;
+        const unsigned k = (unsigned)(i * THREADS + tid), db = __float_as_uint(d2);
+        if (db > bd || (db == bd && k < bk)) { bd = db; bk = k; }
       }
     }
-    best = warp_max_u64(best);
+    unsigned wd = __reduce_max_sync(0xffffffffu, bd);
+    unsigned wk = __reduce_min_sync(0xffffffffu, bd == wd ? bk : 0xffffffffu);
     if (THREADS > 32) {
-      if (lane == 0) swarp[j & 1][warp] = best;
+      if (lane == 0) swarp[j & 1][warp] = ((unsigned long long)wd << 32) | wk;
       __syncthreads();
-      unsigned long long v = lane < THREADS / 32 ? swarp[j & 1][lane] : 0ull;
-      best = warp_max_u64(v);
+      const unsigned long long v = lane < THREADS / 32 ? swarp[j & 1][lane] : 0xffffffffull;
+      const unsigned vd = (unsigned)(v >> 32), vk = (unsigned)v;
+      wd = __reduce_max_sync(0xffffffffu, vd);
+      wk = __reduce_min_sync(0xffffffffu, vd == wd ? vk : 0xffffffffu);
     }
-    last = best == 0ull ? 0 : (int)(0xffffffffu - (unsigned)(best & 0xffffffffull));
+    last = wk == 0xffffffffu ? 0 : (int)wk;
     if (tid == 0) spick[j] = last;
   }
   __syncthreads();
