@@ -457,6 +457,7 @@ transpose_split_kernel(const float* __restrict__ X, int ldx, long long rows, int
 
 // partial[split][o][i] = acc * inv_dy[o] * inv_x[i]
 struct WgradEpilogue {
+  static constexpr int kEpilogueGroups = 2;
   const unsigned* a_max;  // column maxima (bit patterns) of dY: per output channel o (rows of the A operand)
   const unsigned* w_max;  // column maxima of X: per input channel i
   float* part;            // [k_splits][cout][cin]
@@ -620,6 +621,7 @@ constexpr float kBallPlaneScale = 512.f;      // |GroupNorm output| <= |gamma| s
 
 template <int CPG, bool LAST>
 struct BallNormEpilogue {
+  static constexpr int kEpilogueGroups = 2;
   static constexpr bool kReadsTmem = true;
   static constexpr int kChunk = (CPG == 6) ? 24 : 32;           // whole groups, a multiple of 8 columns (C = 96: 24)
   static_assert(kChunk % CPG == 0 && kChunk % 8 == 0, "a chunk holds whole GroupNorm groups");

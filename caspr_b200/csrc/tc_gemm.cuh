@@ -186,13 +186,22 @@ struct epilogue_reads_tmem : std::false_type {};
 template <class E>
 struct epilogue_reads_tmem<E, std::enable_if_t<E::kReadsTmem>> : std::true_type {};
 
+// Epilogue::kEpilogueGroups = 2: two epilogue warpgroups per CTA, group g drains the accumulator buffer g (every other work
+// item) with its own half of the staging buffer.  For layers with a short k-loop the epilogue, not the MMA, bounds a
+// tile (per-ball GroupNorm: 27 k cycles per tile against 1-2 k of MMA), and two groups halve that.
+template <class E, class = void>
+struct epilogue_groups : std::integral_constant<int, 1> {};
+template <class E>
+struct epilogue_groups<E, std::void_t<decltype(E::kEpilogueGroups)>> : std::integral_constant<int, E::kEpilogueGroups> {};
+constexpr int kPairThreadsMax = 64 + 2 * 128;
+
 constexpr int kPairStages = 3;
 constexpr int kPairWTile = (kBN / 2) * kBK * 2;                      // 16 KB: this CTA's half of the W tile
 constexpr int kPairStageBytes = 2 * kATile + 2 * kPairWTile;        // 64 KB
 constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + kStagingBytes + 1024 + 256;
 
 template <class Epilogue>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreadsMax, 1)
 gemm_fp16x3_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                         const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                         const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
@@ -297,10 +306,13 @@ gemm_fp16x3_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
       }
     }
   } else {
+    constexpr int G = epilogue_groups<Epilogue>::value;
     const int q = warp & 3;                                       // TMEM lane quadrant of this warp
-    epi.setup(staging, &tm_o_hi, &tm_o_lo, (int)threadIdx.x - 64);
+    const int grp = (warp - 2) >> 2;                              // epilogue warpgroup (G == 1: only group 0 exists)
+    epi.setup(staging + grp * (kStagingBytes / G), &tm_o_hi, &tm_o_lo, ((int)threadIdx.x - 64) & 127);
     int it = 0;
     for (int item = cluster_id; item < total_items; item += n_clusters, ++it) {
+      if (G == 2 && (it & 1) != grp) continue;                    // group g owns accumulator buffer g
       const int split = item / mn_items, mn = item - split * mn_items;
       const int m_pair = mn / n_tiles, n_tile = mn - m_pair * n_tiles;
       const int m_local = 2 * m_pair + (int)rank;
@@ -366,8 +378,9 @@ inline cudaError_t launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo,
     }
     long long clusters = (long long)((m_tiles + 1) / 2) * n_tiles * k_splits;
     if (clusters > num_sms / 2) clusters = num_sms / 2;
-    gemm_fp16x3_pair_kernel<Epilogue><<<(int)(2 * clusters), kThreads, kPairSmemBytes, s>>>(
-        a_hi, a_lo, w_hi, w_lo, o_hi, o_lo, m_tile0, m_tiles, n_tiles, k_chunks, skip_flag, epi, k_splits);
+    gemm_fp16x3_pair_kernel<Epilogue><<<(int)(2 * clusters), 64 + 128 * epilogue_groups<Epilogue>::value, kPairSmemBytes,
+                                        s>>>(a_hi, a_lo, w_hi, w_lo, o_hi, o_lo, m_tile0, m_tiles, n_tiles, k_chunks,
+                                             skip_flag, epi, k_splits);
   } else {
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(gemm_fp16x3_kernel<Epilogue>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -399,8 +412,9 @@ inline cudaError_t launch_gemm_pair(const CUtensorMap& a_hi, const CUtensorMap& 
   }
   long long clusters = (long long)((m_tiles + 1) / 2) * n_tiles;
   if (clusters > num_sms / 2) clusters = num_sms / 2;
-  gemm_fp16x3_pair_kernel<Epilogue><<<(int)(2 * clusters), kThreads, kPairSmemBytes, s>>>(
-      a_hi, a_lo, w_hi, w_lo, a_hi, a_lo, 0, m_tiles, n_tiles, k_chunks, nullptr, epi, 1);
+  gemm_fp16x3_pair_kernel<Epilogue><<<(int)(2 * clusters), 64 + 128 * epilogue_groups<Epilogue>::value, kPairSmemBytes,
+                                      s>>>(a_hi, a_lo, w_hi, w_lo, a_hi, a_lo, 0, m_tiles, n_tiles, k_chunks, nullptr, epi,
+                                           1);
   return cudaGetLastError();
 }
 
