@@ -207,6 +207,7 @@ void launch_split_rows(const float* x, int ld, long long rows, int cols, long lo
 }
 
 struct LinearEpilogue {
+  static constexpr int kEpilogueGroups = 2;       // each group stages through its own 16 KB half (one buffer)
   const float* bias;
   int bias_rps;           // 0: one bias vector; > 0: bias is (samples, cout), row r uses bias row r / bias_rps
   const float* x_inv;     // per-row 1/scale of X
@@ -220,7 +221,7 @@ struct LinearEpilogue {
   int use_tma;
   uint8_t* stg;
   const CUtensorMap* tm_y;
-  int etid, m_tile_cur, box_row, n_store;
+  int etid, m_tile_cur, box_row, bar_id;
   // optional GroupNorm statistics of the OUTPUT (before any normalisation): per (sample, group) sum and sum
   // of squares accumulated in fp64; requires rows_per_sample % 32 == 0 so a warp never straddles samples
   double* stats;
@@ -231,7 +232,8 @@ struct LinearEpilogue {
   float inv;
 
   __device__ __forceinline__ void setup(uint8_t* staging, const CUtensorMap* o_hi, const CUtensorMap*, int epi_tid) {
-    stg = staging; tm_y = o_hi; etid = epi_tid; n_store = 0;
+    stg = staging; tm_y = o_hi; etid = epi_tid;
+    bar_id = 1 + ((((int)threadIdx.x >> 5) - 2) >> 2);           // named barrier of this epilogue warpgroup
   }
   __device__ __forceinline__ void tile_begin(int m_tile, int n_tile, int q, int lane) {
     if (stats && st_live) flush_stats();               // statistics of the previous tile
@@ -293,21 +295,21 @@ struct LinearEpilogue {
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
     }
     if (use_tma) {
-      // two staging buffers of [128 rows][128 B] (128-byte swizzle); rows / columns beyond the matrix are clipped by TMA
-      uint8_t* buf = stg + (n_store & 1) * (kBM * 128);
-      if (etid == 0) tc::tma_store_wait_read_but_one();            // the store issued two chunks ago has left `buf`
-      tc::named_bar_sync(1, 128);
+      // one staging buffer of [128 rows][128 B] per warpgroup (128-byte swizzle); rows / columns beyond the matrix are
+      // clipped by TMA.  The other warpgroup works on the other accumulator meanwhile.
+      uint8_t* buf = stg;
+      if (etid == 0) tc::tma_store_wait_read();                    // the previous store has left `buf`
+      tc::named_bar_sync(bar_id, 128);
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4)
         *reinterpret_cast<float4*>(buf + box_row * 128 + ((j4 ^ (box_row & 7)) << 4)) =
             make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
       tc::fence_proxy_async_smem();
-      tc::named_bar_sync(1, 128);
+      tc::named_bar_sync(bar_id, 128);
       if (etid == 0) {
         tc::tma_store_2d(tm_y, buf, c, m_tile_cur * kBM);
         tc::tma_store_commit();
       }
-      ++n_store;
       return;
     }
     if (!row_ok) return;
