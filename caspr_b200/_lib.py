@@ -30,7 +30,7 @@ class GnFold(Structure):
 
 
 class GnStats(Structure):
-    _fields_ = [('stats', c_void_p), ('rows_per_sample', c_int), ('groups', c_int)]
+    _fields_ = [('stats', c_void_p), ('rows_per_sample', c_int), ('groups', c_int), ('extrema', c_void_p)]
 
 
 ALLREDUCE_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_int, c_void_p, c_void_p)
@@ -84,6 +84,7 @@ SIGNATURES = {
                                 c_int, _P, c_int, _P]),
     'caspr_groupnorm_project': (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_float, _P, c_int, _P, _P, _P,
                                         c_int, c_int, _P, c_int, _P]),
+    'caspr_gn_max_from_extrema': (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, c_float, _P, c_int, _P]),
     'caspr_augment_xyz': (c_int, [_P, c_int, _P, _P]),
     'caspr_strip_time': (c_int, [_P, c_int, _P, _P]),
     'caspr_broadcast_rows': (c_int, [_P, c_int, c_int, c_int, c_int, _P, c_int, _P]),

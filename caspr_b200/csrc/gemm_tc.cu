@@ -226,6 +226,9 @@ struct LinearEpilogue {
   // of squares accumulated in fp64; requires rows_per_sample % 32 == 0 so a warp never straddles samples
   double* stats;
   int st_rows_per_sample, st_cpg, st_groups;
+  // optional per-(sample, channel) max / min of the output as ordered-uint keys ([samples][2][cout]); Y is then not
+  // written (GroupNorm + max-pool consumers need nothing else, caspr_gn_max_from_extrema)
+  unsigned* ext;
   // per-thread tile state
   long long row;
   int col0;
@@ -289,6 +292,27 @@ struct LinearEpilogue {
         flush_stats();
         st_s = s1; st_q = q1; ++st_g; st_next += st_cpg;
       }
+    }
+    if (ext) {
+      // column extrema over the warp's 32 rows (one sample: rows_per_sample % 32 == 0), one redux per column and bound;
+      // lane j keeps column j and issues the two atomics
+      unsigned my_mx = 0u, my_mn = 0xffffffffu;
+      const int lane = threadIdx.x & 31;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const unsigned key = float_to_ordered(v[j]);
+        const unsigned mx = __reduce_max_sync(0xffffffffu, row_ok ? key : 0u);
+        const unsigned mn = __reduce_min_sync(0xffffffffu, row_ok ? key : 0xffffffffu);
+        if (lane == j) { my_mx = mx; my_mn = mn; }
+      }
+      if (st_live && c + lane < cout) {
+        unsigned* e = ext + (size_t)((row - lane) / st_rows_per_sample) * 2 * cout + c + lane;
+        // the bounds only move outwards: a plain read that already shows a wider bound makes the atomic unnecessary,
+        // which is the case for almost every tile after the first few (hundreds of tiles share one address)
+        if (my_mx > __ldcg(e)) atomicMax(e, my_mx);
+        if (my_mn < __ldcg(e + cout)) atomicMin(e + cout, my_mn);
+      }
+      return;
     }
     if (act_out == CASPR_ACT_RELU) {
 #pragma unroll
@@ -938,15 +962,57 @@ extern "C" int caspr_linear_tc_prepare_weights(const float* W, int ldw, int Cin,
   return CASPR_OK;
 }
 
+namespace {
+__global__ void extrema_init_kernel(unsigned* ext, int samples, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < samples * 2 * C) ext[i] = ((i / C) & 1) ? 0xffffffffu : 0u;      // [sample][max | min][C]
+}
+// same arithmetic as groupnorm_apply_vec_kernel (dense.cu): mean / rstd from the fp64 sums, then
+// (x - mean) * rstd * gamma + beta - evaluated at the channel's max (gamma >= 0) or min (gamma < 0)
+__global__ void gn_max_from_extrema_kernel(const double* __restrict__ stats, const unsigned* __restrict__ ext, int samples,
+                                           int rows_per_sample, int C, int groups, const float* __restrict__ gamma,
+                                           const float* __restrict__ beta, float eps, float* __restrict__ maxout,
+                                           int ld_max) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= samples * C) return;
+  const int sm = i / C, c = i - sm * C;
+  const int cpg = C / groups, g = c / cpg;
+  const double cnt = (double)cpg * (double)rows_per_sample;
+  const double s = stats[((size_t)sm * groups + g) * 2], q = stats[((size_t)sm * groups + g) * 2 + 1];
+  const double mean = s / cnt;
+  double var = q / cnt - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float mu = (float)mean, rs = (float)(1.0 / sqrt(var + (double)eps));
+  const float ga = gamma[c], be = beta[c];
+  const float hi = ordered_to_float(ext[(size_t)sm * 2 * C + c]), lo = ordered_to_float(ext[(size_t)sm * 2 * C + C + c]);
+  const float a = fmaf(__fmul_rn(__fsub_rn(hi, mu), rs), ga, be), b = fmaf(__fmul_rn(__fsub_rn(lo, mu), rs), ga, be);
+  maxout[(size_t)sm * ld_max + c] = fmaxf(a, b);
+}
+}  // namespace
+
+extern "C" int caspr_gn_max_from_extrema(const double* stats, const unsigned* extrema, int samples, int rows_per_sample,
+                                         int C, int groups, const float* gamma, const float* beta, float eps,
+                                         float* maxout, int ld_max, void* stream) {
+  CASPR_REQUIRE(stats && extrema && gamma && beta && maxout && samples > 0 && rows_per_sample > 0 && C > 0);
+  CASPR_REQUIRE(groups > 0 && C % groups == 0 && ld_max >= C);
+  CASPR_COUNT(); gn_max_from_extrema_kernel<<<ceil_div(samples * C, 256), 256, 0, (cudaStream_t)stream>>>(
+      stats, extrema, samples, rows_per_sample, C, groups, gamma, beta, eps, maxout, ld_max);
+  CASPR_CHECK_LAUNCH();
+  return CASPR_OK;
+}
+
 extern "C" int caspr_linear_tc(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y,
                                int ldy, int rows, int Cin, int Cout, int act_in, int act_out,
                                const void* prepared_weights, const caspr_gn_fold* in_norm,
                                const caspr_gn_stats* out_stats, int bias_rows_per_sample, void* workspace,
                                size_t workspace_bytes, void* stream) {
-  CASPR_REQUIRE(X && (W || prepared_weights) && Y && workspace && rows > 0 && Cin > 0 && Cout > 0);
+  const bool reduce_only = out_stats && out_stats->extrema;      // statistics + column extrema, no Y
+  CASPR_REQUIRE(X && (W || prepared_weights) && (Y || reduce_only) && workspace && rows > 0 && Cin > 0 && Cout > 0);
   CASPR_REQUIRE(bias_rows_per_sample >= 0 && (bias_rows_per_sample == 0 || bias));
   // the epilogue stores float4 pieces and keeps one running GroupNorm group per chunk of 32 columns
-  CASPR_REQUIRE(Cout % 4 == 0 && ldy % 4 == 0 && ((uintptr_t)Y & 15) == 0 && (!bias || ((uintptr_t)bias & 15) == 0));
+  CASPR_REQUIRE(Cout % 4 == 0 && (!bias || ((uintptr_t)bias & 15) == 0));
+  CASPR_REQUIRE(reduce_only || (ldy % 4 == 0 && ((uintptr_t)Y & 15) == 0 && ldy >= Cout));
+  CASPR_REQUIRE(!reduce_only || act_out == CASPR_ACT_NONE);
   if (out_stats) CASPR_REQUIRE(Cout / out_stats->groups >= 32);
   CASPR_REQUIRE(act_out == CASPR_ACT_NONE || act_out == CASPR_ACT_RELU);     // sigmoid outputs: caspr_linear
   if (in_norm)
@@ -955,7 +1021,7 @@ extern "C" int caspr_linear_tc(const float* X, int ldx, const float* W, int ldw,
     CASPR_REQUIRE(out_stats->stats && out_stats->groups > 0 && Cout % out_stats->groups == 0 &&
                   out_stats->rows_per_sample > 0 && out_stats->rows_per_sample % 32 == 0 &&
                   rows % out_stats->rows_per_sample == 0);
-  CASPR_REQUIRE(ldx >= Cin && (!W || ldw >= Cin) && ldy >= Cout);
+  CASPR_REQUIRE(ldx >= Cin && (!W || ldw >= Cin));
   CASPR_REQUIRE(act_in == CASPR_ACT_NONE || act_in == CASPR_ACT_RELU);
   CASPR_REQUIRE(((uintptr_t)workspace & 1023) == 0 && ((uintptr_t)prepared_weights & 1023) == 0);
   const Layout l = make_layout(rows, Cin, Cout);
@@ -987,6 +1053,11 @@ extern "C" int caspr_linear_tc(const float* X, int ldx, const float* W, int ldw,
   if (out_stats) {
     const size_t n_stats = (size_t)(rows / out_stats->rows_per_sample) * out_stats->groups * 2;
     if (cudaMemsetAsync(out_stats->stats, 0, n_stats * sizeof(double), s) != cudaSuccess) return CASPR_ELAUNCH;
+    if (reduce_only) {
+      const int samples = rows / out_stats->rows_per_sample;
+      CASPR_COUNT(); extrema_init_kernel<<<ceil_div(samples * 2 * Cout, 256), 256, 0, s>>>(out_stats->extrema, samples, Cout);
+      CASPR_CHECK_LAUNCH();
+    }
   }
 
   CUtensorMap tm_xhi, tm_xlo, tm_whi, tm_wlo;
@@ -1007,6 +1078,7 @@ extern "C" int caspr_linear_tc(const float* X, int ldx, const float* W, int ldw,
     epi.stats = out_stats->stats; epi.st_rows_per_sample = out_stats->rows_per_sample;
     epi.st_groups = out_stats->groups; epi.st_cpg = Cout / out_stats->groups;
   }
+  epi.ext = reduce_only ? out_stats->extrema : nullptr;
   epi.vec_ok = (ldy % 4 == 0) && (((uintptr_t)Y & 15) == 0) && (!bias || ((uintptr_t)bias & 15) == 0);
   const int m_tiles = (int)(l.rows_pad / kBM), n_tiles = l.cout_pad / kBN;
   // fp32 output through TMA (full lines); CASPR_LINEAR_TMA_STORE=0 keeps the direct 16-byte stores
@@ -1014,7 +1086,8 @@ extern "C" int caspr_linear_tc(const float* X, int ldx, const float* W, int ldw,
   {
     static int want = -1;
     if (want < 0) { const char* e = getenv("CASPR_LINEAR_TMA_STORE"); want = (e && e[0] == '0') ? 0 : 1; }
-    epi.use_tma = want && caspr_make_tmap_f32_box32(&tm_y, Y, (uint64_t)rows, (uint64_t)Cout, (uint64_t)ldy, kBM);
+    epi.use_tma = want && !reduce_only &&
+                  caspr_make_tmap_f32_box32(&tm_y, Y, (uint64_t)rows, (uint64_t)Cout, (uint64_t)ldy, kBM);
   }
   caspr_prof_begin(CASPR_PROF_LINEAR, s);
   CASPR_COUNT();

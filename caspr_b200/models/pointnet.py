@@ -4,12 +4,15 @@ Parameter containers are stock torch modules so the state_dict keys / shapes mat
 reference (``conv{1,2,3}.{weight,bias}``, ``bn{1,2,3}.{weight,bias}``); the math runs in
 libcaspr_b200.so on channels-last rows.
 """
+import os
+
 import torch
 import torch.nn as nn
 
 from .. import ops
 
 NUM_GROUPS = 16      # pointnet.py:12
+REDUCE_ONLY = os.environ.get('CASPR_POINTNET_REDUCE_ONLY', '1') != '0'     # conv3 as statistics + extrema only
 
 
 class PointNetfeat(nn.Module):
@@ -30,12 +33,18 @@ class PointNetfeat(nn.Module):
         `pointfeat_out` / `global_out` may be column slices of a wider concat buffer."""
         pf = ops.linear(rows, self.conv1.weight, self.conv1.bias, out=pointfeat_out)
         ops.groupnorm(pf, samples, rows_per_sample, NUM_GROUPS, self.bn1.weight, self.bn1.bias, relu=True)
+        # only the max over the points of bn3(conv3(.)) is used (pointnet.py:40-42): the last GEMM keeps statistics and
+        # per-channel extrema instead of writing its (rows x 1024) output, and the max-pool is read off them
         h3, st3 = ops.conv_gn_relu_conv(pf, self.conv2, self.bn2, self.conv3, samples, rows_per_sample, NUM_GROUPS,
-                                        stats_b=True)
+                                        stats_b=True, reduce_only=REDUCE_ONLY)
         if global_out is None:
             global_out = torch.empty(samples, self.out_size, dtype=torch.float32, device=rows.device)
-        ops.groupnorm(h3, samples, rows_per_sample, NUM_GROUPS, self.bn3.weight, self.bn3.bias, relu=False,
-                      write_back=False, maxout=global_out, stats=st3)
+        if h3 is None:
+            ops.gn_max_from_extrema(st3, samples, rows_per_sample, NUM_GROUPS, self.bn3.weight, self.bn3.bias,
+                                    global_out, eps=self.bn3.eps)
+        else:
+            ops.groupnorm(h3, samples, rows_per_sample, NUM_GROUPS, self.bn3.weight, self.bn3.bias, relu=False,
+                          write_back=False, maxout=global_out, stats=st3)
         return global_out, pf
 
     def forward(self, x):

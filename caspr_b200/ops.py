@@ -221,10 +221,13 @@ def tc_eligible(rows, cin, cout):
             cout % 4 == 0)
 
 
-def conv_gn_relu_conv(x, conv_a, gn_a, conv_b, samples, rows_per_sample, groups, out=None, stats_b=False):
+def conv_gn_relu_conv(x, conv_a, gn_a, conv_b, samples, rows_per_sample, groups, out=None, stats_b=False,
+                      reduce_only=False):
     """Conv1d -> GroupNorm -> ReLU -> Conv1d on rows.  On the tensor-core path the first GEMM's epilogue
     accumulates the GroupNorm statistics and the second GEMM normalises while splitting its operand, so the
-    normalised intermediate never exists in memory.  Returns y (and y's statistics if stats_b)."""
+    normalised intermediate never exists in memory.  Returns y (and y's statistics if stats_b).
+    reduce_only (with stats_b): if the tensor-core path applies, y itself is not produced either - returns
+    (None, (statistics, per-channel extrema)) for `gn_max_from_extrema`; otherwise (y, None) as usual."""
     rows, cin = x.shape
     ca, cb = conv_a.weight.shape[0], conv_b.weight.shape[0]
     # the GEMM epilogue keeps one running GroupNorm group per 32-column chunk: groups of >= 32 channels only
@@ -234,15 +237,20 @@ def conv_gn_relu_conv(x, conv_a, gn_a, conv_b, samples, rows_per_sample, groups,
         h, st = linear(x, conv_a.weight, conv_a.bias, engine='tc', out_stats=(samples, rows_per_sample, groups))
         pn = PendingNorm(st, samples, rows_per_sample, groups, ca, gn_a.weight, gn_a.bias, relu=True, eps=gn_a.eps)
         return linear(h, conv_b.weight, conv_b.bias, out=out, engine='tc', in_norm=pn,
-                      out_stats=(samples, rows_per_sample, groups) if stats_b else None)
+                      out_stats=(samples, rows_per_sample, groups) if stats_b else None,
+                      reduce_only=reduce_only and stats_b)
     h = linear(x, conv_a.weight, conv_a.bias)
     groupnorm(h, samples, rows_per_sample, groups, gn_a.weight, gn_a.bias, eps=gn_a.eps, relu=True)
+    if stats_b and tc_eligible(rows, ca, cb) and rows_per_sample % 32 == 0 and cb // groups >= 32:
+        # the first layer's groups are too narrow for the epilogue statistics, the second layer's are not
+        return linear(h, conv_b.weight, conv_b.bias, out=None if reduce_only else out, engine='tc',
+                      out_stats=(samples, rows_per_sample, groups), reduce_only=reduce_only)
     y = linear(h, conv_b.weight, conv_b.bias, out=out)
     return (y, None) if stats_b else y
 
 
 def linear(x, weight, bias=None, out=None, act_in=ACT_NONE, act_out=ACT_NONE, engine='auto', in_norm=None,
-           out_stats=None, bias_rows_per_sample=0, weight_key=None):
+           out_stats=None, bias_rows_per_sample=0, weight_key=None, reduce_only=False):
     """1x1 Conv1d / Linear on rows: y = act_out(act_in(x) @ W^T + b).
 
     x (rows, Cin) view; weight (Cout, Cin) or Conv1d-shaped (Cout, Cin, 1); out optional (rows, Cout) view.
@@ -250,7 +258,9 @@ def linear(x, weight, bias=None, out=None, act_in=ACT_NONE, act_out=ACT_NONE, en
     Tensor-core engine only: in_norm = PendingNorm of x (normalise while splitting the operand);
     out_stats = (samples, rows_per_sample, groups): also return the fp64 GroupNorm statistics of y;
     bias_rows_per_sample > 0: `bias` is (rows / bias_rows_per_sample, Cout), one bias row per sample;
-    weight_key: the parameter `weight` was derived from (its version keys the cache of split planes)."""
+    weight_key: the parameter `weight` was derived from (its version keys the cache of split planes);
+    reduce_only (with out_stats): y is not written; returns (None, (statistics, extrema)) where extrema holds the
+    per-(sample, channel) max / min of y as ordered keys (`gn_max_from_extrema`)."""
     x, ldx = _rows2d(x, 'x')
     w = weight.reshape(weight.shape[0], weight.shape[1])
     _f32(w, 'weight')
@@ -258,6 +268,25 @@ def linear(x, weight, bias=None, out=None, act_in=ACT_NONE, act_out=ACT_NONE, en
     rows, cin = x.shape
     cout = w.shape[0]
     assert w.shape[1] == cin
+    if reduce_only:
+        assert engine == 'tc' and out_stats is not None and out is None and act_out == ACT_NONE and cout % 4 == 0
+        samples, rps, groups = out_stats
+        stats_t = torch.empty(samples * groups * 2, dtype=torch.float64, device=x.device)
+        ext_t = torch.empty(samples, 2, cout, dtype=torch.int32, device=x.device)
+        stats_s = _lib.GnStats(stats_t.data_ptr(), rps, groups, ext_t.data_ptr())
+        fold_s = None
+        if in_norm is not None:
+            fold_s = _lib.GnFold(in_norm.table().data_ptr(), in_norm.rows_per_sample, int(in_norm.relu))
+        ws_bytes = lib.caspr_linear_tc_workspace_bytes(rows, cin, cout)
+        ws, ws_ptr = _aligned_bytes(ws_bytes, x.device)
+        prepared = _prepared_weights(weight, w, weight_key)
+        _count('linear_tc')
+        check(lib.caspr_linear_tc(_p(x), ldx, _p(w), cin, _p(bias), None, 0, rows, cin, cout, act_in, act_out,
+                                  ctypes.c_void_p(prepared) if prepared else None,
+                                  ctypes.byref(fold_s) if fold_s is not None else None, ctypes.byref(stats_s),
+                                  int(bias_rows_per_sample), ctypes.c_void_p(ws_ptr), ws_bytes, _stream()),
+              'caspr_linear_tc')
+        return None, (stats_t, ext_t)
     if out is None:
         out = torch.empty(rows, cout, dtype=torch.float32, device=x.device)
     out, ldy = _rows2d(out, 'out')
@@ -281,7 +310,7 @@ def linear(x, weight, bias=None, out=None, act_in=ACT_NONE, act_out=ACT_NONE, en
         if out_stats is not None:
             samples, rps, groups = out_stats
             stats_t = torch.empty(samples * groups * 2, dtype=torch.float64, device=x.device)
-            stats_s = _lib.GnStats(stats_t.data_ptr(), rps, groups)
+            stats_s = _lib.GnStats(stats_t.data_ptr(), rps, groups, None)
         ws_bytes = lib.caspr_linear_tc_workspace_bytes(rows, cin, cout)
         ws, ws_ptr = _aligned_bytes(ws_bytes, x.device)
         # weights are split once per (storage, in-place version); CUDA graphs that captured a call are keyed
@@ -464,6 +493,19 @@ def groupnorm_project(x, samples, rows_per_sample, groups, gamma, beta, stats, w
                                       _p(maxout), ld_max, _p(stats), _p(w2d), _p(bias), w2d.shape[0], int(act),
                                       _p(out), out.shape[1], _stream()), 'caspr_groupnorm_project')
     return out
+
+
+def gn_max_from_extrema(stats_ext, samples, rows_per_sample, groups, gamma, beta, maxout, eps=1e-5):
+    """max over each sample's rows of GroupNorm(y) from the statistics and per-channel extrema a `linear(...,
+    reduce_only=True)` call left behind (the normalisation is monotone per channel): y never existed in memory."""
+    stats, ext = stats_ext
+    C = ext.shape[2]
+    maxout, ld_max = _rows2d(maxout, 'maxout')
+    assert maxout.shape == (samples, C)
+    _count('gn_max_from_extrema')
+    check(lib.caspr_gn_max_from_extrema(_p(stats), _p(ext), samples, rows_per_sample, C, groups, _p(gamma), _p(beta),
+                                        float(eps), _p(maxout), ld_max, _stream()), 'caspr_gn_max_from_extrema')
+    return maxout
 
 
 def augment_xyz(x4):

@@ -176,7 +176,17 @@ typedef struct {
 typedef struct {
   double* stats;             /* [samples][groups][2] */
   int rows_per_sample, groups;
+  /* Optional (may be NULL): [samples][2][Cout] order-preserving uint keys of the per-channel MAX and MIN of the output
+   * over each sample's rows (initialised by the call).  When set, Y is NOT written (may be NULL): a GroupNorm followed
+   * by a max-pool only needs the statistics and these extrema - the affine map x -> (x - mean) * rstd * gamma + beta is
+   * monotone per channel, so its maximum over the rows is its value at the max (gamma >= 0) or the min (gamma < 0) of x,
+   * bit for bit: caspr_gn_max_from_extrema.  The activation itself never exists in memory (pointnet.py:40-42). */
+  unsigned* extrema;
 } caspr_gn_stats;
+/* maxout[s, c] = max over the rows of sample s of GroupNorm(x)[row, c], from the statistics and extrema above. */
+int caspr_gn_max_from_extrema(const double* stats, const unsigned* extrema, int samples, int rows_per_sample, int C,
+                              int groups, const float* gamma, const float* beta, float eps, float* maxout,
+                              int ld_max, void* stream);
 int caspr_gn_table(const double* stats, int samples, int groups, int rows_per_sample, int C, float eps,
                    const float* gamma, const float* beta, float* table, void* stream);
 

@@ -229,6 +229,33 @@ def test_groupnorm_matches_torch(ops, samples, rps, C, relu):
     assert _rel(mx2, ref.max(2)[0]) < 1e-5
 
 
+@pytest.mark.parametrize('samples,rps,cin,cout', [(2, 2048, 128, 1024), (3, 1056, 64, 512)])
+def test_gn_max_from_extrema_is_bit_identical(ops, samples, rps, cin, cout):
+    """GroupNorm + max-pool read off the GEMM's statistics and per-channel extrema (the output is never written) against
+    the same GEMM writing its output followed by the GroupNorm max-pool pass: identical bits, also for channels with a
+    negative gamma (where the minimum of the raw output yields the maximum) and a ragged last tile."""
+    g = torch.Generator().manual_seed(cin + cout)
+    rows = samples * rps
+    x = (torch.randn(rows, cin, generator=g) * 1.5).to(DEV)
+    w = (torch.randn(cout, cin, generator=g) / cin ** 0.5).to(DEV)
+    b = (torch.randn(cout, generator=g) * 0.1).to(DEV)
+    gamma = (torch.randn(cout, generator=g)).to(DEV)                       # both signs
+    gamma[5] = 0.0
+    beta = (torch.randn(cout, generator=g) * 0.1).to(DEV)
+    y, st = ops.linear(x, w, b, engine='tc', out_stats=(samples, rps, 16))
+    ref = torch.empty(samples, cout, device=DEV)
+    ops.groupnorm(y, samples, rps, 16, gamma, beta, relu=False, write_back=False, maxout=ref, stats=st)
+    none, st_ext = ops.linear(x, w, b, engine='tc', out_stats=(samples, rps, 16), reduce_only=True)
+    assert none is None
+    got = torch.empty(samples, cout + 8, device=DEV)
+    ops.gn_max_from_extrema(st_ext, samples, rps, 16, gamma, beta, got[:, 4:4 + cout])
+    assert torch.equal(got[:, 4:4 + cout], ref)
+    # and against torch in fp64
+    yd = y.double().view(samples, rps, cout).transpose(1, 2)
+    r64 = torch.nn.functional.group_norm(yd, 16, gamma.double(), beta.double(), eps=1e-5).max(2)[0]
+    assert _rel(ref, r64) < 1e-5
+
+
 @pytest.mark.parametrize('samples,rps,C,P', [(2, 1000, 1600, 4), (3, 77, 64, 1), (1, 5120, 1600, 4), (4, 130, 256, 3)])
 def test_groupnorm_project_matches_chain(ops, samples, rps, C, P):
     """bn2 -> max-pool -> ReLU -> conv3 -> sigmoid of the encoder head in one pass (tpointnet2.py:104-113) vs torch fp64;
