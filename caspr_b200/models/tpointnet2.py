@@ -167,6 +167,14 @@ class TPointNet2(nn.Module):
                                  bias_rows_per_sample=T * N, weight_key=w1)
             pn = ops.PendingNorm(st1, B, T * N, 16, self.latent_feat_size, self.bn1.weight, self.bn1.bias, relu=True,
                                  eps=self.bn1.eps)
+            if not self.regress_tnocs:
+                # only the max-pool of bn2(conv2(.)) is needed (z0): statistics + per-channel extrema instead of the
+                # 1600-wide activation (pointnet.py's global feature uses the same route)
+                _, st_ext = ops.linear(h1, self.conv2.weight, self.conv2.bias, engine='tc', in_norm=pn,
+                                       out_stats=(B, T * N, 16), reduce_only=True)
+                z0 = torch.empty(B, self.latent_feat_size, dtype=torch.float32, device=x.device)
+                ops.gn_max_from_extrema(st_ext, B, T * N, 16, self.bn2.weight, self.bn2.bias, z0, eps=self.bn2.eps)
+                return z0, None
             h2, st2 = ops.linear(h1, self.conv2.weight, self.conv2.bias, out=h1, engine='tc', in_norm=pn,
                                  out_stats=(B, T * N, 16))
         else:
