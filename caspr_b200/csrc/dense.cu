@@ -591,6 +591,45 @@ void launch_gn_apply_vec(dim3 grid, cudaStream_t s, float* X, int ldx, int rows_
 
 }  // namespace
 
+namespace {
+// A handful of rows against a wide layer (per-sequence vectors: the head's global-feature bias, 8 x 1024 -> 1600): the
+// tiled kernel would run 13 CTAs for 120 us.  One warp per output channel streams its weight row once, the input rows
+// sit in shared memory.
+constexpr int kFewRows = 16;
+__global__ void __launch_bounds__(256)
+linear_fewrows_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
+                      const float* __restrict__ bias, float* __restrict__ Y, int ldy, int rows, int Cin, int Cout,
+                      int act_in, int act_out) {
+  extern __shared__ float sx[];                                  // rows x Cin
+  for (int i = threadIdx.x; i < rows * Cin; i += blockDim.x) {
+    const int r = i / Cin, k = i - r * Cin;
+    float v = X[(size_t)r * ldx + k];
+    sx[i] = act_in == CASPR_ACT_RELU ? fmaxf(v, 0.f) : v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= Cout) return;
+  float acc[kFewRows];
+#pragma unroll
+  for (int r = 0; r < kFewRows; ++r) acc[r] = 0.f;
+  const float* w = W + (size_t)c * ldw;
+  for (int k = lane; k < Cin; k += 32) {
+    const float wk = __ldg(w + k);
+#pragma unroll
+    for (int r = 0; r < kFewRows; ++r)
+      if (r < rows) acc[r] = fmaf(wk, sx[r * Cin + k], acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < kFewRows; ++r) {
+    if (r < rows) {                                              // warp-uniform
+      const float v = warp_sum(acc[r]) + (bias ? bias[c] : 0.f);
+      if (lane == 0) Y[(size_t)r * ldy + c] = apply_act(v, act_out);
+    }
+  }
+}
+}  // namespace
+
 extern "C" int caspr_linear(const float* X, int ldx, const float* W, int ldw, const float* bias,
                             float* Y, int ldy, int rows, int Cin, int Cout, int act_in, int act_out,
                             void* stream) {
@@ -598,6 +637,12 @@ extern "C" int caspr_linear(const float* X, int ldx, const float* W, int ldw, co
   CASPR_REQUIRE(ldx >= Cin && ldw >= Cin && ldy >= Cout);
   CASPR_REQUIRE(act_in == CASPR_ACT_NONE || act_in == CASPR_ACT_RELU);
   cudaStream_t s = (cudaStream_t)stream;
+  if (rows <= kFewRows && Cout >= 64 && (size_t)rows * Cin * sizeof(float) <= 48 * 1024) {
+    CASPR_COUNT(); linear_fewrows_kernel<<<ceil_div(Cout, 8), 256, (size_t)rows * Cin * sizeof(float), s>>>(
+        X, ldx, W, ldw, bias, Y, ldy, rows, Cin, Cout, act_in, act_out);
+    CASPR_CHECK_LAUNCH();
+    return CASPR_OK;
+  }
   if (Cout > 64) {
     dim3 grid(ceil_div(rows, 128), ceil_div(Cout, 128));
     CASPR_COUNT(); linear_kernel<128, 128><<<grid, 256, 0, s>>>(X, ldx, W, ldw, bias, Y, ldy, rows, Cin, Cout, act_in, act_out);

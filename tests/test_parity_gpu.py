@@ -112,7 +112,8 @@ def test_three_nn_and_interpolate(ops, n, m):
 
 # ------------------------------------------------------------------------------ dense ops
 @pytest.mark.parametrize('rows,cin,cout', [(1000, 9, 16), (513, 99, 32), (300, 131, 64), (257, 515, 256),
-                                           (129, 1600, 1600), (64, 4, 64), (77, 1600, 4)])
+                                           (129, 1600, 1600), (64, 4, 64), (77, 1600, 4),
+                                           (8, 1024, 1600), (3, 77, 65), (16, 700, 100), (1, 64, 512)])   # few-rows kernel
 def test_linear_matches_fp32(ops, rows, cin, cout):
     g = torch.Generator().manual_seed(rows)
     x = torch.randn(rows, cin, generator=g)
