@@ -669,9 +669,17 @@ AdjWorkspace adj_carve(void* base, int frames, int pts, int H, int C) {
   const size_t n = (size_t)frames * pts;
   const size_t ctot = hyper_ld(H);
   const ParamLayout pl = param_layout(H, C);
-  // chunks of points per frame for the thread-per-channel kernels: enough CTAs for two waves, <= 64 points each
+  // chunks of points per frame for the thread-per-channel kernels: <= 64 points each, and a CTA count that fills whole
+  // waves - these kernels run 512 threads at 34-42 registers, i.e. 3 CTAs per SM = 444 slots, and 640 CTAs (40 frames
+  // x 16 chunks of 64 points) would be one full wave plus a 44 % one
+  const int slots = 148 * 3;
   int nchunk = (2 * 148 + frames - 1) / frames;
   if (nchunk < (pts + kChunkMax - 1) / kChunkMax) nchunk = (pts + kChunkMax - 1) / kChunkMax;
+  {
+    const int waves = (frames * nchunk + slots - 1) / slots;
+    const int fill = waves * slots / frames;                  // chunks per frame that fill `waves` waves
+    if (fill > nchunk) nchunk = fill;
+  }
   if (nchunk > pts) nchunk = pts;
   w.L = (pts + nchunk - 1) / nchunk;
   w.nchunk = (pts + w.L - 1) / w.L;
