@@ -884,14 +884,101 @@ extern "C" size_t caspr_sa_mlp_tc_workspace_bytes(long long rows, int Cin, int C
   return sa_mlp_layout(rows, Cin, C1, C2).total;
 }
 
+namespace {
+// split_rows_kernel on VIRTUAL grouped rows: row (ball, j) = [xyz[idx] - centre | feat[idx]] (the layout of
+// caspr_group_points, PointNet2GroupingLayer) is gathered on the fly, so the grouped tensor - 0.9 GB per encode for SA
+// levels 3-5 at config 2 - is neither written nor read back.  One warp per grouped row, the row is gathered twice (the
+// second time from L1 / L2), same per-row power-of-two scale as split_rows_kernel.
+struct GroupGather {
+  const float *xyz, *new_xyz, *feat;
+  const int32_t* idx;
+  int ld_feat, C, N, M, ns;
+};
+__global__ void __launch_bounds__(256)
+gather_split_rows_kernel(GroupGather gg, long long rows, long long rows_pad, int k_pad, __half2* __restrict__ hi,
+                         __half2* __restrict__ lo, float* __restrict__ inv_scale) {
+  const int lane = threadIdx.x & 31;
+  const int kp2 = k_pad / 2, cols = 3 + gg.C;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows_pad; r += warps) {
+    __half2* h = hi + r * kp2;
+    __half2* l = lo + r * kp2;
+    if (r >= rows) {
+      const __half2 z = __floats2half2_rn(0.f, 0.f);
+      for (int c2 = lane; c2 < kp2; c2 += 32) { h[c2] = z; l[c2] = z; }
+      if (lane == 0) inv_scale[r] = 0.f;
+      continue;
+    }
+    const long long ball = r / gg.ns;
+    const long long src = (ball / gg.M) * gg.N + gg.idx[r];
+    const float* px = gg.xyz + src * 3;
+    const float* pc = gg.new_xyz + ball * 3;
+    const float* pf = gg.feat + src * gg.ld_feat;
+    auto elem = [&](int c) -> float { return c < 3 ? px[c] - pc[c] : pf[c - 3]; };
+    float m = 0.f;
+    for (int c = lane; c < cols; c += 32) m = fmaxf(m, fabsf(elem(c)));
+    m = warp_max(m);
+    float s = 1.f, inv = 1.f;
+    if (m > 0.f && m < 3.0e38f) {
+      int e;
+      frexpf(m, &e);
+      s = ldexpf(1.f, 14 - e);
+      inv = ldexpf(1.f, e - 14);
+    }
+    if (lane == 0) inv_scale[r] = inv;
+    for (int c2 = lane; c2 < kp2; c2 += 32) {
+      const int c = 2 * c2;
+      const float a = (c < cols ? elem(c) : 0.f) * s;
+      const float b = (c + 1 < cols ? elem(c + 1) : 0.f) * s;
+      const __half2 hh = __floats2half2_rn(a, b);
+      const float2 hf = __half22float2(hh);
+      h[c2] = hh;
+      l[c2] = __floats2half2_rn(a - hf.x, b - hf.y);
+    }
+  }
+}
+
+int sa_mlp_tc_impl(const float* X, int ldx, const GroupGather* gg, long long rows, int Cin, int ns,
+                   const void* prep1, const float* b1, const float* g1, const float* e1, int C1,
+                   const void* prep2, const float* b2, const float* g2, const float* e2, int C2,
+                   const void* prep3, const float* b3, const float* g3, const float* e3, int C3,
+                   float eps, float* maxout, int ld_max, void* workspace, size_t workspace_bytes, void* stream);
+}  // namespace
+
+extern "C" int caspr_sa_mlp_tc_grouped(const float* xyz, const float* new_xyz, const float* feat, int ld_feat, int C,
+                                       const int32_t* idx, int B, int N, int M, int ns,
+                                       const void* prep1, const float* b1, const float* g1, const float* e1, int C1,
+                                       const void* prep2, const float* b2, const float* g2, const float* e2, int C2,
+                                       const void* prep3, const float* b3, const float* g3, const float* e3, int C3,
+                                       float eps, float* maxout, int ld_max, void* workspace, size_t workspace_bytes,
+                                       void* stream) {
+  CASPR_REQUIRE(xyz && new_xyz && feat && idx && B > 0 && N > 0 && M > 0 && C > 0 && ld_feat >= C);
+  GroupGather gg;
+  gg.xyz = xyz; gg.new_xyz = new_xyz; gg.feat = feat; gg.idx = idx; gg.ld_feat = ld_feat; gg.C = C; gg.N = N; gg.M = M;
+  gg.ns = ns;
+  return sa_mlp_tc_impl(nullptr, 0, &gg, (long long)B * M * ns, 3 + C, ns, prep1, b1, g1, e1, C1, prep2, b2, g2, e2, C2,
+                        prep3, b3, g3, e3, C3, eps, maxout, ld_max, workspace, workspace_bytes, stream);
+}
+
 extern "C" int caspr_sa_mlp_tc(const float* X, int ldx, long long rows, int Cin, int ns,
                                const void* prep1, const float* b1, const float* g1, const float* e1, int C1,
                                const void* prep2, const float* b2, const float* g2, const float* e2, int C2,
                                const void* prep3, const float* b3, const float* g3, const float* e3, int C3,
                                float eps, float* maxout, int ld_max, void* workspace, size_t workspace_bytes,
                                void* stream) {
-  CASPR_REQUIRE(X && prep1 && prep2 && prep3 && b1 && b2 && b3 && g1 && g2 && g3 && e1 && e2 && e3 && maxout && workspace);
-  CASPR_REQUIRE(rows > 0 && rows % ns == 0 && ldx >= Cin && ld_max >= C3);
+  CASPR_REQUIRE(X && ldx >= Cin);
+  return sa_mlp_tc_impl(X, ldx, nullptr, rows, Cin, ns, prep1, b1, g1, e1, C1, prep2, b2, g2, e2, C2, prep3, b3, g3, e3,
+                        C3, eps, maxout, ld_max, workspace, workspace_bytes, stream);
+}
+
+namespace {
+int sa_mlp_tc_impl(const float* X, int ldx, const GroupGather* gg, long long rows, int Cin, int ns,
+                   const void* prep1, const float* b1, const float* g1, const float* e1, int C1,
+                   const void* prep2, const float* b2, const float* g2, const float* e2, int C2,
+                   const void* prep3, const float* b3, const float* g3, const float* e3, int C3,
+                   float eps, float* maxout, int ld_max, void* workspace, size_t workspace_bytes, void* stream) {
+  CASPR_REQUIRE(prep1 && prep2 && prep3 && b1 && b2 && b3 && g1 && g2 && g3 && e1 && e2 && e3 && maxout && workspace);
+  CASPR_REQUIRE(rows > 0 && rows % ns == 0 && ld_max >= C3);
   CASPR_REQUIRE(caspr_sa_mlp_tc_supported(ns, Cin, C1, C2, C3));
   CASPR_REQUIRE(((uintptr_t)workspace & 1023) == 0 && (((uintptr_t)prep1 | (uintptr_t)prep2 | (uintptr_t)prep3) & 1023) == 0);
   const SaMlpLayout l = sa_mlp_layout(rows, Cin, C1, C2);
@@ -910,7 +997,12 @@ extern "C" int caspr_sa_mlp_tc(const float* X, int ldx, long long rows, int Cin,
       cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
     return CASPR_ELAUNCH;
   // operand planes of the grouped input rows (per-row power-of-two scale)
-  CASPR_COUNT(); launch_split_rows(X, ldx, rows, Cin, l.rows_pad, l.kpad[0], 0, hi[0], lo[0], xinv, NormFold(), 148 * 8, s);
+  if (gg) {
+    CASPR_COUNT(); gather_split_rows_kernel<<<148 * 8, 256, 0, s>>>(*gg, rows, l.rows_pad, l.kpad[0], (__half2*)hi[0],
+                                                                     (__half2*)lo[0], xinv);
+  } else {
+    CASPR_COUNT(); launch_split_rows(X, ldx, rows, Cin, l.rows_pad, l.kpad[0], 0, hi[0], lo[0], xinv, NormFold(), 148 * 8, s);
+  }
   CASPR_CHECK_LAUNCH();
   int rc = sa_mlp_layer_dispatch<false>(C1, hi[0], lo[0], l.rows_pad, l.kpad[0], xinv, 0.f, prep1, Cin, b1, g1, e1, eps, ns,
                                         rows, hi[1], lo[1], l.kpad[1], nullptr, 0, flag, num_sms, s);
@@ -924,8 +1016,6 @@ extern "C" int caspr_sa_mlp_tc(const float* X, int ldx, long long rows, int Cin,
   CASPR_CHECK_LAUNCH();
   return CASPR_OK;
 }
-
-namespace {
 }  // namespace
 
 extern "C" size_t caspr_linear_tc_workspace_bytes(int rows, int Cin, int Cout) {

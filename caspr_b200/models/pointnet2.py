@@ -12,12 +12,15 @@ gather, three_nn, three_interpolate; imports at pointnet2.py:7-10) and torch Con
 this file calls libcaspr_b200.so.  Activations stay channels-last ("rows x channels") from end to
 end, which removes the transposes / contiguous() copies of pointnet2.py:386-387,:408-409.
 """
+import os
+
 import torch
 import torch.nn as nn
 
 from .. import ops
 
 NUM_GROUPS = 16      # pointnet2.py:12
+GATHER_IN_SPLIT = os.environ.get('CASPR_SA_GATHER_IN_SPLIT', '1') != '0'   # SA 3-5: group gather inside the operand split
 
 
 class PointNetFeatureExtractor(nn.Module):
@@ -125,6 +128,13 @@ class PointNet2SetAbstraction(nn.Module):
                 # levels 1-2: gather + three per-ball layers + max in ONE kernel, activations stay in registers
                 ops.sa_fused(xyz, new_xyz, features, bq[s], pointnet.conv_layers, pointnet.bn_layers,
                              out[:, off:off + pointnet.feat_size])
+            elif (features is not None and GATHER_IN_SPLIT and
+                  ops.sa_mlp_tc_supported(grouper.num_samples, self.pointnet_in_channels, widths,
+                                          Bp * M * grouper.num_samples)):
+                # levels 3-5: per-ball GroupNorm in the tcgen05 GEMM epilogues, the group gather folded into the operand
+                # split of the first layer (the grouped tensor never exists)
+                ops.sa_mlp_tc_grouped(xyz, new_xyz, features, bq[s], pointnet.conv_layers, pointnet.bn_layers,
+                                      out[:, off:off + pointnet.feat_size])
             else:
                 rows = ops.group_points(xyz, new_xyz, features, bq[s])
                 pointnet.forward_rows(rows, Bp * M, grouper.num_samples, out[:, off:off + pointnet.feat_size])

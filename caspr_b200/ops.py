@@ -380,6 +380,31 @@ def sa_mlp_tc(rows, ns, convs, norms, out):
     return out
 
 
+def sa_mlp_tc_grouped(xyz, new_xyz, feat, idx, convs, norms, out):
+    """`sa_mlp_tc` with the group gather folded into the operand split: xyz (B,N,3), new_xyz (B,M,3), feat (B,N,C) view,
+    idx (B,M,ns) -> out (B*M, C3) view.  The grouped rows never exist in memory."""
+    B, N, _ = xyz.shape
+    M, ns = idx.shape[1], idx.shape[2]
+    assert feat.dim() == 3 and feat.stride(2) == 1 and feat.stride(0) == N * feat.stride(1)
+    assert xyz.is_contiguous() and new_xyz.is_contiguous() and idx.is_contiguous()
+    C, ld_feat = feat.shape[2], feat.stride(1)
+    out, ld_out = _rows2d(out, 'out')
+    args = []
+    for conv, gn in zip(convs, norms):
+        w = conv.weight.reshape(conv.weight.shape[0], conv.weight.shape[1])
+        assert w.is_contiguous() and w.dtype == torch.float32
+        args += [ctypes.c_void_p(_prepared_weights(conv.weight, w)), _p(conv.bias), _p(gn.weight), _p(gn.bias),
+                 w.shape[0]]
+    c1, c2 = convs[0].weight.shape[0], convs[1].weight.shape[0]
+    nb = lib.caspr_sa_mlp_tc_workspace_bytes(B * M * ns, 3 + C, c1, c2)
+    ws, ws_ptr = _aligned_bytes(nb, xyz.device)
+    _count('sa_mlp_tc_grouped')
+    check(lib.caspr_sa_mlp_tc_grouped(_p(xyz), _p(new_xyz), _p(feat), ld_feat, C, _p(idx), B, N, M, ns, *args,
+                                      float(norms[0].eps), _p(out), ld_out, ctypes.c_void_p(ws_ptr), nb, _stream()),
+          'caspr_sa_mlp_tc_grouped')
+    return out
+
+
 SA_FUSED = True                 # module-wide switch (accuracy / timing studies): fused set-abstraction scale kernel
 SA_MMA = os.environ.get('CASPR_SA_MMA', '1') != '0'     # its tensor-core (mma.sync) version, SA levels 1-2
 

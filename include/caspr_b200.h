@@ -126,6 +126,17 @@ int caspr_sa_mlp_tc(const float* X, int ldx, long long rows, int Cin, int ns,
                     const void* prep3, const float* b3, const float* g3, const float* e3, int C3,
                     float eps, float* maxout, int ld_max, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same with the group gather of caspr_group_points folded into the operand split: the grouped rows
+ * [xyz[idx] - centre | feat[idx]] (B*M*ns x (3 + C)) are formed on the fly and never exist in memory.  Arguments as
+ * caspr_group_points (xyz (B,N,3), new_xyz (B,M,3), feat (B,N,C) with row stride ld_feat, idx (B,M,ns)); workspace as
+ * caspr_sa_mlp_tc_workspace_bytes(B*M*ns, 3 + C, C1, C2). */
+int caspr_sa_mlp_tc_grouped(const float* xyz, const float* new_xyz, const float* feat, int ld_feat, int C,
+                            const int32_t* idx, int B, int N, int M, int ns,
+                            const void* prep1, const float* b1, const float* g1, const float* e1, int C1,
+                            const void* prep2, const float* b2, const float* g2, const float* e2, int C2,
+                            const void* prep3, const float* b3, const float* g3, const float* e3, int C3,
+                            float eps, float* maxout, int ld_max, void* workspace, size_t workspace_bytes, void* stream);
+
 /* One whole scale of a set-abstraction level in a single kernel (pointnet2.py:391-401,649-708): group gather
  * ([xyz[idx]-centre | feat[idx]], caspr_group_points) -> three layers Conv1d(k=1) + GroupNorm(16) (+ReLU after the
  * first two, pointnet2.py:693) with per-ball statistics -> max over the ball's ns rows.  Activations never leave

@@ -440,6 +440,38 @@ def test_sa_mlp_tc_matches_reference_chain(ops, ns, cin, widths):
     assert float(out[:, :4].abs().sum()) == 0 and float(out[:, 4 + widths[2]:].abs().sum()) == 0
 
 
+@pytest.mark.parametrize('ns,C,widths', [(16, 128, (64, 64, 128)), (32, 256, (128, 256, 256))])
+def test_sa_mlp_tc_grouped_equals_materialised_rows(ops, ns, C, widths):
+    """The group gather folded into the operand split (`caspr_sa_mlp_tc_grouped`) must give the bits of the
+    two-step route (`group_points` then `sa_mlp_tc`): the planes it writes are the same numbers."""
+    g = torch.Generator().manual_seed(ns + C)
+    B, N, M = 3, 640, 96
+    xyz = torch.rand(B, N, 3, generator=g).to(DEV)
+    _, new_xyz = ops.fps(xyz, M)
+    i16, i32 = ops.ball_query2(xyz, new_xyz, 0.15, 16, 0.3, 32)
+    idx = i16 if ns == 16 else i32
+    wide = torch.randn(B, N, C + 5, generator=g).to(DEV)
+    feat = wide[:, :, 5:]                                           # strided view
+    convs, norms = [], []
+    dims = [3 + C] + list(widths)
+    for i in range(3):
+        conv = torch.nn.Conv1d(dims[i], dims[i + 1], 1)
+        gn = torch.nn.GroupNorm(16, dims[i + 1])
+        with torch.no_grad():
+            gn.weight.copy_(torch.rand(dims[i + 1], generator=g) + 0.5)
+            gn.bias.copy_(0.2 * torch.randn(dims[i + 1], generator=g))
+        convs.append(conv.to(DEV))
+        norms.append(gn.to(DEV))
+    assert ops.sa_mlp_tc_supported(ns, 3 + C, list(widths), B * M * ns)
+    rows = ops.group_points(xyz, new_xyz, feat, idx)
+    ref = torch.zeros(B * M, widths[2], device=DEV)
+    ops.sa_mlp_tc(rows, ns, convs, norms, ref)
+    out = torch.zeros(B * M, widths[2] + 8, device=DEV)
+    ops.sa_mlp_tc_grouped(xyz, new_xyz, feat, idx, convs, norms, out[:, 8:])
+    assert torch.equal(out[:, 8:], ref)
+    assert float(out[:, :8].abs().sum()) == 0
+
+
 def test_augment_and_broadcast(ops):
     x, _ = synthetic_sequences(1, 2, 100, seed=0)
     x4 = x.view(-1, 4)
