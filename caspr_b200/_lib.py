@@ -139,6 +139,9 @@ SIGNATURES = {
                         [c_float, _P, c_int, _P, c_size_t, _P]),
     'caspr_sa_mlp_tc_grouped': (c_int, [_P, _P, _P, c_int, c_int, _P, c_int, c_int, c_int, c_int] + [_P, _P, _P, _P, c_int] * 3 +
                                 [c_float, _P, c_int, _P, c_size_t, _P]),
+    'caspr_sa_mlp_tc_delayed_workspace_bytes': (c_size_t, [c_longlong, c_int, c_int]),
+    'caspr_sa_mlp_tc_delayed': (c_int, [_P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, _P, c_int] +
+                                [_P, _P, _P, _P, c_int] * 2 + [c_float, _P, c_int, _P, c_size_t, _P]),
     'caspr_cnf_fused_debug_read': (c_int, [_P, c_int]),
     'caspr_ransac_pose_workspace_bytes': (c_size_t, [c_int, c_int]),
     'caspr_ransac_pose': (c_int, [_P, _P, _P, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),

@@ -10,6 +10,7 @@
 // scales exactly, adds the bias, applies the activation and stores fp32 rows with the caller's
 // leading dimension.
 #include "common.cuh"
+#include <algorithm>
 #include "tc_gemm.cuh"
 
 namespace {
@@ -893,6 +894,10 @@ struct GroupGather {
   const float *xyz, *new_xyz, *feat;
   const int32_t* idx;
   int ld_feat, C, N, M, ns;
+  // "delayed aggregation" of the first layer: P = feat . W1[:, 3:]^T per SOURCE point (ld ldp); W1 for its xyz columns
+  const float* P;
+  const float* W1;
+  int ldp, ldw1;
 };
 __global__ void __launch_bounds__(256)
 gather_split_rows_kernel(GroupGather gg, long long rows, long long rows_pad, int k_pad, __half2* __restrict__ hi,
@@ -938,12 +943,130 @@ gather_split_rows_kernel(GroupGather gg, long long rows, long long rows_pad, int
   }
 }
 
+// First per-ball layer with the product taken BEFORE the gather: W1 . [xyz[idx] - centre | feat[idx]] + b =
+// P[idx] + W1[:, :3] . (xyz[idx] - centre) + b with P = feat . W1[:, 3:]^T computed once per source point (every point is
+// a member of ~24 balls at SA level 3, so the layer costs 1/24 of the grouped product and the gather moves C1 instead of
+// 3 + C channels).  A thread owns a grouped row like the threads of BallNormEpilogue: per-ball GroupNorm by shuffles
+// over the ball's 16 / 32 lanes, ReLU, fp16 hi / lo planes of the next layer with the fixed scale kBallPlaneScale.
+template <int CPG>
+__global__ void __launch_bounds__(256)
+sa_first_layer_kernel(GroupGather gg, const float* __restrict__ bias, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, float eps, long long rows, int C1, __half* __restrict__ out_hi,
+                      __half* __restrict__ out_lo, int ld_out, int* __restrict__ range_flag) {
+  extern __shared__ float sp[];                                  // [wx | wy | wz | bias | gamma | beta] x C1
+  float* swx = sp; float* swy = swx + C1; float* swz = swy + C1;
+  float* sb = swz + C1; float* sg = sb + C1; float* se = sg + C1;
+  for (int c = threadIdx.x; c < C1; c += blockDim.x) {
+    swx[c] = gg.W1[(size_t)c * gg.ldw1]; swy[c] = gg.W1[(size_t)c * gg.ldw1 + 1]; swz[c] = gg.W1[(size_t)c * gg.ldw1 + 2];
+    sb[c] = bias[c]; sg[c] = gamma[c]; se[c] = beta[c];
+  }
+  __syncthreads();
+  constexpr int kChunk = 32, kGroups = kChunk / CPG;
+  const int lane = threadIdx.x & 31, ns = gg.ns;
+  const float inv_n = 1.f / (float)(ns * CPG);
+  const long long tiles = (rows + 31) / 32, warps = (long long)gridDim.x * (blockDim.x >> 5);
+  float range_max = 0.f;
+  for (long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < tiles; t += warps) {
+    const long long row = t * 32 + lane;
+    const bool row_ok = row < rows;                              // uniform over a ball (rows % ns == 0)
+    const long long r = row_ok ? row : rows - 1;
+    const long long ball = r / ns;
+    const long long src = (ball / gg.M) * gg.N + gg.idx[r];
+    const float dx = gg.xyz[src * 3] - gg.new_xyz[ball * 3], dy = gg.xyz[src * 3 + 1] - gg.new_xyz[ball * 3 + 1],
+                dz = gg.xyz[src * 3 + 2] - gg.new_xyz[ball * 3 + 2];
+    const float* p = gg.P + src * gg.ldp;
+#pragma unroll 1
+    for (int c = 0; c < C1; c += kChunk) {
+      float x[kChunk];
+#pragma unroll
+      for (int j4 = 0; j4 < kChunk / 4; ++j4) {
+        const float4 v = *reinterpret_cast<const float4*>(p + c + 4 * j4);
+        const float pv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int ch = c + 4 * j4 + k;
+          x[4 * j4 + k] = fmaf(swz[ch], dz, fmaf(swy[ch], dy, fmaf(swx[ch], dx, pv[k]))) + sb[ch];
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g) {
+        float sm = 0.f;
+#pragma unroll
+        for (int k = 0; k < CPG; ++k) sm += x[g * CPG + k];
+        for (int off = ns >> 1; off > 0; off >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, off);
+        const float mean = sm * inv_n;
+        float qv = 0.f;
+#pragma unroll
+        for (int k = 0; k < CPG; ++k) {
+          const float d = x[g * CPG + k] - mean;
+          x[g * CPG + k] = d;
+          qv = fmaf(d, d, qv);
+        }
+        for (int off = ns >> 1; off > 0; off >>= 1) qv += __shfl_xor_sync(0xffffffffu, qv, off);
+        const float rstd = 1.f / sqrtf(qv * inv_n + eps);
+#pragma unroll
+        for (int k = 0; k < CPG; ++k) x[g * CPG + k] *= rstd;
+      }
+      if (row_ok) {
+        uint32_t h[kChunk / 2], l2[kChunk / 2];
+#pragma unroll
+        for (int u = 0; u < kChunk / 2; ++u) {
+          const float a = fmaxf(fmaf(x[2 * u], sg[c + 2 * u], se[c + 2 * u]), 0.f) * kBallPlaneScale;
+          const float b = fmaxf(fmaf(x[2 * u + 1], sg[c + 2 * u + 1], se[c + 2 * u + 1]), 0.f) * kBallPlaneScale;
+          range_max = fmaxf(range_max, fmaxf(a, b));
+          tcg::split2(a, b, h[u], l2[u]);
+        }
+        __half* ph = out_hi + row * ld_out + c;
+        __half* pl = out_lo + row * ld_out + c;
+#pragma unroll
+        for (int j16 = 0; j16 < kChunk / 16; ++j16) {
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ph + 16 * j16),
+                       "r"(h[8 * j16]), "r"(h[8 * j16 + 1]), "r"(h[8 * j16 + 2]), "r"(h[8 * j16 + 3]),
+                       "r"(h[8 * j16 + 4]), "r"(h[8 * j16 + 5]), "r"(h[8 * j16 + 6]), "r"(h[8 * j16 + 7]) : "memory");
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(pl + 16 * j16),
+                       "r"(l2[8 * j16]), "r"(l2[8 * j16 + 1]), "r"(l2[8 * j16 + 2]), "r"(l2[8 * j16 + 3]),
+                       "r"(l2[8 * j16 + 4]), "r"(l2[8 * j16 + 5]), "r"(l2[8 * j16 + 6]), "r"(l2[8 * j16 + 7]) : "memory");
+        }
+      }
+    }
+    if (row_ok) {
+      for (int cc = C1; cc < ld_out; cc += 8) {                  // K padding of the next layer's operand
+        *reinterpret_cast<uint4*>(out_hi + row * ld_out + cc) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(out_lo + row * ld_out + cc) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  }
+  if (range_max > 65504.f) atomicOr(range_flag, 1);
+}
+
 int sa_mlp_tc_impl(const float* X, int ldx, const GroupGather* gg, long long rows, int Cin, int ns,
                    const void* prep1, const float* b1, const float* g1, const float* e1, int C1,
                    const void* prep2, const float* b2, const float* g2, const float* e2, int C2,
                    const void* prep3, const float* b3, const float* g3, const float* e3, int C3,
                    float eps, float* maxout, int ld_max, void* workspace, size_t workspace_bytes, void* stream);
 }  // namespace
+
+extern "C" size_t caspr_sa_mlp_tc_delayed_workspace_bytes(long long rows, int C1, int C2) {
+  if (rows <= 0 || C1 <= 0 || C2 <= 0) return 0;
+  return sa_mlp_layout(rows, 0, C1, C2).total;
+}
+
+extern "C" int caspr_sa_mlp_tc_delayed(const float* xyz, const float* new_xyz, const float* P, int ldp, const int32_t* idx,
+                                       int B, int N, int M, int ns, const float* W1, int ldw1, const float* b1,
+                                       const float* g1, const float* e1, int C1,
+                                       const void* prep2, const float* b2, const float* g2, const float* e2, int C2,
+                                       const void* prep3, const float* b3, const float* g3, const float* e3, int C3,
+                                       float eps, float* maxout, int ld_max, void* workspace, size_t workspace_bytes,
+                                       void* stream) {
+  CASPR_REQUIRE(xyz && new_xyz && P && idx && W1 && B > 0 && N > 0 && M > 0 && ldp >= C1 && ldw1 >= 3);
+  CASPR_REQUIRE(ldp % 4 == 0 && ((uintptr_t)P & 15) == 0 && (C1 == 64 || C1 == 128 || C1 == 256));
+  GroupGather gg;
+  memset(&gg, 0, sizeof(gg));
+  gg.xyz = xyz; gg.new_xyz = new_xyz; gg.idx = idx; gg.N = N; gg.M = M; gg.ns = ns;
+  gg.P = P; gg.ldp = ldp; gg.W1 = W1; gg.ldw1 = ldw1;
+  return sa_mlp_tc_impl(nullptr, 0, &gg, (long long)B * M * ns, 64, ns, nullptr, b1, g1, e1, C1, prep2, b2, g2, e2, C2,
+                        prep3, b3, g3, e3, C3, eps, maxout, ld_max, workspace, workspace_bytes, stream);
+}
 
 extern "C" int caspr_sa_mlp_tc_grouped(const float* xyz, const float* new_xyz, const float* feat, int ld_feat, int C,
                                        const int32_t* idx, int B, int N, int M, int ns,
@@ -954,6 +1077,7 @@ extern "C" int caspr_sa_mlp_tc_grouped(const float* xyz, const float* new_xyz, c
                                        void* stream) {
   CASPR_REQUIRE(xyz && new_xyz && feat && idx && B > 0 && N > 0 && M > 0 && C > 0 && ld_feat >= C);
   GroupGather gg;
+  memset(&gg, 0, sizeof(gg));
   gg.xyz = xyz; gg.new_xyz = new_xyz; gg.feat = feat; gg.idx = idx; gg.ld_feat = ld_feat; gg.C = C; gg.N = N; gg.M = M;
   gg.ns = ns;
   return sa_mlp_tc_impl(nullptr, 0, &gg, (long long)B * M * ns, 3 + C, ns, prep1, b1, g1, e1, C1, prep2, b2, g2, e2, C2,
@@ -977,11 +1101,13 @@ int sa_mlp_tc_impl(const float* X, int ldx, const GroupGather* gg, long long row
                    const void* prep2, const float* b2, const float* g2, const float* e2, int C2,
                    const void* prep3, const float* b3, const float* g3, const float* e3, int C3,
                    float eps, float* maxout, int ld_max, void* workspace, size_t workspace_bytes, void* stream) {
-  CASPR_REQUIRE(prep1 && prep2 && prep3 && b1 && b2 && b3 && g1 && g2 && g3 && e1 && e2 && e3 && maxout && workspace);
+  const bool delayed = gg && gg->P;
+  CASPR_REQUIRE((prep1 || delayed) && prep2 && prep3 && b1 && b2 && b3 && g1 && g2 && g3 && e1 && e2 && e3 && maxout &&
+                workspace);
   CASPR_REQUIRE(rows > 0 && rows % ns == 0 && ld_max >= C3);
   CASPR_REQUIRE(caspr_sa_mlp_tc_supported(ns, Cin, C1, C2, C3));
   CASPR_REQUIRE(((uintptr_t)workspace & 1023) == 0 && (((uintptr_t)prep1 | (uintptr_t)prep2 | (uintptr_t)prep3) & 1023) == 0);
-  const SaMlpLayout l = sa_mlp_layout(rows, Cin, C1, C2);
+  const SaMlpLayout l = sa_mlp_layout(rows, delayed ? 0 : Cin, C1, C2);
   if (workspace_bytes < l.total) return CASPR_EWORKSPACE;
   CASPR_REQUIRE(l.rows_pad / kBM < (1ll << 30));
   cudaStream_t s = (cudaStream_t)stream;
@@ -996,6 +1122,26 @@ int sa_mlp_tc_impl(const float* X, int ldx, const GroupGather* gg, long long row
   if (cudaGetDevice(&dev) != cudaSuccess ||
       cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
     return CASPR_ELAUNCH;
+  if (delayed) {
+    const int blocks = (int)std::min<long long>((rows + 255) / 256, 148 * 8);
+    const size_t smem = (size_t)6 * C1 * sizeof(float);
+#define CASPR_SA_FIRST(CPG) \
+    sa_first_layer_kernel<CPG><<<blocks, 256, smem, s>>>(*gg, b1, g1, e1, eps, rows, C1, hi[1], lo[1], l.kpad[1], flag)
+    CASPR_COUNT();
+    if (C1 == 64) CASPR_SA_FIRST(4);
+    else if (C1 == 128) CASPR_SA_FIRST(8);
+    else CASPR_SA_FIRST(16);
+#undef CASPR_SA_FIRST
+    CASPR_CHECK_LAUNCH();
+    int rc = sa_mlp_layer_dispatch<false>(C2, hi[1], lo[1], l.rows_pad, l.kpad[1], nullptr, 1.f / kBallPlaneScale, prep2, C1,
+                                          b2, g2, e2, eps, ns, rows, hi[2], lo[2], l.kpad[2], nullptr, 0, flag, num_sms, s);
+    if (rc) return rc;
+    rc = sa_mlp_layer_dispatch<true>(C3, hi[2], lo[2], l.rows_pad, l.kpad[2], nullptr, 1.f / kBallPlaneScale, prep3, C2, b3,
+                                     g3, e3, eps, ns, rows, nullptr, nullptr, 0, maxout, ld_max, flag, num_sms, s);
+    if (rc) return rc;
+    CASPR_CHECK_LAUNCH();
+    return CASPR_OK;
+  }
   // operand planes of the grouped input rows (per-row power-of-two scale)
   if (gg) {
     CASPR_COUNT(); gather_split_rows_kernel<<<148 * 8, 256, 0, s>>>(*gg, rows, l.rows_pad, l.kpad[0], (__half2*)hi[0],

@@ -21,6 +21,7 @@ from .. import ops
 
 NUM_GROUPS = 16      # pointnet2.py:12
 GATHER_IN_SPLIT = os.environ.get('CASPR_SA_GATHER_IN_SPLIT', '1') != '0'   # SA 3-5: group gather inside the operand split
+DELAYED_FIRST_LAYER = os.environ.get('CASPR_SA_DELAYED', '1') != '0'       # SA 3-5: first layer before the gather
 
 
 class PointNetFeatureExtractor(nn.Module):
@@ -133,8 +134,13 @@ class PointNet2SetAbstraction(nn.Module):
                                           Bp * M * grouper.num_samples)):
                 # levels 3-5: per-ball GroupNorm in the tcgen05 GEMM epilogues, the group gather folded into the operand
                 # split of the first layer (the grouped tensor never exists)
-                ops.sa_mlp_tc_grouped(xyz, new_xyz, features, bq[s], pointnet.conv_layers, pointnet.bn_layers,
-                                      out[:, off:off + pointnet.feat_size])
+                if DELAYED_FIRST_LAYER and widths[0] in (64, 128, 256):
+                    # first layer's product once per source point, gathered afterwards (every point sits in ~24 balls)
+                    ops.sa_mlp_tc_delayed(xyz, new_xyz, features, bq[s], pointnet.conv_layers, pointnet.bn_layers,
+                                          out[:, off:off + pointnet.feat_size])
+                else:
+                    ops.sa_mlp_tc_grouped(xyz, new_xyz, features, bq[s], pointnet.conv_layers, pointnet.bn_layers,
+                                          out[:, off:off + pointnet.feat_size])
             else:
                 rows = ops.group_points(xyz, new_xyz, features, bq[s])
                 pointnet.forward_rows(rows, Bp * M, grouper.num_samples, out[:, off:off + pointnet.feat_size])

@@ -405,6 +405,36 @@ def sa_mlp_tc_grouped(xyz, new_xyz, feat, idx, convs, norms, out):
     return out
 
 
+def sa_mlp_tc_delayed(xyz, new_xyz, feat, idx, convs, norms, out):
+    """`sa_mlp_tc_grouped` with the first layer's product taken before the gather: P = feat . W1[:, 3:]^T once per
+    source point, then one kernel gathers P, adds W1[:, :3] . (xyz - centre) + b1 and normalises per ball."""
+    B, N, _ = xyz.shape
+    M, ns = idx.shape[1], idx.shape[2]
+    assert feat.dim() == 3 and feat.stride(2) == 1 and feat.stride(0) == N * feat.stride(1)
+    assert xyz.is_contiguous() and new_xyz.is_contiguous() and idx.is_contiguous()
+    C = feat.shape[2]
+    w1 = convs[0].weight
+    c1, c2 = w1.shape[0], convs[1].weight.shape[0]
+    w1_2d = w1.reshape(c1, 3 + C)
+    assert w1_2d.is_contiguous() and w1.dtype == torch.float32
+    w_feat = derived_weight(w1, 'sa_feature_columns', lambda w: w.reshape(w.shape[0], -1)[:, 3:])
+    prod = linear(feat.reshape(B * N, C) if feat.is_contiguous() else feat.flatten(0, 1), w_feat, None, weight_key=w1)
+    out, ld_out = _rows2d(out, 'out')
+    args = [_p(w1_2d), 3 + C, _p(convs[0].bias), _p(norms[0].weight), _p(norms[0].bias), c1]
+    for conv, gn in zip(convs[1:], norms[1:]):
+        w = conv.weight.reshape(conv.weight.shape[0], conv.weight.shape[1])
+        assert w.is_contiguous() and w.dtype == torch.float32
+        args += [ctypes.c_void_p(_prepared_weights(conv.weight, w)), _p(conv.bias), _p(gn.weight), _p(gn.bias),
+                 w.shape[0]]
+    nb = lib.caspr_sa_mlp_tc_delayed_workspace_bytes(B * M * ns, c1, c2)
+    ws, ws_ptr = _aligned_bytes(nb, xyz.device)
+    _count('sa_mlp_tc_delayed')
+    check(lib.caspr_sa_mlp_tc_delayed(_p(xyz), _p(new_xyz), _p(prod), prod.stride(0), _p(idx), B, N, M, ns, *args,
+                                      float(norms[0].eps), _p(out), ld_out, ctypes.c_void_p(ws_ptr), nb, _stream()),
+          'caspr_sa_mlp_tc_delayed')
+    return out
+
+
 SA_FUSED = True                 # module-wide switch (accuracy / timing studies): fused set-abstraction scale kernel
 SA_MMA = os.environ.get('CASPR_SA_MMA', '1') != '0'     # its tensor-core (mma.sync) version, SA levels 1-2
 

@@ -137,6 +137,20 @@ int caspr_sa_mlp_tc_grouped(const float* xyz, const float* new_xyz, const float*
                             const void* prep3, const float* b3, const float* g3, const float* e3, int C3,
                             float eps, float* maxout, int ld_max, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same with the first layer's product taken BEFORE the gather ("delayed aggregation"):
+ *   W1 . [xyz[idx] - centre | feat[idx]] + b1 = P[idx] + W1[:, :3] . (xyz[idx] - centre) + b1,
+ * P (B*N, C1) = feat . W1[:, 3:]^T computed by the caller once per source point (caspr_linear / caspr_linear_tc; row
+ * stride ldp, 16-byte aligned rows).  One kernel gathers P, adds the xyz term, applies the per-ball GroupNorm + ReLU and
+ * writes the second layer's operand planes; layers 2 and 3 as in caspr_sa_mlp_tc.  W1: the first layer's weight
+ * (C1, 3 + C) with row stride ldw1 (only its first three columns are read).  C1 in {64, 128, 256}. */
+size_t caspr_sa_mlp_tc_delayed_workspace_bytes(long long rows, int C1, int C2);
+int caspr_sa_mlp_tc_delayed(const float* xyz, const float* new_xyz, const float* P, int ldp, const int32_t* idx,
+                            int B, int N, int M, int ns, const float* W1, int ldw1, const float* b1, const float* g1,
+                            const float* e1, int C1,
+                            const void* prep2, const float* b2, const float* g2, const float* e2, int C2,
+                            const void* prep3, const float* b3, const float* g3, const float* e3, int C3,
+                            float eps, float* maxout, int ld_max, void* workspace, size_t workspace_bytes, void* stream);
+
 /* One whole scale of a set-abstraction level in a single kernel (pointnet2.py:391-401,649-708): group gather
  * ([xyz[idx]-centre | feat[idx]], caspr_group_points) -> three layers Conv1d(k=1) + GroupNorm(16) (+ReLU after the
  * first two, pointnet2.py:693) with per-ball statistics -> max over the ball's ns rows.  Activations never leave

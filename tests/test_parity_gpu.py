@@ -472,6 +472,51 @@ def test_sa_mlp_tc_grouped_equals_materialised_rows(ops, ns, C, widths):
     assert float(out[:, :8].abs().sum()) == 0
 
 
+@pytest.mark.parametrize('ns,C,widths', [(16, 128, (64, 64, 128)), (32, 128, (64, 96, 128)), (32, 256, (128, 256, 256)),
+                                        (16, 512, (256, 256, 512))])
+def test_sa_mlp_tc_delayed_matches_reference_chain(ops, ns, C, widths):
+    """First per-ball layer taken before the gather (`caspr_sa_mlp_tc_delayed`: P = feat . W1[:, 3:]^T per source point,
+    then gather + xyz term + per-ball GroupNorm in one kernel) against the grouped chain in fp64 torch on the same
+    ball-query indices: ragged ball count, under-filled (padded) balls, strided feature view, output column slice."""
+    g = torch.Generator().manual_seed(ns + C)
+    B, N, M = 3, 700, 99
+    xyz = torch.rand(B, N, 3, generator=g).to(DEV)
+    _, new_xyz = ops.fps(xyz, M)
+    i16, i32 = ops.ball_query2(xyz, new_xyz, 0.15, 16, 0.25, 32)           # r = .15: a mix of full and under-filled balls
+    idx = i16 if ns == 16 else i32
+    wide = torch.randn(B, N, C + 4, generator=g).to(DEV)
+    feat = wide[:, :, 4:]
+    convs, norms = [], []
+    dims = [3 + C] + list(widths)
+    for i in range(3):
+        conv = torch.nn.Conv1d(dims[i], dims[i + 1], 1)
+        gn = torch.nn.GroupNorm(16, dims[i + 1])
+        with torch.no_grad():
+            gn.weight.copy_(torch.rand(dims[i + 1], generator=g) + 0.5)
+            gn.bias.copy_(0.2 * torch.randn(dims[i + 1], generator=g))
+        convs.append(conv.to(DEV))
+        norms.append(gn.to(DEV))
+    out = torch.zeros(B * M, widths[2] + 8, device=DEV)
+    ops.sa_mlp_tc_delayed(xyz, new_xyz, feat, idx, convs, norms, out[:, 4:4 + widths[2]])
+    rows = ops.group_points(xyz, new_xyz, feat, idx).double()
+    h = rows.view(B * M, ns, 3 + C).transpose(1, 2)
+    for i in range(3):
+        h = torch.nn.functional.conv1d(h, convs[i].weight.double(), convs[i].bias.double())
+        h = torch.nn.functional.group_norm(h, 16, norms[i].weight.double(), norms[i].bias.double(), eps=1e-5)
+        if i < 2:
+            h = h.relu()
+    ref = h.max(2)[0]
+    padded = torch.tensor([len(torch.unique(b)) < ns // 2 for b in idx.view(B * M, ns).cpu()])
+    # balls that are mostly copies of one point divide rounding noise by up to 1/sqrt(eps) = 316 in any fp32 evaluation
+    assert _rel(out[:, 4:4 + widths[2]], ref) < 2e-4
+    assert int((~padded).sum()) > 20
+    assert _rel(out[~padded, 4:4 + widths[2]], ref[~padded]) < 3e-5
+    assert float(out[:, :4].abs().sum()) == 0 and float(out[:, 4 + widths[2]:].abs().sum()) == 0
+    ref2 = torch.zeros(B * M, widths[2], device=DEV)
+    ops.sa_mlp_tc_grouped(xyz, new_xyz, feat, idx, convs, norms, ref2)
+    assert _rel(out[:, 4:4 + widths[2]], ref2) < 2e-4
+
+
 def test_augment_and_broadcast(ops):
     x, _ = synthetic_sequences(1, 2, 100, seed=0)
     x4 = x.view(-1, 4)
