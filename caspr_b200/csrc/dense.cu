@@ -523,11 +523,15 @@ groupnorm_apply_vec_kernel(float* __restrict__ X, int ldx, int rows_per_sample, 
     for (int k = 0; k < NQ; ++k) {
       const int qi = lane + 32 * k;
       if (qi < Q && r0 + warp < r1) {
+        // the running maximum only grows: a plain read that already shows a larger key makes the atomic unnecessary
+        // (1280 CTAs x 8 warps share each address at the head's shape; almost all of them lose)
         unsigned* o = maxout_ordered + (size_t)sample * ld_max + qi * 4;
-        atomicMax(o + 0, float_to_ordered(mx[k].x));
-        atomicMax(o + 1, float_to_ordered(mx[k].y));
-        atomicMax(o + 2, float_to_ordered(mx[k].z));
-        atomicMax(o + 3, float_to_ordered(mx[k].w));
+        const unsigned kx = float_to_ordered(mx[k].x), ky = float_to_ordered(mx[k].y),
+                       kz = float_to_ordered(mx[k].z), kw = float_to_ordered(mx[k].w);
+        if (kx > __ldcg(o + 0)) atomicMax(o + 0, kx);
+        if (ky > __ldcg(o + 1)) atomicMax(o + 1, ky);
+        if (kz > __ldcg(o + 2)) atomicMax(o + 2, kz);
+        if (kw > __ldcg(o + 3)) atomicMax(o + 3, kw);
       }
     }
   }
