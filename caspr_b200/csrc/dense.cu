@@ -462,33 +462,42 @@ groupnorm_apply_vec_kernel(float* __restrict__ X, int ldx, int rows_per_sample, 
   }
   __syncthreads();
   // per-quad scale / shift: v*sc + sh with sc = rstd*gamma, sh = beta - mean*rstd*gamma would change the
-  // rounding of (x - mean)*rstd*gamma + beta; keep the reference's operation order instead
-  float mu[NQ], rs[NQ];
+  // rounding of (x - mean)*rstd*gamma + beta; keep the reference's operation order instead.
+  // (mean, rstd) per channel quad sit in shared memory, not in per-lane arrays: the registers go to the row itself,
+  // whose NQ loads are all issued before the first one is consumed (the kernel is otherwise latency-bound: 1.1 TB/s
+  // with one load in flight per dependent chain).
+  __shared__ float2 s_quad[128 * 4];                              // Q <= 512
+  for (int qi = threadIdx.x; qi < Q; qi += 256) {
+    const int g = (qi * 4) / cpg;
+    s_quad[qi] = make_float2(s_mean[g], s_rstd[g]);
+  }
+  __syncthreads();
   float4 mx[NQ];
 #pragma unroll
-  for (int k = 0; k < NQ; ++k) {
-    const int qi = lane + 32 * k;
-    const int g = qi < Q ? (qi * 4) / cpg : 0;
-    mu[k] = s_mean[g];
-    rs[k] = s_rstd[g];
-    mx[k] = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f);
-  }
+  for (int k = 0; k < NQ; ++k) mx[k] = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f);
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
   const float4* w4 = reinterpret_cast<const float4*>(pj.W);
   for (int r = r0 + warp; r < r1; r += 8) {
     float4* row = reinterpret_cast<float4*>(base + (size_t)r * ldx);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 vv[NQ];
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) {
+      const int qi = lane + 32 * k;
+      vv[k] = qi < Q ? row[qi] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
     for (int k = 0; k < NQ; ++k) {
       const int qi = lane + 32 * k;
       if (qi < Q) {
-        float4 v = row[qi];
+        float4 v = vv[k];
+        const float2 mr = s_quad[qi];
         const float4 ga = __ldg(g4 + qi), be = __ldg(b4 + qi);
-        v.x = (v.x - mu[k]) * rs[k] * ga.x + be.x;
-        v.y = (v.y - mu[k]) * rs[k] * ga.y + be.y;
-        v.z = (v.z - mu[k]) * rs[k] * ga.z + be.z;
-        v.w = (v.w - mu[k]) * rs[k] * ga.w + be.w;
+        v.x = (v.x - mr.x) * mr.y * ga.x + be.x;
+        v.y = (v.y - mr.x) * mr.y * ga.y + be.y;
+        v.z = (v.z - mr.x) * mr.y * ga.z + be.z;
+        v.w = (v.w - mr.x) * mr.y * ga.w + be.w;
         if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
         if (write_back) row[qi] = v;
         mx[k].x = fmaxf(mx[k].x, v.x); mx[k].y = fmaxf(mx[k].y, v.y);

@@ -1123,10 +1123,13 @@ int sa_mlp_tc_impl(const float* X, int ldx, const GroupGather* gg, long long row
       cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
     return CASPR_ELAUNCH;
   if (delayed) {
-    const int blocks = (int)std::min<long long>((rows + 255) / 256, 148 * 8);
+    // a warp owns 32 rows; few rows (the coarse levels) get small CTAs so that every SM has work
+    const long long tiles = (rows + 31) / 32;
+    const int wpb = tiles >= 148 * 16 ? 8 : 2;
+    const int blocks = (int)std::min<long long>((tiles + wpb - 1) / wpb, 148 * 8);
     const size_t smem = (size_t)6 * C1 * sizeof(float);
 #define CASPR_SA_FIRST(CPG) \
-    sa_first_layer_kernel<CPG><<<blocks, 256, smem, s>>>(*gg, b1, g1, e1, eps, rows, C1, hi[1], lo[1], l.kpad[1], flag)
+    sa_first_layer_kernel<CPG><<<blocks, 32 * wpb, smem, s>>>(*gg, b1, g1, e1, eps, rows, C1, hi[1], lo[1], l.kpad[1], flag)
     CASPR_COUNT();
     if (C1 == 64) CASPR_SA_FIRST(4);
     else if (C1 == 128) CASPR_SA_FIRST(8);
