@@ -79,3 +79,33 @@ def test_training_gradient_layouts_match_parameter_order():
     assert lib.caspr_latent_ode_param_count(64, 512) == sum(p.numel() for p in lat)
     # shared module registered twice (latent_ode.ode_func / latent_ode.solver.ode_func): one set of Parameters
     assert len(list(model.latent_ode.parameters())) == 8
+
+
+def test_derived_weight_cache_follows_parameter_versions(lib_built):
+    """Matrices derived from a parameter (column subsets of the head's / set-abstraction first layers, ops.derived_weight)
+    are rebuilt when the parameter is modified in place (version counter) and after `invalidate_weight_cache()` (edits
+    through `.data`, which bypass the counter) - host logic only, no kernel runs."""
+    import torch
+    from caspr_b200 import ops
+    p = torch.nn.Parameter(torch.arange(12.0).view(3, 4))
+    calls = []
+
+    def tail(w):
+        calls.append(1)
+        return w[:, 2:]
+
+    a = ops.derived_weight(p, 'tail', tail)
+    assert a.is_contiguous() and torch.equal(a, p.detach()[:, 2:]) and len(calls) == 1
+    assert ops.derived_weight(p, 'tail', tail) is a and len(calls) == 1            # cached
+    with torch.no_grad():
+        p.mul_(2.0)                                                                # bumps the version
+    b = ops.derived_weight(p, 'tail', tail)
+    assert len(calls) == 2 and torch.equal(b, p.detach()[:, 2:])
+    p.data.add_(1.0)                                                               # does NOT bump the version
+    assert ops.derived_weight(p, 'tail', tail) is b
+    ops.invalidate_weight_cache()
+    c = ops.derived_weight(p, 'tail', tail)
+    assert len(calls) == 3 and torch.equal(c, p.detach()[:, 2:])
+    # a different tag on the same parameter is a different entry
+    d = ops.derived_weight(p, 'head', lambda w: w[:, :2])
+    assert torch.equal(d, p.detach()[:, :2]) and ops.derived_weight(p, 'tail', tail) is c
